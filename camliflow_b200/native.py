@@ -1,0 +1,72 @@
+"""ctypes binding of libcamli_b200.so -- the only doorway from Python to the kernels.
+
+There is deliberately NO fallback: if the library is missing or a call fails, a
+RuntimeError is raised.  PyTorch is used for device memory and streams only; the
+entry points receive raw device pointers, sizes and the current CUDA stream.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+from .build import LIB_PATH
+
+_HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "camli_b200.h")
+_lib = None
+
+ABI_VERSION = 1
+
+
+def declared_symbols(header_path=_HEADER):
+    """Names of every function include/camli_b200.h declares."""
+    text = open(header_path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(camli_\w+)\s*\(", text)))
+
+
+def lib():
+    """Load (once) and return the shared library; fail loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libcamli_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python -m camliflow_b200.build`; there is no CPU / PyTorch fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        handle.camli_strerror.restype = ctypes.c_char_p
+        handle.camli_strerror.argtypes = [ctypes.c_int]
+        if handle.camli_abi_version() != ABI_VERSION:
+            raise RuntimeError("libcamli_b200.so ABI %d != expected %d: rebuild the library"
+                               % (handle.camli_abi_version(), ABI_VERSION))
+        _lib = handle
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError("%s failed: %s (code %d)" % (what, lib().camli_strerror(code).decode(), code))
+
+
+def ptr(t):
+    """Device pointer of a tensor as a ctypes void* (None -> NULL)."""
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream():
+    """The current torch CUDA stream as a ctypes void*."""
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda_f32(t, name, contiguous=True):
+    """Argument checks with the reference's TORCH_CHECK wording (k_nearest_neighbor.cpp:6-12 etc.)."""
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be a float tensor" % name)
+    if contiguous and not t.is_contiguous():
+        raise RuntimeError("%s must be a contiguous tensor" % name)
+
+
+i32 = ctypes.c_int
+i64 = ctypes.c_int64
