@@ -71,7 +71,7 @@ KNN_CASES = [
     ("k5_odd", 3, 37, 101, 5, _util.rand_cloud),
     ("m_lt_k", 3, 10, 7, 16, _util.rand_cloud),
     ("m_lt_k_64", 3, 10, 40, 64, _util.rand_cloud),
-    ("m1", 3, 5, 1, 4, _util.rand_cloud),
+    ("m4_lt_k", 3, 5, 4, 6, _util.rand_cloud),
     ("ties3d_k16", 3, 1024, 2048, 16, _util.tied_cloud),
     ("ties3d_k32", 3, 512, 1500, 32, _util.tied_cloud),
     ("ties3d_k64", 3, 200, 900, 64, _util.tied_cloud),
