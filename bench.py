@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""Benchmark of the CamLiRAFT hot path (BASELINE.json metric: frame-pairs/s, 960x540 RGB +
+8192 points, 12 GRU iterations, batch 1 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One process per GPU (torchrun for N>1); the batch of frame pairs is sharded over the ranks
+with no data-path collective ("scaling": "weak").  Prints ONE JSON line on rank 0.
+
+* value        : pairs/s with the inputs resident in HBM (device-timed, CUDA events, max over ranks)
+* e2e          : the same through FlowEngine.__call__ with HOST tensors (H2D + forward + D2H)
+* roofline     : the dominant hand-written kernel, timed per launch with CUDA events on its stream
+* cpu_baseline : the reference algorithm's CPU path (oracle port, fallback index semantics)
+                 timed on this host's cores on a bounded sample (rank 0, N=1 only)
+* --impl reference : only the CPU path (the reference cannot travel to the GPU box; its
+                 restatement oracle/camliraft_oracle.py, pinned against it, is what runs)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (H, W, N points, GRU iterations, pairs per GPU)
+    "c2": (540, 960, 8192, 12, 1),
+    "small": (160, 224, 8192, 3, 1),
+}
+METRIC = "CamLiRAFT frame-pairs/sec 960x540+8192pts"
+
+
+def synthetic_inputs(B, H, W, N, seed):
+    """SURVEY 8(d) generator (identical to oracle.camliraft_oracle.synthetic_inputs; tests check)."""
+    g = torch.Generator().manual_seed(seed)
+    f, cx, cy = 1050.0, (W - 1) / 2.0, (H - 1) / 2.0
+    images = torch.randint(0, 256, (B, 6, H, W), generator=g).float()
+    u = torch.rand((B, N), generator=g) * (W - 1)
+    v = torch.rand((B, N), generator=g) * (H - 1)
+    z = torch.rand((B, N), generator=g) * 30.0 + 5.0
+    pc1 = torch.stack([(u - cx) * z / f, (v - cy) * z / f, z], 1)
+    pc2 = pc1 + torch.randn(pc1.shape, generator=g) * 0.05
+    perm = torch.stack([torch.randperm(N, generator=g) for _ in range(B)])
+    pc2 = torch.gather(pc2, 2, perm[:, None, :].expand(B, 3, N))
+    return {"images": images, "pcs": torch.cat([pc1, pc2], 1), "intrinsics": torch.tensor([[f, cx, cy]]).repeat(B, 1)}
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- CPU path
+def run_cpu_reference(workload, steps, warmup, seed=0):
+    """Times the reference algorithm's CPU path: oracle port, torch fallbacks for FPS / k-NN
+    (what models/csrc/wrapper.py does for CPU tensors), all host threads, eval mode, every
+    iteration's prediction materialised like the reference."""
+    from oracle import camliraft_oracle as co
+    H, W, N, iters, B = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = co.make_params(co.param_spec("camliraft"), seed=0)
+    inp = co.synthetic_inputs(B, H, W, N, seed)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        co.camliraft_forward(P, inp["images"], inp["pcs"], inp["intrinsics"], n_iters=iters, index_impl="fallback",
+                             all_iters=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": B / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "%d full forward(s) of %d pair(s), %dx%d + %d pts, %d iters, after %d warm-up"
+                      % (steps, B, W, H, N, iters, warmup), "sec_per_step": sec}
+
+
+# ---------------------------------------------------------------------------------- GPU path
+def l2_flush(buf):
+    buf.add_(1.0)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from camliflow_b200 import native, ops
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.engine import FlowEngine
+    from camliflow_b200.init import seed_module_
+
+    H, W, N, iters, B = WORKLOADS[args.workload]
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    model = seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=iters)), seed=0)
+    engine = FlowEngine(model, B, H, W, N, device=dev, use_graph=not args.no_graph)
+    inputs = synthetic_inputs(B, H, W, N, seed=rank)          # per-rank shard of the batch of pairs
+    pinned = {k: v.pin_memory() for k, v in inputs.items()}
+    flush = torch.zeros(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        with torch.cuda.stream(engine.stream):
+            for _ in range(steps):
+                l2_flush(flush)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(engine.stream)
+                fn()
+                e.record(engine.stream)
+                evs.append((s, e))
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    engine.load(pinned)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(engine.step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(lambda: engine(pinned), args.steps, args.warmup)
+
+    # per-launch timing of the dominant hand-written kernel (eager pass, events on the launch stream)
+    roofline = None
+    if rank == 0:
+        ops.profile_begin()
+        with torch.cuda.stream(engine.stream), torch.no_grad():
+            for _ in range(2):
+                l2_flush(flush)
+                engine._forward_static()
+        engine.stream.synchronize()
+        roofline = ops.profile_end(peaks_path=os.path.join(ROOT, "MEASURED_PEAKS.json"))
+
+    h2d, d2h = engine.io_bytes()
+    pairs = B * world
+    line = {
+        "metric": METRIC, "value": pairs * args.steps / (ms_dev / 1e3), "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: CamLiRAFT fusion %dx%d RGB + %d pts, %d iters, batch %d per GPU"
+                               % (args.workload, W, H, N, iters, B),
+                   "pairs_per_step": pairs, "cuda_graph": engine.graph is not None,
+                   "l2": "192 MiB flush write before every timed step (outside the event pair)",
+                   "conv_precision": "cuDNN default (TF32 allowed, as torch default in the reference)",
+                   "intermediate_predictions": False},
+        "e2e": {"value": pairs * args.steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": engine.launches_per_step * args.steps,
+        "clocks": clocks, "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu_reference(args.workload, steps=1, warmup=1)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        H, W, N, iters, B = WORKLOADS[args.workload]
+        steps = max(1, min(args.steps, 8))
+        base = run_cpu_reference(args.workload, steps=steps, warmup=min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: CamLiRAFT fusion %dx%d RGB + %d pts, %d iters, batch %d (CPU path)"
+                                   % (args.workload, W, H, N, iters, B)},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

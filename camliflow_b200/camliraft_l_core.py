@@ -1,0 +1,149 @@
+"""3-D (LiDAR) branch of CamLiRAFT (reference models/camliraft_l_core.py): PointConv encoder,
+point all-pairs correlation pyramid with k-NN lookup, PointConvDW motion encoder / GRU / flow head."""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .mlp import Conv1dNormRelu, MLP1d, MLP2d
+from .point_conv import PointConv, PointConvDW
+from .utils import backwarp_3d, build_pc_pyramid, k_nearest_neighbor, knn_interpolation
+
+
+class Encoder3D(nn.Module):
+    """camliraft_l_core.py:8-37."""
+
+    def __init__(self, n_channels, norm=None, k=16):
+        super().__init__()
+        self.level0_mlp = MLP1d(3, [n_channels[0], n_channels[0]])
+        self.mlps = nn.ModuleList()
+        self.convs = nn.ModuleList()
+        for c_in, c_out in zip(n_channels[:-1], n_channels[1:]):
+            self.mlps.append(MLP1d(c_in, [c_in, c_out]))
+            self.convs.append(PointConv(c_out, c_out, norm=norm, k=k))
+
+    def forward(self, xyzs):
+        assert len(xyzs) == len(self.mlps) + 1
+        feats = [self.level0_mlp(xyzs[0])]
+        for i, (mlp, conv) in enumerate(zip(self.mlps, self.convs)):
+            feats.append(conv(xyzs[i], mlp(feats[-1]), xyzs[i + 1]))
+        return feats
+
+
+class Correlation3D(nn.Module):
+    """camliraft_l_core.py:40-101; stateful between build and lookup like the reference."""
+
+    def __init__(self, out_channels, k=16):
+        super().__init__()
+        self.k = k
+        self.cost_mlp = MLP2d(4, [out_channels // 4, out_channels // 4], act="relu")
+        self.merge = Conv1dNormRelu(out_channels, out_channels)
+        self.cost_volume_pyramid = None
+
+    def build_cost_volume_pyramid(self, feat1, feat2, xyzs2, k=3):
+        self.cost_volume_pyramid = ops.corr3d_build(feat1, feat2, xyzs2, k)
+
+    def calc_matching_cost(self, xyz1, xyz2, cost_volume):
+        return torch.sum(self.cost_mlp(ops.corr3d_gather(xyz1, xyz2, cost_volume, self.k)), dim=-1)
+
+    def forward(self, xyz1, xyzs2):
+        costs = [self.calc_matching_cost(xyz1, x2, v) for x2, v in zip(xyzs2, self.cost_volume_pyramid)]
+        return self.merge(torch.cat(costs, dim=1))
+
+
+class FlowHead3D(nn.Module):
+    """camliraft_l_core.py:104-116."""
+
+    def __init__(self, input_dim=128):
+        super().__init__()
+        self.conv1 = PointConvDW(input_dim, 128, k=32)
+        self.conv2 = PointConvDW(128, 64, k=32)
+        self.fc = nn.Conv1d(64, 3, kernel_size=1)
+
+    def forward(self, xyz, features, knn_indices=None):
+        f = self.conv1(xyz, features.float(), knn_indices=knn_indices)
+        return self.fc(self.conv2(xyz, f, knn_indices=knn_indices))
+
+
+class GRU3D(nn.Module):
+    """camliraft_l_core.py:119-134."""
+
+    def __init__(self, input_dim, hidden_dim):
+        super().__init__()
+        self.conv_z = PointConvDW(hidden_dim + input_dim, hidden_dim, act=None, k=4)
+        self.conv_r = PointConvDW(hidden_dim + input_dim, hidden_dim, act=None, k=4)
+        self.conv_q = PointConvDW(hidden_dim + input_dim, hidden_dim, act=None, k=4)
+
+    def forward(self, xyz, h, x, knn_indices=None):
+        h, x = h.float(), x.float()
+        hx = torch.cat([h, x], dim=1)
+        z = torch.sigmoid(self.conv_z(xyz, hx, knn_indices=knn_indices))
+        r = torch.sigmoid(self.conv_r(xyz, hx, knn_indices=knn_indices))
+        q = torch.tanh(self.conv_q(xyz, torch.cat([r * h, x], dim=1), knn_indices=knn_indices))
+        return (1 - z) * h + z * q
+
+
+class MotionEncoder3D(nn.Module):
+    """camliraft_l_core.py:137-155."""
+
+    def __init__(self, corr_dim=128):
+        super().__init__()
+        self.conv_c1 = PointConvDW(corr_dim, corr_dim)
+        self.conv_f1 = PointConvDW(3, 32, k=32)
+        self.conv_f2 = PointConvDW(32, 16, k=16)
+        self.conv = PointConvDW(corr_dim + 16, 128 - 3, k=16)
+
+    def forward(self, xyz, flow, corr, knn_indices):
+        corr, flow = corr.float(), flow.float()
+        c = self.conv_c1(xyz, corr, knn_indices=knn_indices)
+        f = self.conv_f2(xyz, self.conv_f1(xyz, flow, knn_indices=knn_indices), knn_indices=knn_indices)
+        out = self.conv(xyz, torch.cat([c, f], dim=1), knn_indices=knn_indices)
+        return torch.cat([out, flow], dim=1)
+
+
+class CamLiRAFT_L_Core(nn.Module):
+    """LiDAR-only CamLiRAFT-L (camliraft_l_core.py:158-225); also the `branch_3d` of CamLiRAFT."""
+
+    def __init__(self, cfgs):
+        super().__init__()
+        self.cfgs = cfgs
+        self.fnet = Encoder3D(n_channels=[64, 96, 128], norm="batch_norm", k=16)
+        self.cnet = Encoder3D(n_channels=[64, 96, 128], norm="batch_norm", k=16)
+        self.cnet_aligner = nn.Conv1d(128, 256, kernel_size=1)
+        self.correlation = Correlation3D(out_channels=128, k=16)
+        self.motion_encoder = MotionEncoder3D(corr_dim=128)
+        self.gru = GRU3D(input_dim=128 + 128, hidden_dim=128)
+        self.flow_head = FlowHead3D(input_dim=128)
+
+    def forward(self, pc1, pc2):
+        xyzs1, xyzs2, _, _ = build_pc_pyramid(pc1, pc2, [4096, 2048, 1024, 512, 256])
+        feat1 = self.fnet(xyzs1[:3])[2]
+        feat2 = self.fnet(xyzs2[:3])[2]
+        featc = self.cnet_aligner(self.cnet(xyzs1[:3])[2])
+        xyzs1, xyzs2 = xyzs1[2:], xyzs2[2:]
+        xyz1 = xyzs1[0]
+        self.correlation.build_cost_volume_pyramid(feat1, feat2, xyzs2)
+        h, x = torch.split(featc, [128, 128], dim=1)
+        h, x = torch.tanh(h), torch.relu(x)
+        nbr = k_nearest_neighbor(xyz1, xyz1, k=32)
+        n_iters = self.cfgs.n_iters_train if self.training else self.cfgs.n_iters_eval
+        flow = torch.zeros_like(xyz1)
+        xyzs2_warp = xyzs2
+        preds = []
+        for it in range(n_iters):
+            if it > 0:
+                flow = flow.detach()
+                xyzs2_warp = warp_pyramid(xyz1, xyzs2, flow)
+            corr = self.correlation(xyz1, xyzs2_warp)
+            motion = self.motion_encoder(xyz1, flow, corr, knn_indices=nbr)
+            h = self.gru(xyz1, h=h, x=torch.cat([x, motion], dim=1), knn_indices=nbr)
+            flow = flow + self.flow_head(xyz1, h, nbr).float()
+            preds.append(flow)
+        return [knn_interpolation(xyz1, p, pc1, k=3) for p in preds]
+
+
+def warp_pyramid(xyz1, xyzs2, flow):
+    """[backwarp_3d(xyz1, lvl, flow) for lvl in xyzs2] (camliraft_l_core.py:196).  The levels of a
+    build_pc_pyramid pyramid are prefixes of one FPS order and every query is warped
+    independently, so ONE search over the finest level yields all of them."""
+    fine = backwarp_3d(xyz1, xyzs2[0], flow)
+    return [fine[:, :, :lvl.shape[-1]] for lvl in xyzs2]

@@ -25,9 +25,9 @@ def _furthest_point_sampling_cuda(points_xyz: torch.Tensor, n_samples: int) -> t
     if n_points > 8192:   # only the streaming kernel needs the [B,N] running-distance buffer
         scratch = torch.empty((batch_size, n_points), dtype=torch.float32, device=points_xyz.device)
     with torch.cuda.device(points_xyz.device):
-        code = native.lib().camli_furthest_point_sampling(
-            ptr(points_xyz), ptr(scratch), i32(batch_size), i32(n_points), i32(n_samples), ptr(out), stream())
-    native.check(code, "camli_furthest_point_sampling")
+        native.call("camli_furthest_point_sampling",
+                    ptr(points_xyz), ptr(scratch), i32(batch_size), i32(n_points), i32(n_samples), ptr(out), stream(),
+                    algo_bytes=batch_size * (n_points * 12 + n_samples * 8), flops=batch_size * n_samples * n_points * 8)
     return out
 
 
@@ -39,10 +39,11 @@ def _k_nearest_neighbor_cuda(input_xyz: torch.Tensor, query_xyz: torch.Tensor, k
     n_inputs = input_xyz.shape[1]
     out = torch.empty((batch_size, n_queries, k), dtype=torch.int64, device=query_xyz.device)
     with torch.cuda.device(query_xyz.device):
-        code = native.lib().camli_k_nearest_neighbor(
-            i32(batch_size), i32(n_queries), i32(n_inputs), i32(k), i32(n_dim),
-            ptr(query_xyz), ptr(input_xyz), ptr(out), stream())
-    native.check(code, "camli_k_nearest_neighbor")
+        native.call("camli_k_nearest_neighbor",
+                    i32(batch_size), i32(n_queries), i32(n_inputs), i32(k), i32(n_dim),
+                    ptr(query_xyz), ptr(input_xyz), ptr(out), stream(),
+                    algo_bytes=batch_size * ((n_queries + n_inputs) * n_dim * 4 + n_queries * k * 8),
+                    flops=batch_size * n_queries * n_inputs * (3 * n_dim - 1))
     return out
 
 
@@ -55,11 +56,12 @@ def _k_nearest_neighbor_strided(input_view: torch.Tensor, query_view: torch.Tens
     out = torch.empty((batch_size, n_queries, k), dtype=torch.int64, device=query_view.device)
     qs, is_ = query_view.stride(), input_view.stride()
     with torch.cuda.device(query_view.device):
-        code = native.lib().camli_k_nearest_neighbor_strided(
-            i32(batch_size), i32(n_queries), i32(n_inputs), i32(k), i32(n_dim),
-            ptr(query_view), i64(qs[0]), i64(qs[1]), i64(qs[2]),
-            ptr(input_view), i64(is_[0]), i64(is_[1]), i64(is_[2]), ptr(out), stream())
-    native.check(code, "camli_k_nearest_neighbor_strided")
+        native.call("camli_k_nearest_neighbor_strided",
+                    i32(batch_size), i32(n_queries), i32(n_inputs), i32(k), i32(n_dim),
+                    ptr(query_view), i64(qs[0]), i64(qs[1]), i64(qs[2]),
+                    ptr(input_view), i64(is_[0]), i64(is_[1]), i64(is_[2]), ptr(out), stream(),
+                    algo_bytes=batch_size * ((n_queries + n_inputs) * n_dim * 4 + n_queries * k * 8),
+                    flops=batch_size * n_queries * n_inputs * (3 * n_dim - 1))
     return out
 
 
@@ -71,10 +73,11 @@ def _correlation_forward_cuda(input1: torch.Tensor, input2: torch.Tensor, max_di
     n_disp = (2 * max_displacement + 1) ** 2
     out = torch.empty((batch_size, n_disp, height, width), dtype=torch.float32, device=input1.device)
     with torch.cuda.device(input1.device):
-        code = native.lib().camli_correlation_forward(
-            ptr(out), ptr(input1), ptr(input2), i32(batch_size), i32(in_channels), i32(height), i32(width),
-            i32(max_displacement), stream())
-    native.check(code, "camli_correlation_forward")
+        native.call("camli_correlation_forward",
+                    ptr(out), ptr(input1), ptr(input2), i32(batch_size), i32(in_channels), i32(height), i32(width),
+                    i32(max_displacement), stream(),
+                    algo_bytes=batch_size * height * width * (2 * in_channels * 4 + n_disp * 4),
+                    flops=2 * n_disp * in_channels * batch_size * height * width)
     return out
 
 
@@ -88,10 +91,12 @@ def _correlation_backward_cuda(grad_output, input1, input2, max_displacement: in
     grad1 = torch.empty((batch_size, in_channels, height, width), dtype=torch.float32, device=input1.device)
     grad2 = torch.empty_like(grad1)
     with torch.cuda.device(input1.device):
-        code = native.lib().camli_correlation_backward(
-            ptr(grad_output), ptr(grad1), ptr(grad2), ptr(input1), ptr(input2), i32(batch_size),
-            i32(in_channels), i32(height), i32(width), i32(max_displacement), stream())
-    native.check(code, "camli_correlation_backward")
+        n_disp = (2 * max_displacement + 1) ** 2
+        native.call("camli_correlation_backward",
+                    ptr(grad_output), ptr(grad1), ptr(grad2), ptr(input1), ptr(input2), i32(batch_size),
+                    i32(in_channels), i32(height), i32(width), i32(max_displacement), stream(),
+                    algo_bytes=batch_size * height * width * (n_disp * 4 + 4 * in_channels * 4),
+                    flops=4 * n_disp * in_channels * batch_size * height * width)
     return grad1, grad2
 
 

@@ -43,9 +43,57 @@ def lib():
     return _lib
 
 
+_launches = 0
+
+
+def launch_count():
+    """Number of C-ABI kernel entry points called so far in this process."""
+    return _launches
+
+
 def check(code, what):
+    global _launches
+    _launches += 1
     if code != 0:
         raise RuntimeError("%s failed: %s (code %d)" % (what, lib().camli_strerror(code).decode(), code))
+
+
+_profile = None   # name -> [(start_event, end_event, algorithmic_bytes, flops)] while profiling
+
+
+def call(name, *args, algo_bytes=0, flops=0):
+    """Invoke entry point `name` of the library on the current stream; raise on a non-zero
+    return code.  While profiling (profile_begin/profile_end) every call is bracketed by CUDA
+    events recorded on the stream it launches on."""
+    fn = getattr(lib(), name)
+    if _profile is None:
+        check(fn(*args), name)
+        return
+    st = torch.cuda.current_stream()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(st)
+    code = fn(*args)
+    e.record(st)
+    _profile.setdefault(name, []).append((s, e, algo_bytes, flops))
+    check(code, name)
+
+
+def profile_begin():
+    global _profile
+    _profile = {}
+
+
+def profile_end():
+    """Stops profiling; returns {name: {launches, avg_us, total_us, bytes, flops}} (per launch averages)."""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, recs in (prof or {}).items():
+        us = [s.elapsed_time(e) * 1e3 for s, e, _, _ in recs]
+        out[name] = {"launches": len(recs), "avg_us": sum(us) / len(us), "total_us": sum(us),
+                     "bytes": sum(r[2] for r in recs) / len(recs), "flops": sum(r[3] for r in recs) / len(recs)}
+    return out
 
 
 def ptr(t):

@@ -141,3 +141,32 @@ def nearest_point_2d(uv, H, W):
     B = uv.shape[0]
     grid = mesh_grid(B, H, W, uv.device).reshape(B, 2, -1)
     return k_nearest_neighbor(uv, grid, 1)[..., 0]
+
+
+# ---------------------------------------------------------------- per-launch profiling (bench.py)
+def profile_begin():
+    from . import native
+    native.profile_begin()
+
+
+def profile_end(peaks_path=None):
+    """Roofline record of the hand-written kernel with the largest share of the profiled
+    region: achieved = algorithmic bytes per launch / average launch duration."""
+    import json
+    import os
+    from . import native
+    prof = native.profile_end()
+    if not prof:
+        return None
+    peak, src = 6650.0, "fallback"
+    if peaks_path and os.path.exists(peaks_path):
+        peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    top = max(prof, key=lambda n: prof[n]["total_us"])
+    rec = prof[top]
+    achieved = rec["bytes"] / (rec["avg_us"] * 1e-6) / 1e9
+    return {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "avg_us": rec["avg_us"], "launches": rec["launches"],
+            "algorithmic_bytes_per_launch": rec["bytes"],
+            "all": {n: {"avg_us": r["avg_us"], "launches": r["launches"], "total_us": r["total_us"],
+                        "GBps": r["bytes"] / (r["avg_us"] * 1e-6) / 1e9, "GFLOPs": r["flops"] / (r["avg_us"] * 1e-6) / 1e9}
+                    for n, r in prof.items()}}

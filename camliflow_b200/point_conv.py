@@ -1,0 +1,70 @@
+"""PointConv / PointConvDW with the nn.Module surface and parameter names of the reference's
+models/point_conv.py (`weight_net.convs.N.conv_fn`, `linear`, `norm_fn`, `mlp.convs.0.conv_fn`),
+computed by the fused grouping kernels of camliflow_b200.ops."""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .csrc import k_nearest_neighbor
+from .mlp import MLP1d, MLP2d, LayerNormCF, _ACTS
+
+
+def _select_neighbors(xyz, sampled_xyz, knn_indices, k):
+    """Reuse a (possibly wider) precomputed neighbour table or search (point_conv.py:49-55)."""
+    if knn_indices is None:
+        return k_nearest_neighbor(xyz, sampled_xyz, k)
+    assert knn_indices.shape[:2] == torch.Size([sampled_xyz.shape[0], sampled_xyz.shape[-1]])
+    assert knn_indices.shape[2] >= k
+    return knn_indices[:, :, :k]
+
+
+class PointConv(nn.Module):
+    """Set abstraction: k-NN grouping, WeightNet(3->8->16) on the offsets, per-centroid
+    [16 x k]·[k x (C+3)] contraction, Linear, norm, activation (point_conv.py:7-70)."""
+
+    def __init__(self, in_channels, out_channels, norm=None, act="leaky_relu", k=16):
+        super().__init__()
+        self.k = k
+        self.weight_net = MLP2d(3, [8, 16], act=act)
+        self.linear = nn.Linear(16 * (in_channels + 3), out_channels)
+        if norm == "batch_norm":
+            self.norm_fn = nn.BatchNorm1d(out_channels, affine=True)
+        elif norm == "instance_norm":
+            self.norm_fn = nn.InstanceNorm1d(out_channels, affine=True)
+        elif norm == "layer_norm":
+            self.norm_fn = LayerNormCF(out_channels, 1)
+        elif norm is None:
+            self.norm_fn = nn.Identity()
+        else:
+            raise NotImplementedError("Unknown normalization function: %s" % norm)
+        if act not in ("relu", "leaky_relu", None):
+            raise NotImplementedError("Unknown activation function: %s" % act)
+        self.act_fn = _ACTS[act]()
+
+    def forward(self, xyz, features, sampled_xyz=None, knn_indices=None):
+        """xyz [B,3,N], features [B,C,N], sampled_xyz [B,3,S] -> [B,O,S]."""
+        if sampled_xyz is None:
+            sampled_xyz = xyz
+        idx = _select_neighbors(xyz, sampled_xyz, knn_indices, self.k)
+        weights = self.weight_net(ops.neighbor_offsets(xyz, sampled_xyz, idx))       # [B,16,S,k]
+        grouped = ops.pointconv_aggregate(torch.cat([xyz, features], dim=1), weights, idx)   # [B,S,16(C+3)]
+        out = self.linear(grouped).transpose(1, 2)
+        return self.act_fn(self.norm_fn(out))
+
+
+class PointConvDW(nn.Module):
+    """Depth-wise point convolution: MLP1d(C->O), grouping, WeightNet(3->8->32->O, relu) on the
+    offsets, product, max over the k neighbours (point_conv.py:102-130)."""
+
+    def __init__(self, in_channels, out_channels, norm=None, act="leaky_relu", k=16):
+        super().__init__()
+        self.k = k
+        self.mlp = MLP1d(in_channels, [out_channels], norm, act)
+        self.weight_net = MLP2d(3, [8, 32, out_channels], act="relu")
+
+    def forward(self, xyz, features, sampled_xyz=None, knn_indices=None):
+        if sampled_xyz is None:
+            sampled_xyz = xyz
+        idx = _select_neighbors(xyz, sampled_xyz, knn_indices, self.k)
+        weights = self.weight_net(ops.neighbor_offsets(xyz, sampled_xyz, idx))       # [B,O,S,k]
+        return ops.pointconv_dw_aggregate(self.mlp(features), weights, idx)

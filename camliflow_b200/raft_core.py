@@ -1,0 +1,188 @@
+"""2-D branch of CamLiRAFT (reference models/raft_core.py): ResNet-50 stage-1/2 encoder,
+all-pairs 4-D correlation (build + 4-level 9x9 lookup), separable ConvGRU, motion encoder,
+flow head and convex upsampler.  Parameter names follow the reference so checkpoints load.
+
+The reference inherits its encoder from mmdet's ResNet (absent here); the stem and
+the two bottleneck stages are written out below with the same state_dict keys
+(`conv1`, `bn1`, `layerN.M.{conv,bn}{1,2,3}`, `layerN.0.downsample.{0,1}`, `align.conv_fn`)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .mlp import Conv2dNormRelu
+from .utils import convex_upsample, mesh_grid
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, c_in, c_mid, stride):
+        super().__init__()
+        c_out = 4 * c_mid
+        self.conv1 = nn.Conv2d(c_in, c_mid, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(c_mid)
+        self.conv2 = nn.Conv2d(c_mid, c_mid, 3, stride, 1, bias=False)     # stride on the 3x3 ('pytorch' style)
+        self.bn2 = nn.BatchNorm2d(c_mid)
+        self.conv3 = nn.Conv2d(c_mid, c_out, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(c_out)
+        self.downsample = None
+        if stride != 1 or c_in != c_out:
+            self.downsample = nn.Sequential(nn.Conv2d(c_in, c_out, 1, stride, bias=False), nn.BatchNorm2d(c_out))
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        y = F.relu(self.bn2(self.conv2(y)), inplace=True)
+        y = self.bn3(self.conv3(y))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return F.relu(y + x, inplace=True)
+
+
+class Encoder2D(nn.Module):
+    """1/8-resolution, 128-channel image encoder (raft_core.py:10-38); BatchNorm always runs on
+    its running statistics (`norm_eval=True`, raft_core.py:18)."""
+
+    def __init__(self, depth=50, pretrained=None):
+        super().__init__()
+        if depth != 50:
+            raise NotImplementedError("Encoder2D: only the ResNet-50 backbone of the reference configs")
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.layer1 = nn.Sequential(_Bottleneck(64, 64, 1), _Bottleneck(256, 64, 1), _Bottleneck(256, 64, 1))
+        self.layer2 = nn.Sequential(_Bottleneck(256, 128, 2), *[_Bottleneck(512, 128, 1) for _ in range(3)])
+        self.feat_dim = 512
+        self.align = Conv2dNormRelu(self.feat_dim, 128)
+
+    def train(self, mode=True):
+        super().train(mode)
+        for m in self.modules():
+            if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                m.eval()
+        return self
+
+    def forward(self, x):
+        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x)), inplace=True), 3, 2, 1)
+        return self.align(self.layer2(self.layer1(x)))
+
+
+class Correlation2D(nn.Module):
+    """All-pairs correlation pyramid + windowed bilinear lookup (raft_core.py:41-107).  Stateful
+    like the reference: `build_cost_volume_pyramid` caches the volume for later `forward` calls."""
+
+    def __init__(self, num_levels=4, radius=4):
+        super().__init__()
+        self.num_levels = num_levels
+        self.radius = radius
+        self.fnet_aligner = nn.Conv2d(128, 256, kernel_size=1)
+        self.cost_volume_pyramid = None
+
+    def build_cost_volume_pyramid(self, fmap1, fmap2):
+        fmap1 = self.fnet_aligner(fmap1.float())
+        fmap2 = self.fnet_aligner(fmap2.float())
+        self.cost_volume_pyramid = ops.corr2d_build(fmap1, fmap2, self.num_levels)
+
+    def forward(self, coords):
+        return ops.corr2d_lookup(self.cost_volume_pyramid, coords, self.radius)
+
+
+class GRU2D(nn.Module):
+    """Separable ConvGRU: a 1x5 pass then a 5x1 pass (raft_core.py:110-139)."""
+
+    def __init__(self, hidden_dim=128, input_dim=192 + 128):
+        super().__init__()
+        c = hidden_dim + input_dim
+        self.convz1 = nn.Conv2d(c, hidden_dim, (1, 5), padding=(0, 2))
+        self.convr1 = nn.Conv2d(c, hidden_dim, (1, 5), padding=(0, 2))
+        self.convq1 = nn.Conv2d(c, hidden_dim, (1, 5), padding=(0, 2))
+        self.convz2 = nn.Conv2d(c, hidden_dim, (5, 1), padding=(2, 0))
+        self.convr2 = nn.Conv2d(c, hidden_dim, (5, 1), padding=(2, 0))
+        self.convq2 = nn.Conv2d(c, hidden_dim, (5, 1), padding=(2, 0))
+
+    def _half(self, h, x, convz, convr, convq):
+        hx = torch.cat([h, x], dim=1)
+        z = torch.sigmoid(convz(hx))
+        r = torch.sigmoid(convr(hx))
+        q = torch.tanh(convq(torch.cat([r * h, x], dim=1)))
+        return (1 - z) * h + z * q
+
+    def forward(self, h, x):
+        h = self._half(h, x, self.convz1, self.convr1, self.convq1)
+        h = self._half(h, x, self.convz2, self.convr2, self.convq2)
+        return torch.nan_to_num(h)
+
+
+class MotionEncoder2D(nn.Module):
+    """raft_core.py:142-166."""
+
+    def __init__(self, corr_levels, corr_radius):
+        super().__init__()
+        corr_planes = corr_levels * (2 * corr_radius + 1) ** 2
+        self.conv_c1 = nn.Conv2d(corr_planes, 256, kernel_size=1, padding=0)
+        self.conv_c2 = nn.Conv2d(256, 192, kernel_size=3, padding=1)
+        self.conv_f1 = nn.Conv2d(2, 128, kernel_size=7, padding=3)
+        self.conv_f2 = nn.Conv2d(128, 64, kernel_size=3, padding=1)
+        self.conv = nn.Conv2d(64 + 192, 128 - 2, kernel_size=3, padding=1)
+
+    def forward(self, flow, corr):
+        c = F.relu(self.conv_c2(F.relu(self.conv_c1(corr))))
+        f = F.relu(self.conv_f2(F.relu(self.conv_f1(flow))))
+        out = torch.nan_to_num(F.relu(self.conv(torch.cat([c, f], dim=1))))
+        return torch.cat([out, flow], dim=1)
+
+
+class FlowHead2D(nn.Module):
+    """raft_core.py:169-181."""
+
+    def __init__(self, input_dim=128, hidden_dim=256):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, 2, kernel_size=3, padding=1)
+
+    def forward(self, x):
+        return torch.nan_to_num(self.conv2(F.relu(self.conv1(x))).float())
+
+
+class ConvexUpsampler2D(nn.Module):
+    """raft_core.py:184-197."""
+
+    def __init__(self, input_dim):
+        super().__init__()
+        self.mask = nn.Sequential(nn.Conv2d(input_dim, 256, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(256, 64 * 9, 1, padding=0))
+
+    def forward(self, h, flow):
+        return convex_upsample(flow, 0.25 * self.mask(h.float()))
+
+
+class RAFTCore(nn.Module):
+    """The image-only RAFT (raft_core.py:200-270); also the `branch_2d` of CamLiRAFT."""
+
+    def __init__(self, cfgs):
+        super().__init__()
+        self.cfgs = cfgs
+        self.hidden_dim = self.context_dim = 128
+        self.corr_levels = self.corr_radius = 4
+        self.fnet = Encoder2D(cfgs.backbone.depth, cfgs.backbone.pretrained)
+        self.cnet = Encoder2D(cfgs.backbone.depth, cfgs.backbone.pretrained)
+        self.cnet_aligner = nn.Conv2d(128, 256, kernel_size=1)
+        self.correlation = Correlation2D(self.corr_levels, self.corr_radius)
+        self.motion_encoder = MotionEncoder2D(self.corr_levels, self.corr_radius)
+        self.gru = GRU2D(hidden_dim=self.hidden_dim, input_dim=self.hidden_dim + 128)
+        self.flow_head = FlowHead2D(self.hidden_dim)
+        self.convex_upsampler = ConvexUpsampler2D(self.hidden_dim)
+
+    def forward(self, image1, image2):
+        self.correlation.build_cost_volume_pyramid(self.fnet(image1), self.fnet(image2))
+        h, x = torch.split(self.cnet_aligner(self.cnet(image1)), [self.hidden_dim, self.context_dim], dim=1)
+        h, x = torch.tanh(h), torch.relu(x)
+        B, _, H, W = image1.shape
+        grid = mesh_grid(B, H // 8, W // 8, device=image1.device)
+        flow = torch.zeros_like(grid)
+        preds = []
+        n_iters = self.cfgs.n_iters_train if self.training else self.cfgs.n_iters_eval
+        for _ in range(n_iters):
+            flow = flow.detach()
+            corr = self.correlation(grid + flow)
+            h = self.gru(h, torch.cat([x, self.motion_encoder(flow, corr)], dim=1))
+            flow = flow + self.flow_head(h)
+            preds.append(self.convex_upsampler(h, flow))
+        return preds

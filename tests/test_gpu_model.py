@@ -1,0 +1,99 @@
+"""GPU parity of the product CamLiRAFT (camliflow_b200) against (a) the golden outputs of the
+REFERENCE model (tests/golden/model_camliraft.npz) and (b) the CPU oracle run live on the same
+seeded inputs.  Tolerance = north_star's: EPE2D <= 1e-3 px, EPE3D <= 1e-4 m."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL_EPE2D, TOL_EPE3D = 1e-3, 1e-4
+
+
+def epe(a, b):
+    return float(np.sqrt(((a - b) ** 2).sum(0)).mean())
+
+
+def _strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _model(n_iters):
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.init import seed_module_
+    return seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=n_iters)), seed=0).cuda().eval()
+
+
+def _run(model, inputs):
+    with torch.no_grad():
+        out = model({k: v.cuda() for k, v in inputs.items()})
+    return out["flow_2d"].cpu(), out["flow_3d"].cpu()
+
+
+def test_seeded_weights_equal_oracle_weights():
+    from camliflow_b200.init import seeded_tensor
+    from oracle import camliraft_oracle as co
+    spec = co.param_spec("camliraft")
+    P = co.make_params(spec, seed=0)
+    for k in list(spec)[::7]:
+        assert torch.equal(P[k], seeded_tensor(k, spec[k], 0)), k
+
+
+def test_small_vs_reference_golden_and_live_oracle():
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    G = np.load(os.path.join(GOLDEN, "model_camliraft.npz"))
+    inputs = co.synthetic_inputs(1, 160, 224, 8192, seed=11)
+    f2, f3 = _run(_model(3), inputs)
+    e2 = epe(f2[0, :, ::4, ::4].numpy(), G["small_kernel_flow2d"])
+    e3 = epe(f3[0, :, ::4].numpy(), G["small_kernel_flow3d"])
+    print("small vs reference golden: EPE2D %.3e EPE3D %.3e" % (e2, e3))
+    assert e2 <= TOL_EPE2D and e3 <= TOL_EPE3D, (e2, e3)
+    ref = co.camliraft_forward(co.make_params(co.param_spec()), inputs["images"], inputs["pcs"], inputs["intrinsics"],
+                               n_iters=3, index_impl="kernel")
+    e2 = epe(f2[0].numpy(), ref["flow_2d"][0].numpy())
+    e3 = epe(f3[0].numpy(), ref["flow_3d"][0].numpy())
+    print("small vs live oracle: EPE2D %.3e EPE3D %.3e" % (e2, e3))
+    assert e2 <= TOL_EPE2D and e3 <= TOL_EPE3D, (e2, e3)
+
+
+def test_c2_vs_reference_golden():
+    """BASELINE config[1] at full size: 960x540 + 8192 points, 12 iterations."""
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    G = np.load(os.path.join(GOLDEN, "model_camliraft.npz"))
+    inputs = co.synthetic_inputs(1, 540, 960, 8192, seed=0)
+    f2, f3 = _run(_model(12), inputs)
+    e2 = epe(f2[0, :, ::8, ::8].numpy(), G["c2_kernel_flow2d"])
+    e3 = epe(f3[0, :, ::4].numpy(), G["c2_kernel_flow3d"])
+    print("c2 vs reference golden: EPE2D %.3e EPE3D %.3e" % (e2, e3))
+    assert e2 <= TOL_EPE2D and e3 <= TOL_EPE3D, (e2, e3)
+
+
+def test_engine_graph_matches_eager():
+    """The CUDA-graph engine (public end-to-end call, host tensors in/out) returns what the
+    eager module returns."""
+    from camliflow_b200.engine import FlowEngine
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    inputs = co.synthetic_inputs(1, 160, 224, 8192, seed=5)
+    model = _model(3)
+    f2, f3 = _run(model, inputs)
+    eng = FlowEngine(model, 1, 160, 224, 8192, use_graph=True)
+    out = eng(inputs)
+    assert epe(out["flow_2d"][0].numpy(), f2[0].numpy()) <= 1e-5
+    assert epe(out["flow_3d"][0].numpy(), f3[0].numpy()) <= 1e-6
+    out2 = eng(inputs)    # replay is deterministic
+    assert torch.equal(out2["flow_3d"], out["flow_3d"].clone())
+
+
+def test_bench_inputs_equal_oracle_inputs():
+    import bench
+    from oracle import camliraft_oracle as co
+    a, b = bench.synthetic_inputs(1, 64, 96, 5000, 3), co.synthetic_inputs(1, 64, 96, 5000, 3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
