@@ -2,6 +2,9 @@
 schedules the two branches and the CLFM fusion sites around the hot loop."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
 
 from .camliraft_l_core import CamLiRAFT_L_Core, warp_pyramid
 from .clfm import CLFM
@@ -50,19 +53,24 @@ class CamLiRAFT_Core(nn.Module):
         uv1 = torch.stack([uv1[:, 0] * sx, uv1[:, 1] * sy], dim=1)
         uv2 = torch.stack([uv2[:, 0] * sx, uv2[:, 1] * sy], dim=1)
 
+        # channel-last point features from here on; pixel -> nearest projected point tables are
+        # computed once per cloud (the reference repeats the search at every fusion site and iteration)
+        feat1_3d, feat2_3d, featc_3d = ops.rows_of(feat1_3d), ops.rows_of(feat2_3d), ops.rows_of(featc_3d)
+        nn1 = ops.nearest_point_2d(uv1, fh, fw)
         if cfgs.fuse_fnet:
-            feat1_2d, feat1_3d = self.clfm_fnet(uv1, feat1_2d, feat1_3d)
-            feat2_2d, feat2_3d = self.clfm_fnet(uv2, feat2_2d, feat2_3d)
+            nn2 = ops.nearest_point_2d(uv2, fh, fw)
+            feat1_2d, feat1_3d = self.clfm_fnet.forward_rows(uv1, feat1_2d, feat1_3d, nn1)
+            feat2_2d, feat2_3d = self.clfm_fnet.forward_rows(uv2, feat2_2d, feat2_3d, nn2)
         if cfgs.fuse_cnet:
-            featc_2d, featc_3d = self.clfm_cnet(uv1, featc_2d, featc_3d)
+            featc_2d, featc_3d = self.clfm_cnet.forward_rows(uv1, featc_2d, featc_3d, nn1)
 
         h_2d, x_2d = torch.split(b2.cnet_aligner(featc_2d), [128, 128], dim=1)
         h_2d, x_2d = torch.tanh(h_2d), torch.relu(x_2d)
-        h_3d, x_3d = torch.split(b3.cnet_aligner(featc_3d), [128, 128], dim=1)
-        h_3d, x_3d = torch.tanh(h_3d), torch.relu(x_3d)
+        hx_3d = F.linear(featc_3d, b3.cnet_aligner.weight.flatten(1), b3.cnet_aligner.bias)
+        h_3d, x_3d = torch.tanh(hx_3d[..., :128]), torch.relu(hx_3d[..., 128:])
 
         b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
-        b3.correlation.build_cost_volume_pyramid(feat1_3d, feat2_3d, xyzs2)
+        b3.correlation.build_cost_volume_pyramid(ops.cf_of(feat1_3d), ops.cf_of(feat2_3d), xyzs2)
         nbr = k_nearest_neighbor(xyz1, xyz1, k=32)
 
         n_iters = cfgs.n_iters_train if self.training else cfgs.n_iters_eval
@@ -72,6 +80,7 @@ class CamLiRAFT_Core(nn.Module):
         flow_2d = torch.zeros_like(grid)
         flow_3d = torch.zeros_like(xyz1)
         xyzs2_warp = xyzs2
+        dw_cache = {}                  # iteration-invariant WeightNet outputs of the PointConvDW layers
         preds_2d, preds_3d = [], []
         for it in range(n_iters):
             if it > 0:
@@ -79,22 +88,22 @@ class CamLiRAFT_Core(nn.Module):
                 xyzs2_warp = warp_pyramid(xyz1, xyzs2, flow_3d)
 
             corr_2d = b2.correlation(grid + flow_2d)
-            corr_3d = b3.correlation(xyz1, xyzs2_warp)
+            corr_3d = b3.correlation.forward_rows(xyz1, xyzs2_warp)
             if cfgs.fuse_corr:
-                corr_2d, corr_3d = self.clfm_corr(uv1, corr_2d, corr_3d)
+                corr_2d, corr_3d = self.clfm_corr.forward_rows(uv1, corr_2d, corr_3d, nn1)
 
             motion_2d = b2.motion_encoder(flow_2d, corr_2d)
-            motion_3d = b3.motion_encoder(xyz1, flow_3d, corr_3d, knn_indices=nbr)
+            motion_3d = b3.motion_encoder.forward_rows(xyz1, ops.rows_of(flow_3d), corr_3d, nbr, dw_cache)
             if cfgs.fuse_motion:
-                motion_2d, motion_3d = self.clfm_motion(uv1, motion_2d, motion_3d)
+                motion_2d, motion_3d = self.clfm_motion.forward_rows(uv1, motion_2d, motion_3d, nn1)
 
             h_2d = b2.gru(h=h_2d, x=torch.cat([x_2d, motion_2d], dim=1))
-            h_3d = b3.gru(xyz1, h=h_3d, x=torch.cat([x_3d, motion_3d], dim=1), knn_indices=nbr)
+            h_3d = b3.gru.forward_rows(xyz1, h_3d, torch.cat([x_3d, motion_3d], dim=-1), nbr, dw_cache)
             if cfgs.fuse_hidden:
-                h_2d, h_3d = self.clfm_hidden(uv1, h_2d, h_3d)
+                h_2d, h_3d = self.clfm_hidden.forward_rows(uv1, h_2d, h_3d, nn1)
 
             flow_2d = flow_2d + b2.flow_head(h_2d)
-            flow_3d = flow_3d + b3.flow_head(xyz1, h_3d, nbr)
+            flow_3d = flow_3d + ops.cf_of(b3.flow_head.forward_rows(xyz1, h_3d, nbr, dw_cache))
             if every or it == n_iters - 1:
                 preds_2d.append(b2.convex_upsampler(h_2d, flow_2d))
                 preds_3d.append(knn_interpolation(xyz1, flow_3d, pc1, k=3))

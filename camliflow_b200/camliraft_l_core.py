@@ -2,6 +2,7 @@
 point all-pairs correlation pyramid with k-NN lookup, PointConvDW motion encoder / GRU / flow head."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from .mlp import Conv1dNormRelu, MLP1d, MLP2d
@@ -42,12 +43,18 @@ class Correlation3D(nn.Module):
     def build_cost_volume_pyramid(self, feat1, feat2, xyzs2, k=3):
         self.cost_volume_pyramid = ops.corr3d_build(feat1, feat2, xyzs2, k)
 
-    def calc_matching_cost(self, xyz1, xyz2, cost_volume):
-        return torch.sum(self.cost_mlp(ops.corr3d_gather(xyz1, xyz2, cost_volume, self.k)), dim=-1)
-
     def forward(self, xyz1, xyzs2):
-        costs = [self.calc_matching_cost(xyz1, x2, v) for x2, v in zip(xyzs2, self.cost_volume_pyramid)]
-        return self.merge(torch.cat(costs, dim=1))
+        """xyz1 [B,3,n1], xyzs2: the (warped) pyramid of the second cloud -> [B,128,n1]."""
+        return ops.cf_of(self.forward_rows(xyz1, xyzs2))
+
+    def forward_rows(self, xyz1, xyzs2):
+        """One launch for the 4 x (k-NN + gather + cost MLP + sum over k), then the merge GEMM."""
+        if self.k != 16:
+            raise NotImplementedError("Correlation3D: the fused lookup is built for k=16 (all reference configs)")
+        (w1, b1), (w2, b2) = self.cost_mlp.convs[0].folded(), self.cost_mlp.convs[1].folded()
+        costs = ops.corr3d_lookup_rows(xyz1, xyzs2, self.cost_volume_pyramid, w1.contiguous(), b1.contiguous(),
+                                       w2.contiguous(), b2.contiguous())
+        return self.merge.forward_rows(costs)
 
 
 class FlowHead3D(nn.Module):
@@ -59,9 +66,13 @@ class FlowHead3D(nn.Module):
         self.conv2 = PointConvDW(128, 64, k=32)
         self.fc = nn.Conv1d(64, 3, kernel_size=1)
 
-    def forward(self, xyz, features, knn_indices=None):
-        f = self.conv1(xyz, features.float(), knn_indices=knn_indices)
-        return self.fc(self.conv2(xyz, f, knn_indices=knn_indices))
+    def forward(self, xyz, features, knn_indices=None, cache=None):
+        return ops.cf_of(self.forward_rows(xyz, ops.rows_of(features.float()), knn_indices, cache))
+
+    def forward_rows(self, xyz, feat_rows, knn_indices=None, cache=None):
+        f = self.conv1.forward_rows(xyz, feat_rows, knn_indices=knn_indices, cache=cache)
+        f = self.conv2.forward_rows(xyz, f, knn_indices=knn_indices, cache=cache)
+        return F.linear(f, self.fc.weight.flatten(1), self.fc.bias)
 
 
 class GRU3D(nn.Module):
@@ -73,12 +84,15 @@ class GRU3D(nn.Module):
         self.conv_r = PointConvDW(hidden_dim + input_dim, hidden_dim, act=None, k=4)
         self.conv_q = PointConvDW(hidden_dim + input_dim, hidden_dim, act=None, k=4)
 
-    def forward(self, xyz, h, x, knn_indices=None):
-        h, x = h.float(), x.float()
-        hx = torch.cat([h, x], dim=1)
-        z = torch.sigmoid(self.conv_z(xyz, hx, knn_indices=knn_indices))
-        r = torch.sigmoid(self.conv_r(xyz, hx, knn_indices=knn_indices))
-        q = torch.tanh(self.conv_q(xyz, torch.cat([r * h, x], dim=1), knn_indices=knn_indices))
+    def forward(self, xyz, h, x, knn_indices=None, cache=None):
+        return ops.cf_of(self.forward_rows(xyz, ops.rows_of(h.float()), ops.rows_of(x.float()), knn_indices, cache))
+
+    def forward_rows(self, xyz, h, x, knn_indices=None, cache=None):
+        kw = dict(knn_indices=knn_indices, cache=cache)
+        hx = torch.cat([h, x], dim=-1)
+        z = torch.sigmoid(self.conv_z.forward_rows(xyz, hx, **kw))
+        r = torch.sigmoid(self.conv_r.forward_rows(xyz, hx, **kw))
+        q = torch.tanh(self.conv_q.forward_rows(xyz, torch.cat([r * h, x], dim=-1), **kw))
         return (1 - z) * h + z * q
 
 
@@ -92,12 +106,15 @@ class MotionEncoder3D(nn.Module):
         self.conv_f2 = PointConvDW(32, 16, k=16)
         self.conv = PointConvDW(corr_dim + 16, 128 - 3, k=16)
 
-    def forward(self, xyz, flow, corr, knn_indices):
-        corr, flow = corr.float(), flow.float()
-        c = self.conv_c1(xyz, corr, knn_indices=knn_indices)
-        f = self.conv_f2(xyz, self.conv_f1(xyz, flow, knn_indices=knn_indices), knn_indices=knn_indices)
-        out = self.conv(xyz, torch.cat([c, f], dim=1), knn_indices=knn_indices)
-        return torch.cat([out, flow], dim=1)
+    def forward(self, xyz, flow, corr, knn_indices, cache=None):
+        return ops.cf_of(self.forward_rows(xyz, ops.rows_of(flow.float()), ops.rows_of(corr.float()), knn_indices, cache))
+
+    def forward_rows(self, xyz, flow, corr, knn_indices, cache=None):
+        kw = dict(knn_indices=knn_indices, cache=cache)
+        c = self.conv_c1.forward_rows(xyz, corr, **kw)
+        f = self.conv_f2.forward_rows(xyz, self.conv_f1.forward_rows(xyz, flow, **kw), **kw)
+        out = self.conv.forward_rows(xyz, torch.cat([c, f], dim=-1), **kw)
+        return torch.cat([out, flow], dim=-1)
 
 
 class CamLiRAFT_L_Core(nn.Module):
@@ -128,15 +145,17 @@ class CamLiRAFT_L_Core(nn.Module):
         n_iters = self.cfgs.n_iters_train if self.training else self.cfgs.n_iters_eval
         flow = torch.zeros_like(xyz1)
         xyzs2_warp = xyzs2
+        h, x = ops.rows_of(h), ops.rows_of(x)
+        cache = {}                     # iteration-invariant WeightNet outputs of the PointConvDW layers
         preds = []
         for it in range(n_iters):
             if it > 0:
                 flow = flow.detach()
                 xyzs2_warp = warp_pyramid(xyz1, xyzs2, flow)
-            corr = self.correlation(xyz1, xyzs2_warp)
-            motion = self.motion_encoder(xyz1, flow, corr, knn_indices=nbr)
-            h = self.gru(xyz1, h=h, x=torch.cat([x, motion], dim=1), knn_indices=nbr)
-            flow = flow + self.flow_head(xyz1, h, nbr).float()
+            corr = self.correlation.forward_rows(xyz1, xyzs2_warp)
+            motion = self.motion_encoder.forward_rows(xyz1, ops.rows_of(flow), corr, nbr, cache)
+            h = self.gru.forward_rows(xyz1, h, torch.cat([x, motion], dim=-1), nbr, cache)
+            flow = flow + ops.cf_of(self.flow_head.forward_rows(xyz1, h, nbr, cache))
             preds.append(flow)
         return [knn_interpolation(xyz1, p, pc1, k=3) for p in preds]
 
@@ -145,5 +164,7 @@ def warp_pyramid(xyz1, xyzs2, flow):
     """[backwarp_3d(xyz1, lvl, flow) for lvl in xyzs2] (camliraft_l_core.py:196).  The levels of a
     build_pc_pyramid pyramid are prefixes of one FPS order and every query is warped
     independently, so ONE search over the finest level yields all of them."""
+    for coarse in xyzs2[1:]:
+        assert coarse.shape[-1] <= xyzs2[0].shape[-1]
     fine = backwarp_3d(xyz1, xyzs2[0], flow)
     return [fine[:, :, :lvl.shape[-1]] for lvl in xyzs2]

@@ -7,7 +7,6 @@ import torch.nn as nn
 
 from . import ops
 from .mlp import Conv1dNormRelu, Conv2dNormRelu
-from .utils import grid_sample_wrapper, mesh_grid
 
 
 class FusionAwareInterp(nn.Module):
@@ -21,15 +20,17 @@ class FusionAwareInterp(nn.Module):
         self.out_conv = Conv2dNormRelu(n_channels_3d, n_channels_3d, norm=norm)
         self.score_net = nn.Sequential(Conv2dNormRelu(3, 16), Conv2dNormRelu(16, n_channels_3d, act="sigmoid"))
 
-    def forward(self, uv, feat_2d, feat_3d):
-        B, _, H, W = feat_2d.shape
-        nn_idx = ops.nearest_point_2d(uv, H, W)                                   # [B,HW]
-        grid = mesh_grid(B, H, W, uv.device).reshape(B, 2, -1)
-        off = ops.gather_points(uv, nn_idx) - grid                                # [B,2,HW]
-        score_in = torch.cat([off, torch.linalg.norm(off, dim=1, keepdim=True)], dim=1)
-        score = self.score_net(score_in.view(B, 3, H, W))
-        final = score * ops.gather_points(feat_3d, nn_idx).view(B, -1, H, W)
-        return self.out_conv(final)
+    def forward(self, uv, feat_2d, feat_3d, nn_idx=None):
+        return self.forward_rows(uv, feat_2d.shape[-2:], ops.rows_of(feat_3d), nn_idx)
+
+    def forward_rows(self, uv, hw, feat3d_rows, nn_idx=None):
+        """feat3d_rows [B,N,C] -> [B,C,H,W] (NHWC storage).  `nn_idx` [B,HW]: the pixel -> nearest
+        projected point table; it only depends on (uv, H, W), so callers looping over fusion
+        sites / GRU iterations compute it once."""
+        H, W = hw
+        if nn_idx is None:
+            nn_idx = ops.nearest_point_2d(uv, H, W)
+        return self.out_conv(ops.clfm_interp(uv, nn_idx, feat3d_rows, self.score_net, H, W))
 
 
 class SKFusion(nn.Module):
@@ -49,13 +50,22 @@ class SKFusion(nn.Module):
                                     nn.ReLU(inplace=True))
         self.fc_out = nn.Sequential(nn.Linear(out_channels // reduction, out_channels * 2, bias=False), nn.Sigmoid())
 
+    def _blend_weights(self, pooled):
+        B, C = pooled.shape
+        return torch.softmax(self.fc_out(self.fc_mid(pooled)).view(B, C, 2), dim=-1)
+
     def forward(self, feat_2d, feat_3d):
         a, b = self.align1(feat_2d), self.align2(feat_3d)
         B, C = a.shape[:2]
-        pooled = (a + b).flatten(2).mean(-1)
-        w = torch.softmax(self.fc_out(self.fc_mid(pooled)).view(B, C, 2), dim=-1)
+        w = self._blend_weights((a + b).flatten(2).mean(-1))
         shape = (B, C) + (1,) * (a.dim() - 2)
         return a * w[..., 0].reshape(shape) + b * w[..., 1].reshape(shape)
+
+    def forward_rows(self, rows_2d, rows_3d):
+        """'ncm' variant on channel-last point features [B,N,C]."""
+        a, b = self.align1.forward_rows(rows_2d), self.align2.forward_rows(rows_3d)
+        w = self._blend_weights((a + b).mean(1))
+        return a * w[:, None, :, 0] + b * w[:, None, :, 1]
 
 
 class CLFM(nn.Module):
@@ -70,10 +80,16 @@ class CLFM(nn.Module):
         self.fuse2d = SKFusion(in_channels_2d, in_channels_3d, in_channels_2d, "nchw", norm, reduction=2)
         self.fuse3d = SKFusion(in_channels_2d, in_channels_3d, in_channels_3d, "ncm", norm, reduction=2)
 
-    def forward(self, uv, feat_2d, feat_3d):
-        feat_2d, feat_3d = feat_2d.float(), feat_3d.float()
-        interp = self.interp(uv, feat_2d.detach(), feat_3d.detach())
+    def forward(self, uv, feat_2d, feat_3d, nn_idx=None):
+        """uv [B,2,N], feat_2d [B,C2,H,W], feat_3d [B,C3,N] -> (out2d [B,C2,H,W], out3d [B,C3,N])."""
+        out2d, out3d_rows = self.forward_rows(uv, feat_2d, ops.rows_of(feat_3d.float()), nn_idx)
+        return out2d, ops.cf_of(out3d_rows)
+
+    def forward_rows(self, uv, feat_2d, feat3d_rows, nn_idx=None):
+        """Same with channel-last point features in and out."""
+        feat_2d = feat_2d.float()
+        interp = self.interp.forward_rows(uv, feat_2d.shape[-2:], feat3d_rows.detach(), nn_idx)
         out2d = self.fuse2d(feat_2d, interp)
-        sampled = grid_sample_wrapper(feat_2d.detach(), uv)
-        out3d = self.fuse3d(self.mlps3d(sampled.detach()), feat_3d)
+        sampled = ops.bilinear_sample_rows(feat_2d.detach(), uv)
+        out3d = self.fuse3d.forward_rows(self.mlps3d.forward_rows(sampled), feat3d_rows)
         return out2d, out3d

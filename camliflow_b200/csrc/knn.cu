@@ -13,25 +13,12 @@
 // reference's rule literally (skip if d > worst; place after all entries <= d,
 // scanning down from j = min(idx, k-1); the last entry is dropped), so results
 // are bit-identical, including on exact distance ties.
-#include "common.cuh"
+#include "knn_search.cuh"
 
 namespace {
 
 constexpr int KNN_WARPS_PER_CTA = 8;
-constexpr float KNN_INIT_DIST = 1e9f;   // k_nearest_neighbor_kernel.cu:72
 
-// Element strides of a [B, points, D] view: lets the same kernel read the
-// reference's channel-last [B,N,D] layout and the models' channel-first [B,D,N]
-// tensors without the transpose+contiguous copy wrapper.py:119-122 performs.
-struct KnnView { long long sb, sp, sd; };
-
-template <int D>
-__device__ __forceinline__ float knn_dist(const float* __restrict__ p, long long sd, float ux, float uy, float uz) {
-    if (D == 3) return camli_sqdist3(ux - __ldg(p), uy - __ldg(p + sd), uz - __ldg(p + 2 * sd));
-    return camli_sqdist2(ux - __ldg(p), uy - __ldg(p + sd));
-}
-
-// SLOTS = 1 handles k <= 32, SLOTS = 2 handles k <= 64.
 template <int D, int SLOTS>
 __global__ void __launch_bounds__(KNN_WARPS_PER_CTA * 32)
 knn_warp_kernel(int n, int m, int k, const float* __restrict__ query_all, KnnView qv,
@@ -41,60 +28,13 @@ knn_warp_kernel(int n, int m, int k, const float* __restrict__ query_all, KnnVie
     if (q >= n) return;   // whole warp leaves together
     const int b = blockIdx.y;
     const float* __restrict__ qp = query_all + b * qv.sb + q * qv.sp;
-    const float* __restrict__ input = input_all + b * iv.sb;
     int64_t* __restrict__ out = idx_all + ((size_t)b * n + q) * k;
-
     const float ux = __ldg(qp), uy = __ldg(qp + qv.sd), uz = (D == 3) ? __ldg(qp + 2 * qv.sd) : 0.f;
 
-    // entry e = lane (slot 0) and e = 32 + lane (slot 1)
-    float hd0 = KNN_INIT_DIST, hd1 = KNN_INIT_DIST;
-    int hi0 = 0, hi1 = 0;
-    float worst = KNN_INIT_DIST;          // distance held by entry k-1
-    const int last = k - 1;
-
-    // software prefetch of the next 32 candidates
-    float d_next = 0.f;
-    if (lane < m) d_next = knn_dist<D>(input + lane * iv.sp, iv.sd, ux, uy, uz);
-
-    for (int base = 0; base < m; base += 32) {
-        const float d = d_next;
-        const int nxt = base + 32 + lane;
-        if (nxt < m) d_next = knn_dist<D>(input + nxt * iv.sp, iv.sd, ux, uy, uz);
-
-        const bool cand = (base + lane < m) && !(d > worst);
-        unsigned pending = __ballot_sync(CAMLI_FULL_MASK, cand);
-        while (pending) {
-            const int src = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const float cd = __shfl_sync(CAMLI_FULL_MASK, d, src);
-            if (cd > worst) continue;                       // list tightened since the ballot
-            const int ci = base + src;
-            const int limit = min(ci, last);                // reference: j = min(idx, k-1)
-            // p = number of entries e < limit with dist <= cd  (list is sorted)
-            int p = __popc(__ballot_sync(CAMLI_FULL_MASK, lane < limit && hd0 <= cd));
-            if (SLOTS == 2)
-                p += __popc(__ballot_sync(CAMLI_FULL_MASK, lane + 32 < limit && hd1 <= cd));
-            // entries p < e <= limit take entry e-1, entry p takes the candidate
-            const float up_d0 = __shfl_up_sync(CAMLI_FULL_MASK, hd0, 1);
-            const int up_i0 = __shfl_up_sync(CAMLI_FULL_MASK, hi0, 1);
-            if (SLOTS == 2) {
-                float up_d1 = __shfl_up_sync(CAMLI_FULL_MASK, hd1, 1);
-                int up_i1 = __shfl_up_sync(CAMLI_FULL_MASK, hi1, 1);
-                const float wrap_d = __shfl_sync(CAMLI_FULL_MASK, hd0, 31);
-                const int wrap_i = __shfl_sync(CAMLI_FULL_MASK, hi0, 31);
-                if (lane == 0) { up_d1 = wrap_d; up_i1 = wrap_i; }
-                const int e1 = lane + 32;
-                if (e1 > p && e1 <= limit) { hd1 = up_d1; hi1 = up_i1; }
-                else if (e1 == p) { hd1 = cd; hi1 = ci; }
-            }
-            if (lane > p && lane <= limit) { hd0 = up_d0; hi0 = up_i0; }
-            else if (lane == p) { hd0 = cd; hi0 = ci; }
-            worst = (SLOTS == 2 && last >= 32) ? __shfl_sync(CAMLI_FULL_MASK, hd1, last - 32)
-                                               : __shfl_sync(CAMLI_FULL_MASK, hd0, last);
-        }
-    }
-    if (lane < k) out[lane] = (int64_t)hi0;
-    if (SLOTS == 2 && lane + 32 < k) out[lane + 32] = (int64_t)hi1;
+    const KnnPlainPoints<D> pts{input_all + b * iv.sb, iv.sp, iv.sd};
+    const KnnList r = knn_warp_search<SLOTS>(pts, m, k, ux, uy, uz);
+    if (lane < k) out[lane] = (int64_t)r.i0;
+    if (SLOTS == 2 && lane + 32 < k) out[lane + 32] = (int64_t)r.i1;
 }
 
 template <int D>

@@ -64,6 +64,15 @@ class _ConvNormAct(nn.Module):
     def forward(self, x):
         return self.act_fn(self.norm_fn(self.conv_fn(x)))
 
+    def forward_rows(self, x):
+        """Channel-last evaluation of a 1x1 layer: x [..., C_in] -> [..., C_out] (one GEMM + epilogue)."""
+        n = self.norm_fn
+        foldable = isinstance(n, nn.Identity) or (isinstance(n, nn.modules.batchnorm._BatchNorm) and not n.training)
+        if not foldable or self.conv_fn.weight[0, 0].numel() != 1:     # training-mode norm or a real kernel window
+            return self.forward(x.movedim(-1, 1)).movedim(1, -1)
+        w, b = self.folded()
+        return self.act_fn(torch.nn.functional.linear(x, w, b))
+
     def folded(self):
         """(weight [O,I], bias [O]) of the 1x1 convolution with an eval-mode BatchNorm folded in."""
         w = self.conv_fn.weight.flatten(1)
@@ -97,6 +106,11 @@ class _MLP(nn.Module):
     def forward(self, x):
         for layer in self.convs:
             x = layer(x)
+        return x
+
+    def forward_rows(self, x):
+        for layer in self.convs:
+            x = layer.forward_rows(x)
         return x
 
 

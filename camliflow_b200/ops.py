@@ -1,24 +1,69 @@
 """Fused hot-path operators (host side).  Every function here is the doorway to one kernel
-(family) of libcamli_b200.so; tensors keep the reference's logical layouts at this boundary
-([B,C,N] point features, [B,C,H,W] maps) so the callers read like the reference's cores.
+(family) of libcamli_b200.so (include/camli_b200.h).  Two layouts are used:
 
-There is no CPU path: all functions require CUDA tensors and a built library.
+  * "cf"   -- the reference's channel-first logical layout ([B,C,N] point features, [B,3,N]
+              coordinates, [B,C,H,W] maps) at the module boundaries;
+  * "rows" -- channel-last storage ([B,N,C]; NHWC for maps) inside the fused paths, so that a
+              neighbour's feature vector is one contiguous, coalesced read.
+
+There is no CPU path and no eager-PyTorch fallback: CUDA tensors and a built library are
+required.  Forward only for now: calling these with tensors that require grad raises.
 """
+import ctypes
+
 import torch
 import torch.nn.functional as F
 
+from . import native
 from .csrc import k_nearest_neighbor
+from .native import i32, i64, ptr, stream
 
 
 def _need_cuda(*tensors):
     for t in tensors:
         if not t.is_cuda:
             raise RuntimeError("camliflow_b200.ops: CUDA tensors required (there is no CPU fallback)")
+        if t.is_floating_point() and t.dtype != torch.float32:
+            raise RuntimeError("camliflow_b200.ops: float32 tensors required, got %s" % t.dtype)
+
+
+def _no_grad(name, *tensors):
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise NotImplementedError("camliflow_b200.ops.%s has no backward yet: run under torch.no_grad()" % name)
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _int_array(values, ctype=ctypes.c_int):
+    return (ctype * len(values))(*values)
+
+
+def rows_of(x_cf):
+    """[B,C,N] (any strides) -> contiguous [B,N,C]; free when x_cf is already a transposed view of rows."""
+    t = x_cf.transpose(1, 2)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def cf_of(rows):
+    """[B,N,C] rows -> logical [B,C,N] view."""
+    return rows.transpose(1, 2)
+
+
+def nhwc_rows(x):
+    """[B,C,H,W] (any strides) -> contiguous NHWC storage viewed as [B,H,W,C]."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw_view(rows_bhwc):
+    """NHWC storage [B,H,W,C] -> logical [B,C,H,W] (channels_last strides)."""
+    return rows_bhwc.permute(0, 3, 1, 2)
 
 
 # ---------------------------------------------------------------- grouping / interpolation
 def gather_points(data, idx):
-    """data [B,C,N], idx [B,...] (i64) -> [B,C,...]: models/utils.py:62-80."""
+    """data [B,C,N], idx [B,...] (i64) -> [B,C,...]: models/utils.py:62-80 (one-off uses only)."""
     _need_cuda(data, idx)
     B, C = data.shape[:2]
     flat = idx.reshape(B, 1, -1).expand(B, C, -1)
@@ -26,31 +71,65 @@ def gather_points(data, idx):
 
 
 def knn_interpolate(input_xyz, input_feat, query_xyz, k=3):
-    """models/utils.py:130-146."""
+    """Three-NN inverse-distance interpolation fused with the search (models/utils.py:130-146).
+    input_xyz [B,3,m], input_feat [B,F,m], query_xyz [B,3,n] -> [B,F,n]."""
     _need_cuda(input_xyz, input_feat, query_xyz)
-    idx = k_nearest_neighbor(input_xyz, query_xyz, k)
-    d = torch.linalg.norm(gather_points(input_xyz, idx) - query_xyz[..., None], dim=1).clamp(1e-8)
-    w = 1.0 / d
-    w = w / torch.sum(w, -1, keepdim=True)
-    return torch.sum(gather_points(input_feat, idx) * w[:, None], -1)
+    _no_grad("knn_interpolate", input_xyz, input_feat, query_xyz)
+    B, Fc, m = input_feat.shape
+    n = query_xyz.shape[-1]
+    out = torch.empty((B, Fc, n), dtype=torch.float32, device=input_feat.device)
+    qs, xs, fs, os_ = query_xyz.stride(), input_xyz.stride(), input_feat.stride(), out.stride()
+    with torch.cuda.device(out.device):
+        native.call("camli_three_nn_interpolate", i32(B), i32(n), i32(m), i32(k), i32(Fc),
+                    ptr(query_xyz), i64(qs[0]), i64(qs[2]), i64(qs[1]),
+                    ptr(input_xyz), i64(xs[0]), i64(xs[2]), i64(xs[1]),
+                    ptr(input_feat), i64(fs[0]), i64(fs[1]), i64(fs[2]),
+                    ptr(out), i64(os_[0]), i64(os_[1]), i64(os_[2]), stream(),
+                    algo_bytes=B * ((n + m) * 12 + n * k * (Fc * 4 + 12) + n * Fc * 4), flops=B * n * m * 8)
+    return out
+
+
+def backwarp_3d(xyz1, xyz2, flow12, k=3):
+    """xyz2 + interp(xyz1 + flow12, -flow12)(xyz2) in one kernel (models/utils.py:149-159)."""
+    _need_cuda(xyz1, xyz2, flow12)
+    _no_grad("backwarp_3d", xyz1, xyz2, flow12)
+    xyz1, xyz2, flow12 = xyz1.contiguous(), xyz2.contiguous(), flow12.contiguous()
+    B, _, m = xyz1.shape
+    n = xyz2.shape[-1]
+    out = torch.empty_like(xyz2)
+    with torch.cuda.device(out.device):
+        native.call("camli_backwarp_3d", i32(B), i32(n), i32(m), i32(k), ptr(xyz1), ptr(flow12), ptr(xyz2), ptr(out),
+                    stream(), algo_bytes=B * (m * 24 + n * 24), flops=B * n * m * 11)
+    return out
 
 
 # ---------------------------------------------------------------- image-side sampling
-def bilinear_sample(feat2d, uv):
-    """feat2d [B,C,H,W], uv [B,2,N] pixel coords -> [B,C,N] (align_corners, zero padding)."""
+def bilinear_sample_rows(feat2d, uv):
+    """feat2d [B,C,H,W] (channels_last preferred), uv [B,2,N] pixel coords -> rows [B,N,C]
+    (align_corners, zero padding; models/utils.py:262-269)."""
     _need_cuda(feat2d, uv)
-    H, W = feat2d.shape[2:]
-    gx = 2.0 * uv[:, 0] / (W - 1) - 1.0
-    gy = 2.0 * uv[:, 1] / (H - 1) - 1.0
-    g = torch.stack([gx, gy], -1)[:, :, None, :]
-    return F.grid_sample(feat2d, g, "bilinear", align_corners=True)[..., 0]
+    _no_grad("bilinear_sample", feat2d, uv)
+    B, C, H, W = feat2d.shape
+    N = uv.shape[-1]
+    src = nhwc_rows(feat2d)
+    uv = uv.contiguous()
+    out = torch.empty((B, N, C), dtype=torch.float32, device=feat2d.device)
+    with torch.cuda.device(out.device):
+        native.call("camli_bilinear_sample_rows", i32(B), i32(H), i32(W), i32(N), i32(C), ptr(src), ptr(uv), ptr(out),
+                    i64(C), stream(), algo_bytes=B * N * (5 * C * 4 + 8))
+    return out
+
+
+def bilinear_sample(feat2d, uv):
+    """Channel-first result [B,C,N] of bilinear_sample_rows."""
+    return cf_of(bilinear_sample_rows(feat2d, uv))
 
 
 def convex_upsample(flow, mask, s=8):
-    """models/utils.py:191-204."""
+    """models/utils.py:191-204 (once per forward at inference)."""
     _need_cuda(flow, mask)
     B, _, H, W = flow.shape
-    mask = torch.softmax(mask.float().view(B, 1, 9, s, s, H, W), 2)
+    mask = torch.softmax(mask.float().reshape(B, 1, 9, s, s, H, W), 2)
     up = F.unfold(flow.float() * s, [3, 3], padding=1).view(B, 2, 9, 1, 1, H, W)
     up = torch.sum(mask * up, 2).permute(0, 1, 4, 2, 5, 3)
     return up.reshape(B, 2, H * s, W * s)
@@ -58,59 +137,89 @@ def convex_upsample(flow, mask, s=8):
 
 # ---------------------------------------------------------------- RAFT all-pairs correlation
 def corr2d_build(fmap1, fmap2, num_levels):
-    """All-pairs volume of two [B,C,H,W] maps scaled by 1/sqrt(C) plus its 2x2 average-pooled
-    pyramid over the (h2,w2) axes: models/raft_core.py:56-68.  Returns a list of [B,H*W,H_l,W_l]."""
+    """All-pairs volume of two [B,C,H,W] maps scaled by 1/sqrt(C) and its 2x2 average-pooled pyramid
+    (models/raft_core.py:56-68).  Returns [B,H*W,h_l,w_l] per level; the coarser levels come from one
+    fused pass over level 0."""
     _need_cuda(fmap1, fmap2)
+    _no_grad("corr2d_build", fmap1, fmap2)
     B, C, H, W = fmap1.shape
-    vol = torch.matmul(fmap1.view(B, C, H * W).transpose(1, 2), fmap2.view(B, C, H * W))
-    vol = (vol / torch.sqrt(torch.tensor(float(C)))).reshape(B * H * W, 1, H, W)
+    a = nhwc_rows(fmap1).view(B, H * W, C)
+    b = nhwc_rows(fmap2).view(B, H * W, C)
+    vol = torch.bmm(a * (1.0 / C ** 0.5), b.transpose(1, 2)).view(B, H * W, H, W)
     pyr = [vol]
+    h, w = H, W
     for _ in range(num_levels - 1):
-        vol = F.avg_pool2d(vol, 2, stride=2)
-        pyr.append(vol)
-    return [v.view(B, H * W, v.shape[-2], v.shape[-1]) for v in pyr]
+        h, w = h // 2, w // 2
+        pyr.append(torch.empty((B, H * W, h, w), dtype=torch.float32, device=vol.device))
+    if num_levels > 1:
+        with torch.cuda.device(vol.device):
+            native.call("camli_corr2d_pool_pyramid", ptr(vol), _ptr_array(pyr[1:]), i32(num_levels), i64(B * H * W),
+                        i32(H), i32(W), stream(),
+                        algo_bytes=sum(v.numel() for v in pyr) * 4)
+    return pyr
 
 
-def corr2d_lookup(pyramid, coords, radius):
-    """models/raft_core.py:71-107: coords [B,2,H,W] -> [B, L*(2r+1)^2, H, W]; window index i moves x,
-    j moves y (the reference's meshgrid quirk)."""
-    _need_cuda(coords)
-    r = radius
-    coords = coords.permute(0, 2, 3, 1).float()
-    B, H, W, _ = coords.shape
-    d = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
-    delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), -1).view(1, 2 * r + 1, 2 * r + 1, 2)
-    out = []
-    for i, vol in enumerate(pyramid):
-        h, w = vol.shape[-2:]
-        c = coords.reshape(B * H * W, 1, 1, 2) / 2 ** i + delta
-        g = torch.cat([2 * c[..., 0:1] / (w - 1) - 1, 2 * c[..., 1:2] / (h - 1) - 1], -1)
-        s = F.grid_sample(vol.reshape(B * H * W, 1, h, w), g, align_corners=True)
-        out.append(s.view(B, H, W, -1))
-    return torch.cat(out, -1).permute(0, 3, 1, 2).contiguous()
+def corr2d_lookup(pyramid, coords, radius, channels_last=True):
+    """models/raft_core.py:71-107: coords [B,2,H,W] -> logical [B, L*(2r+1)^2, H, W] (NHWC storage when
+    channels_last); window index i moves x, j moves y (the reference's meshgrid quirk)."""
+    _need_cuda(coords, *pyramid)
+    _no_grad("corr2d_lookup", coords, *pyramid)
+    coords = coords.float().contiguous()
+    B, _, H, W = coords.shape
+    L, n_ch = len(pyramid), len(pyramid) * (2 * radius + 1) ** 2
+    if channels_last:
+        store = torch.empty((B, H, W, n_ch), dtype=torch.float32, device=coords.device)
+        out = nchw_view(store)
+    else:
+        store = out = torch.empty((B, n_ch, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        native.call("camli_corr2d_lookup", _ptr_array(pyramid), _int_array([v.shape[-2] for v in pyramid]),
+                    _int_array([v.shape[-1] for v in pyramid]), i32(L), ptr(coords), ptr(store), i32(B), i32(H), i32(W),
+                    i32(radius), i32(1 if channels_last else 0), stream(),
+                    algo_bytes=B * H * W * (L * ((2 * radius + 2) ** 2 + (2 * radius + 1) ** 2) * 4 + 8))
+    return out
 
 
 # ---------------------------------------------------------------- point all-pairs correlation
 def corr3d_build(feat1, feat2, xyzs2, k=3):
-    """models/camliraft_l_core.py:51-60."""
+    """models/camliraft_l_core.py:51-60: feat [B,C,n] -> volumes [B,n1,n2_l]."""
     _need_cuda(feat1, feat2)
-    vol = torch.bmm(feat1.float().transpose(1, 2), feat2.float()) / feat1.shape[1]
+    _no_grad("corr3d_build", feat1, feat2)
+    B, C, n1 = feat1.shape
+    vol = torch.bmm(rows_of(feat1.float()), feat2.float()) / C
     pyr = [vol]
     for i in range(1, len(xyzs2)):
         idx = k_nearest_neighbor(xyzs2[i - 1], xyzs2[i], k)
-        pyr.append(torch.mean(gather_points(pyr[i - 1], idx), -1))
+        n_in, n_out = pyr[-1].shape[-1], xyzs2[i].shape[-1]
+        nxt = torch.empty((B, n1, n_out), dtype=torch.float32, device=vol.device)
+        with torch.cuda.device(vol.device):
+            native.call("camli_corr3d_pool", i32(B), i32(n1), i32(n_in), i32(n_out), i32(k), ptr(pyr[-1]), ptr(idx),
+                        ptr(nxt), stream(), algo_bytes=B * n1 * (n_in + n_out) * 4)
+        pyr.append(nxt)
     return pyr
 
 
-def corr3d_gather(xyz1, xyz2, volume, k):
-    """For every point of xyz1 its k nearest points of xyz2: relative offsets and the matching
-    volume entries, stacked as [B,4,n1,k] (models/camliraft_l_core.py:62-76)."""
-    _need_cuda(xyz1, xyz2, volume)
-    B, n1, n2 = volume.shape
-    idx = k_nearest_neighbor(xyz2, xyz1, k)
-    off = gather_points(xyz2, idx) - xyz1[:, :, :, None]
-    c = torch.gather(volume, 2, idx).view(B, 1, n1, k)
-    return torch.cat([off, c], 1)
+def corr3d_lookup_rows(xyz1, xyzs2, pyramid, W1, b1, W2, b2):
+    """Correlation3D.forward before `merge` (models/camliraft_l_core.py:62-98), every level in one
+    launch: rows [B,n1,32*L]."""
+    _need_cuda(xyz1, *xyzs2, *pyramid)
+    _no_grad("corr3d_lookup", xyz1, *xyzs2, *pyramid, W1, W2)
+    xyz1 = xyz1.contiguous()
+    B, _, n1 = xyz1.shape
+    L = len(pyramid)
+    out = torch.empty((B, n1, 32 * L), dtype=torch.float32, device=xyz1.device)
+    strides = []
+    for x in xyzs2:
+        s = x.stride()
+        strides += [s[0], s[2], s[1]]
+    k = 16
+    with torch.cuda.device(xyz1.device):
+        native.call("camli_corr3d_lookup", i32(B), i32(n1), i32(L), ptr(xyz1), _ptr_array(xyzs2),
+                    _int_array(strides, ctypes.c_int64), _int_array([x.shape[-1] for x in xyzs2]), _ptr_array(pyramid),
+                    ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(out), i32(32 * L), stream(),
+                    algo_bytes=B * sum(n1 * 12 + x.shape[-1] * 12 + n1 * k * 16 + n1 * 128 for x in xyzs2),
+                    flops=B * sum(n1 * x.shape[-1] * 8 + n1 * k * 2 * (4 * 32 + 32 * 32) for x in xyzs2))
+    return out
 
 
 # ---------------------------------------------------------------- point convolutions
@@ -119,15 +228,51 @@ def neighbor_offsets(xyz, sampled_xyz, idx):
     return gather_points(xyz, idx) - sampled_xyz[:, :, :, None]
 
 
-def pointconv_dw_aggregate(feat, weights, idx):
-    """max_k( feat[:, :, idx] * weights ): feat [B,O,N], weights [B,O,S,k], idx [B,S,k] -> [B,O,S]
-    (models/point_conv.py:126-128)."""
-    return torch.max(gather_points(feat, idx) * weights, -1)[0]
+def pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, weight_net):
+    """WeightNet(3->8->32->O, ReLU) of every neighbour offset as rows [B,S,k,O]
+    (models/point_conv.py:122-127).  Depends only on geometry + layer parameters."""
+    _need_cuda(xyz, sampled_xyz, knn_idx)
+    convs = weight_net.convs
+    params = []
+    for c in convs:
+        w, b = c.folded()
+        params += [w.contiguous(), b.contiguous()]
+    _no_grad("pointconv_dw_weights", xyz, sampled_xyz, *params)
+    B, _, N = xyz.shape
+    S, K = knn_idx.shape[1], knn_idx.shape[2]
+    O = params[4].shape[0]
+    assert params[0].shape == (8, 3) and params[2].shape == (32, 8) and params[4].shape[1] == 32
+    knn_idx = knn_idx.contiguous()
+    out = torch.empty((B, S, k, O), dtype=torch.float32, device=xyz.device)
+    xs, cs = xyz.stride(), sampled_xyz.stride()
+    with torch.cuda.device(xyz.device):
+        native.call("camli_pointconv_dw_weights", i32(B), i32(N), i32(S), i32(K), i32(k), i32(O),
+                    ptr(xyz), i64(xs[0]), i64(xs[2]), i64(xs[1]), ptr(sampled_xyz), i64(cs[0]), i64(cs[2]), i64(cs[1]),
+                    ptr(knn_idx), *[ptr(p) for p in params], ptr(out), stream(),
+                    algo_bytes=B * S * k * (O * 4 + 8 + 12), flops=2 * B * S * k * (24 + 256 + 32 * O))
+    return out
+
+
+def pointconv_dw_gather_max(feat_rows, weights, knn_idx, k):
+    """out[b,s,o] = max_j feat_rows[b, idx[b,s,j], o] * weights[b,s,j,o] (models/point_conv.py:126-128):
+    feat_rows [B,N,O], weights [B,S,k,O], knn_idx [B,S,K>=k] -> rows [B,S,O]."""
+    _need_cuda(feat_rows, weights, knn_idx)
+    _no_grad("pointconv_dw_gather_max", feat_rows, weights)
+    assert feat_rows.is_contiguous() and weights.is_contiguous()
+    knn_idx = knn_idx.contiguous()
+    B, N, O = feat_rows.shape
+    S, K = knn_idx.shape[1], knn_idx.shape[2]
+    out = torch.empty((B, S, O), dtype=torch.float32, device=feat_rows.device)
+    with torch.cuda.device(out.device):
+        native.call("camli_pointconv_dw_gather_max", i32(B), i32(N), i32(S), i32(K), i32(k), i32(O), ptr(feat_rows), i64(O),
+                    ptr(weights), ptr(knn_idx), ptr(out), i64(O), stream(),
+                    algo_bytes=B * S * (k * (2 * O * 4 + 8) + O * 4), flops=B * S * k * O * 2)
+    return out
 
 
 def pointconv_aggregate(feat, weights, idx):
     """Per centroid [16 x k] @ [k x C]: feat [B,C,N], weights [B,16,S,k], idx [B,S,k]
-    -> [B,S,16*C] (models/point_conv.py:62-66)."""
+    -> [B,S,16*C] (models/point_conv.py:62-66).  Encoder only (6 calls per forward)."""
     B, S = idx.shape[:2]
     g = gather_points(feat, idx).permute(0, 2, 3, 1)
     return torch.matmul(weights.transpose(1, 2), g).reshape(B, S, -1)
@@ -143,9 +288,24 @@ def nearest_point_2d(uv, H, W):
     return k_nearest_neighbor(uv, grid, 1)[..., 0]
 
 
+def clfm_interp(uv, nn_idx, feat3d_rows, score_net, H, W):
+    """FusionAwareInterp before out_conv (models/clfm.py:57-75): logical [B,C,H,W], NHWC storage."""
+    _need_cuda(uv, nn_idx, feat3d_rows)
+    (w1, b1), (w2, b2) = score_net[0].folded(), score_net[1].folded()
+    _no_grad("clfm_interp", uv, feat3d_rows, w1, w2)
+    assert feat3d_rows.is_contiguous()
+    B, N, C = feat3d_rows.shape
+    uv, nn_idx = uv.contiguous(), nn_idx.contiguous()
+    store = torch.empty((B, H, W, C), dtype=torch.float32, device=uv.device)
+    with torch.cuda.device(uv.device):
+        native.call("camli_clfm_interp", i32(B), i32(H), i32(W), i32(N), i32(C), ptr(uv), ptr(nn_idx), ptr(feat3d_rows),
+                    i64(C), ptr(w1.contiguous()), ptr(b1.contiguous()), ptr(w2.contiguous()), ptr(b2.contiguous()),
+                    ptr(store), stream(), algo_bytes=B * H * W * (8 + 8 + 2 * C * 4), flops=2 * B * H * W * (48 + 16 * C))
+    return nchw_view(store)
+
+
 # ---------------------------------------------------------------- per-launch profiling (bench.py)
 def profile_begin():
-    from . import native
     native.profile_begin()
 
 
@@ -154,7 +314,6 @@ def profile_end(peaks_path=None):
     region: achieved = algorithmic bytes per launch / average launch duration."""
     import json
     import os
-    from . import native
     prof = native.profile_end()
     if not prof:
         return None

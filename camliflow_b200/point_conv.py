@@ -9,13 +9,17 @@ from .csrc import k_nearest_neighbor
 from .mlp import MLP1d, MLP2d, LayerNormCF, _ACTS
 
 
-def _select_neighbors(xyz, sampled_xyz, knn_indices, k):
-    """Reuse a (possibly wider) precomputed neighbour table or search (point_conv.py:49-55)."""
+def _neighbor_table(xyz, sampled_xyz, knn_indices, k):
+    """A precomputed (possibly wider) neighbour table, or a fresh search (point_conv.py:49-55)."""
     if knn_indices is None:
         return k_nearest_neighbor(xyz, sampled_xyz, k)
     assert knn_indices.shape[:2] == torch.Size([sampled_xyz.shape[0], sampled_xyz.shape[-1]])
     assert knn_indices.shape[2] >= k
-    return knn_indices[:, :, :k]
+    return knn_indices
+
+
+def _select_neighbors(xyz, sampled_xyz, knn_indices, k):
+    return _neighbor_table(xyz, sampled_xyz, knn_indices, k)[:, :, :k]
 
 
 class PointConv(nn.Module):
@@ -62,9 +66,20 @@ class PointConvDW(nn.Module):
         self.mlp = MLP1d(in_channels, [out_channels], norm, act)
         self.weight_net = MLP2d(3, [8, 32, out_channels], act="relu")
 
-    def forward(self, xyz, features, sampled_xyz=None, knn_indices=None):
+    def forward(self, xyz, features, sampled_xyz=None, knn_indices=None, cache=None):
+        """xyz [B,3,N], features [B,C,N] -> [B,O,S] (a transposed view of channel-last storage)."""
+        return ops.cf_of(self.forward_rows(xyz, ops.rows_of(features), sampled_xyz, knn_indices, cache))
+
+    def forward_rows(self, xyz, feat_rows, sampled_xyz=None, knn_indices=None, cache=None):
+        """Channel-last fast path: feat_rows [B,N,C] -> [B,S,O].  `cache` (a dict owned by the caller)
+        keeps the WeightNet output, which depends only on (xyz, neighbour table, layer parameters),
+        across the iterations of a recurrent loop."""
         if sampled_xyz is None:
             sampled_xyz = xyz
-        idx = _select_neighbors(xyz, sampled_xyz, knn_indices, self.k)
-        weights = self.weight_net(ops.neighbor_offsets(xyz, sampled_xyz, idx))       # [B,O,S,k]
-        return ops.pointconv_dw_aggregate(self.mlp(features), weights, idx)
+        table = _neighbor_table(xyz, sampled_xyz, knn_indices, self.k)
+        weights = cache.get(id(self)) if cache is not None else None
+        if weights is None:
+            weights = ops.pointconv_dw_weights(xyz, sampled_xyz, table, self.k, self.weight_net)
+            if cache is not None:
+                cache[id(self)] = weights
+        return ops.pointconv_dw_gather_max(self.mlp.forward_rows(feat_rows), weights, table, self.k)

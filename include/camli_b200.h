@@ -100,6 +100,114 @@ int camli_correlation_backward(const float* grad_out, float* grad_in1, float* gr
                                int B, int C, int H, int W, int max_displacement,
                                void* stream);
 
+
+/* ------------------------------------------------------------------------- *
+ * L1: fused hot-path operators of the CamLiRAFT cores
+ *   "rows" = channel-last storage: [B, points, ld] f32 with ld >= channels.
+ *   Arguments named *_host are HOST arrays (of device pointers / sizes).
+ * ------------------------------------------------------------------------- */
+
+/*
+ * RAFT correlation lookup, all pyramid levels in one launch.
+ * Replaces Correlation2D.forward (models/raft_core.py:71-107).
+ * volumes_host[l]: device pointer of level l, [B, H*W, level_h[l], level_w[l]] f32;
+ * coords [B,2,H,W] (x then y, in level-0 pixels); radius must be 4.
+ * out: [B, n_levels*81, H, W] f32 if out_nhwc == 0, else NHWC [B, H, W, n_levels*81].
+ * channel = l*81 + i*9 + j, i offsets x and j offsets y (the reference's order);
+ * bilinear, align_corners, zero padding.
+ */
+int camli_corr2d_lookup(const float* const* volumes_host, const int* level_h_host, const int* level_w_host,
+                        int n_levels, const float* coords, float* out, int B, int H, int W,
+                        int radius, int out_nhwc, void* stream);
+
+/*
+ * Every coarser level of the correlation-volume pyramid from one read of level 0:
+ * level l = 2x2 average pooling (stride 2, floor) of level l-1 over the trailing (h, w) axes,
+ * the avg_pool2d loop of models/raft_core.py:65-68.  vol0 [rows, h0, w0]; coarser_host[l-1]:
+ * device pointer of level l, [rows, h0>>l, w0>>l], l = 1..n_levels-1.
+ */
+int camli_corr2d_pool_pyramid(const float* vol0, float* const* coarser_host, int n_levels, int64_t rows,
+                              int h0, int w0, void* stream);
+
+/*
+ * Three-NN (k <= 32) inverse-distance interpolation fused with the neighbour search.
+ * Replaces knn_interpolation (models/utils.py:130-146).  All tensors are addressed through
+ * element strides: query_xyz/input_xyz as [B, points, 3] views (batch, point, dim),
+ * input_feat/out as [B, F, points] views (batch, channel, point).
+ */
+int camli_three_nn_interpolate(int B, int n, int m, int k, int F,
+                               const float* query_xyz, int64_t q_sb, int64_t q_sp, int64_t q_sd,
+                               const float* input_xyz, int64_t i_sb, int64_t i_sp, int64_t i_sd,
+                               const float* input_feat, int64_t f_sb, int64_t f_sc, int64_t f_sp,
+                               float* out, int64_t o_sb, int64_t o_sc, int64_t o_sp, void* stream);
+
+/*
+ * backwarp_3d (models/utils.py:149-159): xyz2_warp = xyz2 + interp_k(xyz1 + flow12, -flow12)(xyz2).
+ * xyz1, flow12 [B,3,m]; xyz2, xyz2_warp [B,3,n]; contiguous channel-first.
+ */
+int camli_backwarp_3d(int B, int n, int m, int k, const float* xyz1, const float* flow12,
+                      const float* xyz2, float* xyz2_warp, void* stream);
+
+/*
+ * PointConvDW WeightNet (models/point_conv.py:122-127): weights_out[b,s,j,:] =
+ * relu(W3 relu(W2 relu(W1 (xyz[idx[b,s,j]] - centre[b,s]) + b1) + b2) + b3), rows [B,S,k,O].
+ * xyz / centre_xyz: [B, points, 3] views (element strides batch, point, dim);
+ * knn_idx [B,S,K] i64 of which the first k columns are used; W1 [8,3], W2 [32,8], W3 [O,32].
+ */
+int camli_pointconv_dw_weights(int B, int N, int S, int K, int k, int O,
+                               const float* xyz, int64_t x_sb, int64_t x_sp, int64_t x_sd,
+                               const float* centre_xyz, int64_t c_sb, int64_t c_sp, int64_t c_sd,
+                               const int64_t* knn_idx,
+                               const float* W1, const float* b1, const float* W2, const float* b2,
+                               const float* W3, const float* b3, float* weights_out, void* stream);
+
+/*
+ * PointConvDW aggregation (models/point_conv.py:126-128):
+ * out_rows[b,s,o] = max_{j<k} feat_rows[b, idx[b,s,j], o] * weights[b,s,j,o].  k <= 32.
+ */
+int camli_pointconv_dw_gather_max(int B, int N, int S, int K, int k, int O,
+                                  const float* feat_rows, int64_t ld_feat, const float* weights,
+                                  const int64_t* knn_idx, float* out_rows, int64_t ld_out, void* stream);
+
+/*
+ * Point-correlation lookup, all levels in one launch (Correlation3D.forward up to the `merge`
+ * convolution, models/camliraft_l_core.py:62-98): per level l, the 16 nearest points of
+ * xyz2_levels[l] around every xyz1 point, MLP 4->32->32 (ReLU) of (offset, volume entry),
+ * summed over the neighbours, written to out_rows[b, q, 32*l : 32*l+32].
+ * xyz1 [B,3,n1] contiguous; xyz2_levels_host[l]: device pointer of a [B, n2, 3] view with
+ * element strides xyz2_strides_host[3l..3l+2] = (batch, point, dim); volumes_host[l] [B,n1,n2_host[l]].
+ */
+int camli_corr3d_lookup(int B, int n1, int n_levels, const float* xyz1,
+                        const float* const* xyz2_levels_host, const int64_t* xyz2_strides_host,
+                        const int* n2_host, const float* const* volumes_host,
+                        const float* W1, const float* b1, const float* W2, const float* b2,
+                        float* out_rows, int ld_out, void* stream);
+
+/*
+ * One pooling step of the point-correlation pyramid (models/camliraft_l_core.py:56-60):
+ * vol_out[b,p,q] = mean_{j<k} vol_in[b,p,knn_idx[b,q,j]];  vol_in [B,n1,n_in], vol_out [B,n1,n_out].
+ */
+int camli_corr3d_pool(int B, int n1, int n_in, int n_out, int k, const float* vol_in,
+                      const int64_t* knn_idx, float* vol_out, void* stream);
+
+/*
+ * CLFM 3D->2D gather + ScoreNet (FusionAwareInterp.forward before out_conv, models/clfm.py:57-75):
+ * out_rows[b,p,:] = sigmoid(W2 leaky(W1 [du,dv,|d|] + b1) + b2) * feat3d_rows[b, nn_idx[b,p], :]
+ * with (du,dv) = uv[b,:,nn] - pixel(p).  uv [B,2,N]; nn_idx [B,H*W] i64; W1 [16,3]; W2 [C,16];
+ * out_rows NHWC [B,H*W,C].
+ */
+int camli_clfm_interp(int B, int H, int W, int N, int C, const float* uv, const int64_t* nn_idx,
+                      const float* feat3d_rows, int64_t ld_feat,
+                      const float* W1, const float* b1, const float* W2, const float* b2,
+                      float* out_rows, void* stream);
+
+/*
+ * Bilinear sample of an NHWC map at pixel coordinates uv [B,2,N] (align_corners, zeros
+ * outside): grid_sample_wrapper, models/utils.py:262-269.  out_rows [B,N,ld_out].
+ */
+int camli_bilinear_sample_rows(int B, int H, int W, int N, int C, const float* feat_nhwc, const float* uv,
+                               float* out_rows, int64_t ld_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,172 @@
+"""GPU parity of the fused hot-path kernels (called through the C-ABI via camliflow_b200.ops)
+against the plain-PyTorch fp32 formulas of tests/torch_ref.py on the same CUDA tensors.
+Index-producing parts are bit-exact by construction (they share knn_search.cuh with the k-NN
+kernel, itself bit-exact vs the reference kernels); floating-point results are compared with the
+tolerances written below."""
+import pytest
+import torch
+
+from tests import torch_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from camliflow_b200 import ops
+    return ops
+
+
+def _knn(a, q, k):
+    from camliflow_b200.csrc import k_nearest_neighbor
+    return k_nearest_neighbor(a, q, k)
+
+
+def _cloud(B, N, dev, seed, scale=10.0):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(B, 3, N, generator=g) - 0.5) * scale).to(dev)
+
+
+def _close(a, b, atol, rtol=1e-5, what=""):
+    err = (a - b).abs().max().item()
+    assert torch.allclose(a, b, atol=atol, rtol=rtol), "%s max|diff| %.3e" % (what, err)
+
+
+@pytest.mark.parametrize("B,m,n,F,k", [(1, 2048, 8192, 3, 3), (2, 2048, 2048, 3, 3), (2, 500, 333, 70, 3),
+                                       (1, 64, 50, 5, 8)])
+def test_knn_interpolate(dev, B, m, n, F, k):
+    xi, xq = _cloud(B, m, dev, 1), _cloud(B, n, dev, 2)
+    feat = torch.randn(B, F, m, device=dev)
+    out = _ops().knn_interpolate(xi, feat, xq, k)
+    ref = R.knn_interpolate(xi, feat, xq, _knn(xi, xq, k))
+    _close(out, ref, 1e-5, what="knn_interpolate")
+
+
+def test_knn_interpolate_coincident_points(dev):
+    """Queries that coincide with inputs hit the clamp(1e-8) branch."""
+    xi = _cloud(1, 1024, dev, 3)
+    feat = torch.randn(1, 3, 1024, device=dev)
+    out = _ops().knn_interpolate(xi, feat, xi[:, :, :512].contiguous(), 3)
+    ref = R.knn_interpolate(xi, feat, xi[:, :, :512], _knn(xi, xi[:, :, :512].contiguous(), 3))
+    _close(out, ref, 1e-5, what="coincident")
+
+
+@pytest.mark.parametrize("B,m,n", [(1, 2048, 2048), (2, 1000, 700)])
+def test_backwarp_3d_and_prefix_levels(dev, B, m, n):
+    xyz1, xyz2 = _cloud(B, m, dev, 4), _cloud(B, n, dev, 5)
+    flow = torch.randn(B, 3, m, device=dev) * 0.3
+    out = _ops().backwarp_3d(xyz1, xyz2, flow, 3)
+    warped = xyz1 + flow
+    ref = xyz2 + R.knn_interpolate(warped, -flow, xyz2, _knn(warped, xyz2, 3))
+    _close(out, ref, 1e-5, what="backwarp_3d")
+    # every coarser level of a prefix pyramid is a prefix of the finest level's result
+    half = xyz2[:, :, :n // 2].contiguous()
+    out_half = _ops().backwarp_3d(xyz1, half, flow, 3)
+    assert torch.equal(out_half, out[:, :, :n // 2])
+
+
+@pytest.mark.parametrize("B,C,H,W,N", [(1, 128, 68, 120, 2048), (2, 324, 20, 28, 300), (1, 7, 5, 6, 50)])
+def test_bilinear_sample(dev, B, C, H, W, N):
+    g = torch.Generator().manual_seed(6)
+    feat = torch.randn(B, C, H, W, generator=g).to(dev)
+    uv = torch.stack([torch.rand(B, N, generator=g) * (W + 3) - 2, torch.rand(B, N, generator=g) * (H + 3) - 2], 1).to(dev)
+    uv[:, :, :4] = torch.tensor([[0.0, W - 1.0, 3.0, W - 1.0], [0.0, H - 1.0, H - 1.0, 2.5]], device=dev)   # exact corners
+    for src in (feat, feat.contiguous(memory_format=torch.channels_last)):
+        out = _ops().bilinear_sample(src, uv)
+        _close(out, R.bilinear_sample(feat, uv), 1e-5, what="bilinear_sample")
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 256, 68, 120), (2, 64, 17, 30), (1, 32, 9, 11)])
+def test_corr2d_build_and_lookup(dev, B, C, H, W):
+    g = torch.Generator().manual_seed(7)
+    f1, f2 = torch.randn(B, C, H, W, generator=g).to(dev), torch.randn(B, C, H, W, generator=g).to(dev)
+    L = 4 if min(H, W) >= 16 else 3
+    pyr = _ops().corr2d_build(f1, f2, L)
+    ref_pyr = R.corr2d_build(f1, f2, L)
+    for a, b in zip(pyr, ref_pyr):
+        assert a.shape == b.shape
+        _close(a, b, 2e-5, what="corr2d_build level")
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    coords = (torch.stack([xs, ys], 0)[None].expand(B, 2, H, W) + torch.randn(B, 2, H, W, generator=g) * 6).to(dev)
+    coords[:, :, 0, 0] = torch.tensor([0.0, 0.0], device=dev)          # exactly on a grid corner
+    coords[:, :, 0, 1] = torch.tensor([-30.0, 500.0], device=dev)       # far outside
+    coords[:, :, 1, 0] = torch.tensor([W - 1.0, H - 1.0], device=dev)
+    ref = R.corr2d_lookup(ref_pyr, coords, 4)
+    for cl in (True, False):
+        out = _ops().corr2d_lookup(ref_pyr, coords, 4, channels_last=cl)
+        assert out.shape == ref.shape
+        # grid_sample re-derives every tap position through a normalise/un-normalise round trip
+        # (|dx| ~ 1e-5 px at W=120), ours uses one exact fractional offset per pixel and level
+        _close(out, ref, 2e-4, rtol=1e-4, what="corr2d_lookup cl=%s" % cl)
+
+
+def test_corr3d_pool_and_lookup(dev):
+    B, n1 = 2, 512
+    g = torch.Generator().manual_seed(8)
+    xyz1 = _cloud(B, n1, dev, 9)
+    full = _cloud(B, 512, dev, 10)
+    xyzs2 = [full[:, :, :n] for n in (512, 256, 128, 64)]              # prefix pyramid (strided views)
+    vol = torch.randn(B, n1, 512, generator=g).to(dev)
+    pyr_ref = [vol]
+    for i in range(1, 4):
+        pyr_ref.append(R.corr3d_pool(pyr_ref[-1], _knn(xyzs2[i - 1], xyzs2[i], 3)))
+    feat1 = torch.randn(B, 32, n1, generator=g).to(dev)
+    feat2 = torch.randn(B, 32, 512, generator=g).to(dev)
+    pyr = _ops().corr3d_build(feat1, feat2, xyzs2, 3)
+    _close(pyr[0], torch.bmm(feat1.transpose(1, 2), feat2) / 32, 1e-5, what="corr3d volume")
+    p = pyr[0]
+    for i in range(1, 4):
+        p = R.corr3d_pool(p, _knn(xyzs2[i - 1], xyzs2[i], 3))
+        _close(pyr[i], p, 1e-5, what="corr3d pool %d" % i)
+    W1, b1 = torch.randn(32, 4, generator=g).to(dev) * 0.5, torch.randn(32, generator=g).to(dev) * 0.1
+    W2, b2 = torch.randn(32, 32, generator=g).to(dev) * 0.2, torch.randn(32, generator=g).to(dev) * 0.1
+    out = _ops().corr3d_lookup_rows(xyz1, xyzs2, pyr_ref, W1, b1, W2, b2)
+    idxs = [_knn(x.contiguous(), xyz1, 16) for x in xyzs2]
+    ref = R.corr3d_lookup(xyz1, xyzs2, pyr_ref, idxs, W1, b1, W2, b2)
+    _close(out.transpose(1, 2), ref, 2e-4, rtol=1e-4, what="corr3d_lookup")
+
+
+@pytest.mark.parametrize("B,N,S,K,k,O", [(1, 2048, 2048, 32, 32, 128), (2, 600, 600, 32, 16, 125), (1, 512, 512, 32, 4, 128),
+                                         (1, 300, 100, 16, 16, 16)])
+def test_pointconv_dw(dev, B, N, S, K, k, O):
+    from camliflow_b200.mlp import MLP2d
+    g = torch.Generator().manual_seed(11)
+    xyz = _cloud(B, N, dev, 12)
+    centre = xyz[:, :, :S].contiguous()
+    idx = _knn(xyz, centre, K)
+    wn = MLP2d(3, [8, 32, O], act="relu").to(dev)
+    params = []
+    for c in wn.convs:
+        c.conv_fn.weight.data = torch.randn(c.conv_fn.weight.shape, generator=g).to(dev) * 0.4
+        c.conv_fn.bias.data = torch.randn(c.conv_fn.bias.shape, generator=g).to(dev) * 0.2
+        params += [c.conv_fn.weight.data.flatten(1), c.conv_fn.bias.data]
+    with torch.no_grad():
+        wc = _ops().pointconv_dw_weights(xyz, centre, idx, k, wn)
+    ref_w = R.pointconv_dw_weights(xyz, centre, idx[:, :, :k], params)
+    _close(wc, ref_w, 1e-4, rtol=1e-4, what="dw weights")
+    feat = torch.randn(B, O, N, generator=g).to(dev)
+    out = _ops().pointconv_dw_gather_max(_ops().rows_of(feat), ref_w, idx, k)
+    ref = R.pointconv_dw_gather_max(feat, ref_w, idx[:, :, :k])
+    assert torch.equal(out.transpose(1, 2), ref)      # product + max: no rounding freedom
+
+
+@pytest.mark.parametrize("B,H,W,N,C", [(1, 68, 120, 2048, 128), (2, 9, 13, 100, 40)])
+def test_clfm_interp(dev, B, H, W, N, C):
+    from camliflow_b200.mlp import Conv2dNormRelu
+    g = torch.Generator().manual_seed(13)
+    uv = torch.stack([torch.rand(B, N, generator=g) * (W - 1), torch.rand(B, N, generator=g) * (H - 1)], 1).to(dev)
+    feat3d = torch.randn(B, C, N, generator=g).to(dev)
+    sn = torch.nn.Sequential(Conv2dNormRelu(3, 16), Conv2dNormRelu(16, C, act="sigmoid")).to(dev)
+    nn_idx = _ops().nearest_point_2d(uv, H, W)
+    with torch.no_grad():
+        out = _ops().clfm_interp(uv, nn_idx, _ops().rows_of(feat3d), sn, H, W)
+        ref = R.clfm_interp(uv, nn_idx, feat3d, sn[0].conv_fn.weight.flatten(1), sn[0].conv_fn.bias,
+                            sn[1].conv_fn.weight.flatten(1), sn[1].conv_fn.bias, H, W)
+    assert out.shape == ref.shape
+    _close(out, ref, 1e-5, what="clfm_interp")

@@ -1,0 +1,73 @@
+"""CPU tests of the product's host side (module wiring, layouts, caches, state_dict names) with the
+kernels answered by their PyTorch formulas (tests/_cpu_ops.py), against the REFERENCE model's golden
+outputs.  The kernels themselves are tested on the GPU (tests/test_gpu_ops.py, test_gpu_model.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import camliraft_oracle as co
+from tests._cpu_ops import cpu_kernels
+from tests._util import GOLDEN
+
+
+def epe(a, b):
+    return float(np.sqrt(((a - b) ** 2).sum(0)).mean())
+
+
+def _model(n_iters):
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.init import seed_module_
+    return seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=n_iters)), seed=0).eval()
+
+
+def test_state_dict_is_the_reference_state_dict():
+    sd = _model(1).state_dict()
+    spec = co.param_spec("camliraft")
+    assert set(sd) == set(spec)
+    assert all(tuple(sd[k].shape) == spec[k] for k in spec)
+    P = co.make_params(spec, seed=0)
+    assert all(torch.equal(sd[k], P[k]) for k in spec)
+
+
+def test_product_graph_matches_reference_golden_small():
+    G = np.load(os.path.join(GOLDEN, "model_camliraft.npz"))
+    inputs = co.synthetic_inputs(1, 160, 224, 8192, seed=11)
+    with cpu_kernels(), torch.no_grad():
+        out = _model(3)(inputs)
+    e2 = epe(out["flow_2d"][0, :, ::4, ::4].numpy(), G["small_kernel_flow2d"])
+    e3 = epe(out["flow_3d"][0, :, ::4].numpy(), G["small_kernel_flow3d"])
+    assert e2 <= 1e-3 and e3 <= 1e-4, (e2, e3)
+
+
+def test_module_surface_matches_rows_fast_path():
+    """PointConvDW / CLFM public (channel-first) calls equal their channel-last fast paths."""
+    from camliflow_b200 import ops
+    from camliflow_b200.clfm import CLFM
+    from camliflow_b200.point_conv import PointConvDW
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.rand(2, 3, 300, generator=g) * 4
+    feat = torch.randn(2, 24, 300, generator=g)
+    with cpu_kernels(), torch.no_grad():
+        conv = PointConvDW(24, 40, k=8).eval()
+        a = conv(xyz, feat)
+        cache = {}
+        b = conv.forward_rows(xyz, ops.rows_of(feat), cache=cache)
+        c = conv.forward_rows(xyz, ops.rows_of(feat), cache=cache)      # served from the cache
+        assert a.shape == (2, 40, 300) and torch.equal(a, b.transpose(1, 2)) and torch.equal(b, c)
+        assert len(cache) == 1
+        clfm = CLFM(16, 24, norm="batch_norm").eval()
+        uv = torch.stack([torch.rand(2, 300, generator=g) * 11, torch.rand(2, 300, generator=g) * 8], 1)
+        f2d = torch.randn(2, 16, 9, 12, generator=g)
+        o2, o3 = clfm(uv, f2d, feat)
+        assert o2.shape == f2d.shape and o3.shape == feat.shape
+
+
+def test_ops_refuse_cpu_tensors():
+    from camliflow_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.knn_interpolate(torch.rand(1, 3, 10), torch.rand(1, 3, 10), torch.rand(1, 3, 5))
+    with pytest.raises(RuntimeError):
+        ops.corr2d_lookup([torch.rand(1, 4, 2, 2)], torch.rand(1, 2, 2, 2), 4)
