@@ -223,11 +223,6 @@ def corr3d_lookup_rows(xyz1, xyzs2, pyramid, W1, b1, W2, b2):
 
 
 # ---------------------------------------------------------------- point convolutions
-def neighbor_offsets(xyz, sampled_xyz, idx):
-    """[B,3,S,k] offsets of the grouped neighbours from their centroid."""
-    return gather_points(xyz, idx) - sampled_xyz[:, :, :, None]
-
-
 def pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, weight_net):
     """WeightNet(3->8->32->O, ReLU) of every neighbour offset as rows [B,S,k,O]
     (models/point_conv.py:122-127).  Depends only on geometry + layer parameters."""
@@ -270,12 +265,26 @@ def pointconv_dw_gather_max(feat_rows, weights, knn_idx, k):
     return out
 
 
-def pointconv_aggregate(feat, weights, idx):
-    """Per centroid [16 x k] @ [k x C]: feat [B,C,N], weights [B,16,S,k], idx [B,S,k]
-    -> [B,S,16*C] (models/point_conv.py:62-66).  Encoder only (6 calls per forward)."""
-    B, S = idx.shape[:2]
-    g = gather_points(feat, idx).permute(0, 2, 3, 1)
-    return torch.matmul(weights.transpose(1, 2), g).reshape(B, S, -1)
+def pointconv_group(rows, sampled_xyz, knn_idx, k, weight_net, negative_slope):
+    """PointConv grouping (models/point_conv.py:56-66): rows [B,N,3+C] = [xyz | features] channel-last,
+    sampled_xyz [B,3,S], knn_idx [B,S,K>=k]; WeightNet(3->8->16) evaluated in-kernel.
+    Returns [B,S,16*(3+C)] in the order the reference's Linear expects (weight-major)."""
+    _need_cuda(rows, sampled_xyz, knn_idx)
+    (w1, b1), (w2, b2) = weight_net.convs[0].folded(), weight_net.convs[1].folded()
+    _no_grad("pointconv_group", rows, w1, w2)
+    assert rows.is_contiguous() and w1.shape == (8, 3) and w2.shape == (16, 8)
+    knn_idx = knn_idx.contiguous()
+    B, N, C = rows.shape
+    S, K = knn_idx.shape[1], knn_idx.shape[2]
+    out = torch.empty((B, S, 16 * C), dtype=torch.float32, device=rows.device)
+    cs = sampled_xyz.stride()
+    with torch.cuda.device(rows.device):
+        native.call("camli_pointconv_group", i32(B), i32(N), i32(S), i32(K), i32(k), i32(C), ptr(rows), i64(C),
+                    ptr(sampled_xyz), i64(cs[0]), i64(cs[2]), i64(cs[1]), ptr(knn_idx),
+                    ptr(w1.contiguous()), ptr(b1.contiguous()), ptr(w2.contiguous()), ptr(b2.contiguous()),
+                    ctypes.c_float(negative_slope), ptr(out), stream(),
+                    algo_bytes=B * S * (k * (C * 4 + 8) + 16 * C * 4), flops=2 * B * S * 16 * k * C)
+    return out
 
 
 # ---------------------------------------------------------------- CLFM

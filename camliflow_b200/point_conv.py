@@ -18,8 +18,6 @@ def _neighbor_table(xyz, sampled_xyz, knn_indices, k):
     return knn_indices
 
 
-def _select_neighbors(xyz, sampled_xyz, knn_indices, k):
-    return _neighbor_table(xyz, sampled_xyz, knn_indices, k)[:, :, :k]
 
 
 class PointConv(nn.Module):
@@ -44,15 +42,16 @@ class PointConv(nn.Module):
         if act not in ("relu", "leaky_relu", None):
             raise NotImplementedError("Unknown activation function: %s" % act)
         self.act_fn = _ACTS[act]()
+        self._slope = {"relu": 0.0, "leaky_relu": 0.1, None: 1.0}[act]
 
     def forward(self, xyz, features, sampled_xyz=None, knn_indices=None):
         """xyz [B,3,N], features [B,C,N], sampled_xyz [B,3,S] -> [B,O,S]."""
         if sampled_xyz is None:
             sampled_xyz = xyz
-        idx = _select_neighbors(xyz, sampled_xyz, knn_indices, self.k)
-        weights = self.weight_net(ops.neighbor_offsets(xyz, sampled_xyz, idx))       # [B,16,S,k]
-        grouped = ops.pointconv_aggregate(torch.cat([xyz, features], dim=1), weights, idx)   # [B,S,16(C+3)]
-        out = self.linear(grouped).transpose(1, 2)
+        table = _neighbor_table(xyz, sampled_xyz, knn_indices, self.k)
+        rows = ops.rows_of(torch.cat([xyz, features], dim=1))                      # [B,N,3+C]
+        grouped = ops.pointconv_group(rows, sampled_xyz, table, self.k, self.weight_net, self._slope)
+        out = self.linear(grouped).transpose(1, 2)                                 # [B,O,S]
         return self.act_fn(self.norm_fn(out))
 
 

@@ -208,6 +208,19 @@ int camli_clfm_interp(int B, int H, int W, int N, int C, const float* uv, const 
 int camli_bilinear_sample_rows(int B, int H, int W, int N, int C, const float* feat_nhwc, const float* uv,
                                float* out_rows, int64_t ld_out, void* stream);
 
+/*
+ * PointConv grouping stage (models/point_conv.py:56-66): rows [B,N,ld_rows] hold [xyz | features]
+ * channel-last (xyz in columns 0..2, C columns used); out[b,s,w*C + c] =
+ * sum_{j<k} WeightNet(xyz[idx[b,s,j]] - centre[b,s])[w] * rows[b, idx[b,s,j], c], w < 16, with
+ * WeightNet = act(W2 act(W1 d + b1) + b2), act = leaky(negative_slope) (0 => ReLU, 1 => identity).
+ * centre_xyz: [B,S,3] view with element strides (batch, point, dim).  k <= 32, C <= 256.
+ */
+int camli_pointconv_group(int B, int N, int S, int K, int k, int C,
+                          const float* rows, int64_t ld_rows,
+                          const float* centre_xyz, int64_t c_sb, int64_t c_sp, int64_t c_sd,
+                          const int64_t* knn_idx, const float* W1, const float* b1, const float* W2,
+                          const float* b2, float negative_slope, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

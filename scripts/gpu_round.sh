@@ -1,14 +1,10 @@
 #!/bin/bash
 # One GPU-box round: parity tests, bench, launch list. Outputs under gpurun_out/.
-set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt
-timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q -s 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+tail -25 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-timeout 300 python bench.py --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/bench_eager.json 2>> gpurun_out/bench.err
-tail -c 1500 gpurun_out/bench_eager.json
-timeout 600 python scripts/microbench_l0.py > gpurun_out/microbench_l0.log 2>&1; tail -3 gpurun_out/microbench_l0.log
+tail -c 3500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 wc -l gpurun_out/launches.csv

@@ -63,6 +63,8 @@ def cpu_kernels():
         (ops, "corr3d_lookup_rows"): corr3d_lookup_rows,
         (ops, "pointconv_dw_weights"): lambda xyz, s, idx, k, wn: R.pointconv_dw_weights(xyz, s, idx[:, :, :k], _folded(wn.convs)),
         (ops, "pointconv_dw_gather_max"): lambda f, w, idx, k: ops.rows_of(R.pointconv_dw_gather_max(ops.cf_of(f), w, idx[:, :, :k])),
+        (ops, "pointconv_group"): lambda rows, sx, idx, k, wn, slope: R.pointconv_group(
+            ops.cf_of(rows)[:, :3], ops.cf_of(rows)[:, 3:], sx, idx[:, :, :k], *_folded(wn.convs), slope),
         (ops, "clfm_interp"): lambda uv, nn, f, sn, H, W: R.clfm_interp(uv, nn, ops.cf_of(f), *_folded(sn), H, W),
         (ut, "k_nearest_neighbor"): _knn, (ut, "furthest_point_sampling"): _fps,
         (pc, "k_nearest_neighbor"): _knn, (cc, "k_nearest_neighbor"): _knn, (cl, "k_nearest_neighbor"): _knn,

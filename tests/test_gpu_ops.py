@@ -170,3 +170,21 @@ def test_clfm_interp(dev, B, H, W, N, C):
                             sn[1].conv_fn.weight.flatten(1), sn[1].conv_fn.bias, H, W)
     assert out.shape == ref.shape
     _close(out, ref, 1e-5, what="clfm_interp")
+
+
+@pytest.mark.parametrize("B,N,S,C,k,act", [(1, 8192, 4096, 96, 16, "leaky_relu"), (2, 4096, 2048, 128, 16, "leaky_relu"),
+                                           (1, 500, 200, 13, 9, "relu"), (1, 300, 300, 195, 16, None)])
+def test_pointconv_group(dev, B, N, S, C, k, act):
+    from camliflow_b200.mlp import MLP2d
+    g = torch.Generator().manual_seed(14)
+    xyz = _cloud(B, N, dev, 15)
+    centre = xyz[:, :, :S].contiguous()
+    feat = torch.randn(B, C, N, generator=g).to(dev)
+    idx = _knn(xyz, centre, k)
+    wn = MLP2d(3, [8, 16], act=act).to(dev)
+    slope = {"relu": 0.0, "leaky_relu": 0.1, None: 1.0}[act]
+    with torch.no_grad():
+        out = _ops().pointconv_group(_ops().rows_of(torch.cat([xyz, feat], 1)), centre, idx, k, wn, slope)
+        ref = R.pointconv_group(xyz, feat, centre, idx, wn.convs[0].conv_fn.weight.flatten(1), wn.convs[0].conv_fn.bias,
+                                wn.convs[1].conv_fn.weight.flatten(1), wn.convs[1].conv_fn.bias, slope)
+    _close(out, ref, 1e-4, rtol=1e-4, what="pointconv_group")

@@ -100,3 +100,13 @@ def clfm_interp(uv, nn_idx, feat3d, W1, b1, W2, b2, H, W):
     s = F.leaky_relu(F.conv2d(si, W1[:, :, None, None], b1), 0.1)
     s = torch.sigmoid(F.conv2d(s, W2[:, :, None, None], b2))
     return (s[..., 0] * gather_cf(feat3d, nn_idx)).view(B, -1, H, W)
+
+
+def pointconv_group(xyz, feat, sampled_xyz, idx, W1, b1, W2, b2, slope):
+    """models/point_conv.py:56-66: [B,S,16*(3+C)]."""
+    B, S = idx.shape[:2]
+    off = gather_cf(xyz, idx) - sampled_xyz[:, :, :, None]
+    w = F.leaky_relu(F.conv2d(off, W1[:, :, None, None], b1), slope)
+    w = F.leaky_relu(F.conv2d(w, W2[:, :, None, None], b2), slope).transpose(1, 2)      # [B,S,16,k]
+    g = gather_cf(torch.cat([xyz, feat], 1), idx).permute(0, 2, 3, 1)                   # [B,S,k,3+C]
+    return torch.matmul(w, g).reshape(B, S, -1)
