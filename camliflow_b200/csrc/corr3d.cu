@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int C3_WARPS = 8;
+constexpr int C3_WARPS = KNN_WARPS;
 constexpr int C3_K = 16;
 constexpr int C3_H = 32;
 constexpr int C3_MAX_LEVELS = 8;
@@ -30,18 +30,24 @@ corr3d_lookup_kernel(const __grid_constant__ Corr3dLevels lv, int n1, const floa
                      const float* __restrict__ W1, const float* __restrict__ b1,                        // [32,4],[32]
                      const float* __restrict__ W2, const float* __restrict__ b2,                        // [32,32],[32]
                      float* __restrict__ out, int ld_out) {                                             // rows [B,n1,ld]
+    __shared__ KnnTile tile;
     __shared__ __align__(16) float s_h1[C3_WARPS][C3_K][C3_H];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * C3_WARPS + warp;
-    if (q >= n1) return;
+    const bool active = q < n1;
     const int level = blockIdx.y, b = blockIdx.z;
     const int n2 = lv.n2[level];
-    const float* qp = xyz1 + (size_t)b * 3 * n1 + q;
-    const float ux = __ldg(qp), uy = __ldg(qp + n1), uz = __ldg(qp + 2 * n1);
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (active) {
+        const float* qp = xyz1 + (size_t)b * 3 * n1 + q;
+        ux = __ldg(qp); uy = __ldg(qp + n1); uz = __ldg(qp + 2 * n1);
+    }
     const float* x2 = lv.xyz2[level] + b * lv.sb[level];
     const long long sp = lv.sp[level], sd = lv.sd[level];
     const KnnPlainPoints<3> pts{x2, sp, sd};
-    const KnnList r = knn_warp_search<1>(pts, n2, C3_K, ux, uy, uz);
+    KnnList r;
+    knn_cta_search<3, 1>(r, tile, pts, n2, C3_K, active, ux, uy, uz);
+    if (!active) return;
 
     // lanes 0..15: neighbour offset + matching cost
     float in0 = 0.f, in1 = 0.f, in2 = 0.f, in3 = 0.f;

@@ -14,6 +14,7 @@
 //
 // Tie rule (bit-exact with the reference tree, which takes the right operand
 // on `<=`): winner = max over points of (dist, bitrev10(i & 1023), -i).
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace {
@@ -128,6 +129,127 @@ fps_streaming_kernel(const float* __restrict__ xyz_all, float* __restrict__ dist
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster path (2048 < N <= 16384): the rounds of ONE cloud are spread over a thread-block cluster
+// of 8 CTAs (8 SMs).  A single 1024-thread CTA is issue-bound at ~1 kcycle per round (N*10
+// instructions through 4 schedulers); splitting the points 8 ways leaves ~100 cycles of math per
+// round, plus one DSMEM exchange: every CTA reduces its slice to a (key, xyz) record, stores it
+// into all 8 CTAs' shared memory (distributed shared memory), and after one cluster barrier every
+// CTA picks the global winner locally.  Records are double-buffered by round parity so one
+// barrier per round is enough.
+//
+// The tie rule is carried by an explicit 64-bit key: hi = float bits of the distance (>= 0, so
+// integer order = float order), lo = bitrev10(i & 1023) << 22 | (0x3FFFFF - i); max over it =
+// (largest distance, largest bit-reversed owner thread of the reference kernel, smallest i).
+namespace cg = cooperative_groups;
+
+constexpr int FPSC_CTAS = 8;
+constexpr int FPSC_THREADS = 256;
+constexpr int FPSC_WARPS = FPSC_THREADS / 32;
+constexpr int FPSC_MAX_N = FPSC_CTAS * FPSC_THREADS * 8;   // 16384
+
+struct __align__(16) FpsRecord { int hi; unsigned lo; float x, y, z; int pad0, pad1, pad2; };
+
+__device__ __forceinline__ unsigned fps_key_lo(int i) {
+    return ((__brev((unsigned)i & 1023u) >> 22) << 22) | (0x3FFFFFu - (unsigned)i);
+}
+
+template <int PPT>
+__global__ void __cluster_dims__(FPSC_CTAS, 1, 1) __launch_bounds__(FPSC_THREADS, 1)
+fps_cluster_kernel(const float* __restrict__ xyz_all, int N, int S, int64_t* __restrict__ out_all) {
+    __shared__ float4 s_pts[PPT * FPSC_THREADS];                  // this CTA's slice
+    __shared__ FpsRecord s_warp[FPSC_WARPS];
+    __shared__ FpsRecord s_rec[2][FPSC_CTAS];                     // written by every CTA of the cluster
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / FPSC_CTAS;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float* __restrict__ xyz = xyz_all + (size_t)cloud * N * 3;
+    int64_t* __restrict__ out = out_all + (size_t)cloud * S;
+
+    // point i = (j * CTAS + rank) * THREADS + t  (coalesced 256-point chunks, round-robin over CTAs)
+    float px[PPT], py[PPT], pz[PPT], pd[PPT];
+    unsigned plo[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int i = (j * FPSC_CTAS + rank) * FPSC_THREADS + t;
+        if (i < N) {
+            px[j] = xyz[i * 3 + 0]; py[j] = xyz[i * 3 + 1]; pz[j] = xyz[i * 3 + 2];
+            pd[j] = 1e10f;                                        // furthest_point_sampling.cpp:12
+            plo[j] = fps_key_lo(i);
+        } else {
+            px[j] = py[j] = pz[j] = 0.f;
+            pd[j] = -2.f;                                         // never beats a real point
+            plo[j] = 0u;
+        }
+        s_pts[j * FPSC_THREADS + t] = make_float4(px[j], py[j], pz[j], 0.f);
+    }
+    float cx = __ldg(xyz + 0), cy = __ldg(xyz + 1), cz = __ldg(xyz + 2);   // first sample: index 0
+    int cur = 0;
+    cluster.sync();                                               // all CTAs resident before any DSMEM store
+
+    for (int s = 0; s < S; ++s) {
+        if (rank == 0 && t == 0) out[s] = (int64_t)cur;
+        if (s == S - 1) break;
+        // ---- local slice: update running distances, thread-local best
+        float best_d = -3.f;
+        unsigned best_lo = 0u;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = camli_sqdist3(px[j] - cx, py[j] - cy, pz[j] - cz);
+            const float nd = fminf(pd[j], d);
+            pd[j] = nd;
+            if (nd > best_d || (nd == best_d && plo[j] > best_lo)) { best_d = nd; best_lo = plo[j]; }
+        }
+        // ---- warp, then CTA
+        int hi = __float_as_int(best_d);
+        int hmax = __reduce_max_sync(CAMLI_FULL_MASK, hi);
+        unsigned lmax = __reduce_max_sync(CAMLI_FULL_MASK, hi == hmax ? best_lo : 0u);
+        if (hi == hmax && best_lo == lmax) { s_warp[warp].hi = hmax; s_warp[warp].lo = lmax; }
+        __syncthreads();
+        if (warp == 0) {
+            const int whi = lane < FPSC_WARPS ? s_warp[lane].hi : (int)0x80000000;
+            const unsigned wlo = lane < FPSC_WARPS ? s_warp[lane].lo : 0u;
+            hmax = __reduce_max_sync(CAMLI_FULL_MASK, whi);
+            lmax = __reduce_max_sync(CAMLI_FULL_MASK, whi == hmax ? wlo : 0u);
+            if (lane < FPSC_CTAS) {
+                FpsRecord r;
+                r.hi = hmax; r.lo = lmax; r.pad0 = r.pad1 = r.pad2 = 0;
+                r.x = r.y = r.z = 0.f;
+                if (hmax >= 0) {                                  // this CTA owns at least one real point
+                    const int i = (int)(0x3FFFFFu - (lmax & 0x3FFFFFu));
+                    const int chunk = i / FPSC_THREADS;           // = j * CTAS + rank
+                    const float4 p = s_pts[(chunk / FPSC_CTAS) * FPSC_THREADS + (i % FPSC_THREADS)];
+                    r.x = p.x; r.y = p.y; r.z = p.z;
+                }
+                FpsRecord* dst = cluster.map_shared_rank(&s_rec[s & 1][rank], lane);
+                *dst = r;
+            }
+        }
+        cluster.sync();                                           // release/acquire: records visible cluster-wide
+        // ---- every thread picks the winner among the 8 records (identical everywhere)
+        int bh = (int)0x80000000;
+        unsigned bl = 0u;
+        int bi = 0;
+#pragma unroll
+        for (int c = 0; c < FPSC_CTAS; ++c) {
+            const int h = s_rec[s & 1][c].hi;
+            const unsigned l = s_rec[s & 1][c].lo;
+            if (h > bh || (h == bh && l > bl)) { bh = h; bl = l; bi = c; }
+        }
+        cx = s_rec[s & 1][bi].x; cy = s_rec[s & 1][bi].y; cz = s_rec[s & 1][bi].z;
+        cur = (int)(0x3FFFFFu - (bl & 0x3FFFFFu));
+    }
+    cluster.sync();                                               // no CTA exits while peers may still store to it
+}
+
+template <int PPT>
+int fps_launch_cluster(const float* xyz, int B, int N, int S, int64_t* out, cudaStream_t st) {
+    fps_cluster_kernel<PPT><<<B * FPSC_CTAS, FPSC_THREADS, 0, st>>>(xyz, N, S, out);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
 template <int PPT>
 int fps_launch_register(const float* xyz, int B, int N, int S, int64_t* out, cudaStream_t st) {
     const size_t smem = (size_t)N * sizeof(float4);
@@ -140,6 +262,14 @@ int fps_launch_register(const float* xyz, int B, int N, int S, int64_t* out, cud
 
 }  // namespace
 
+// Tuning switch (tests exercise both paths): 1 = cluster kernel for 2048 < N <= 16384.
+static int camli_fps_use_cluster = 1;
+extern "C" int camli_fps_set_cluster_path(int enable) {
+    const int old = camli_fps_use_cluster;
+    camli_fps_use_cluster = enable ? 1 : 0;
+    return old;
+}
+
 extern "C" int camli_furthest_point_sampling(const float* xyz, float* dists_tmp, int B, int N, int S,
                                              int64_t* out, void* stream) {
     if (B < 0 || N < 1 || S < 0) return CAMLI_EINVAL;
@@ -148,6 +278,12 @@ extern "C" int camli_furthest_point_sampling(const float* xyz, float* dists_tmp,
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 1 * FPS_THREADS) return fps_launch_register<1>(xyz, B, N, S, out, st);
     if (N <= 2 * FPS_THREADS) return fps_launch_register<2>(xyz, B, N, S, out, st);
+    if (camli_fps_use_cluster) {
+        const int per = FPSC_CTAS * FPSC_THREADS;
+        if (N <= 2 * per) return fps_launch_cluster<2>(xyz, B, N, S, out, st);
+        if (N <= 4 * per) return fps_launch_cluster<4>(xyz, B, N, S, out, st);
+        if (N <= FPSC_MAX_N) return fps_launch_cluster<8>(xyz, B, N, S, out, st);
+    }
     if (N <= 4 * FPS_THREADS) return fps_launch_register<4>(xyz, B, N, S, out, st);
     if (N <= FPS_MAX_REG_POINTS) return fps_launch_register<8>(xyz, B, N, S, out, st);
     if (!dists_tmp) return CAMLI_EINVAL;

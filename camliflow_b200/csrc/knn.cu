@@ -17,22 +17,25 @@
 
 namespace {
 
-constexpr int KNN_WARPS_PER_CTA = 8;
-
 template <int D, int SLOTS>
-__global__ void __launch_bounds__(KNN_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_warp_kernel(int n, int m, int k, const float* __restrict__ query_all, KnnView qv,
                 const float* __restrict__ input_all, KnnView iv, int64_t* __restrict__ idx_all) {
+    __shared__ KnnTile tile;
     const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * KNN_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (q >= n) return;   // whole warp leaves together
+    const int q = blockIdx.x * KNN_WARPS + (threadIdx.x >> 5);
+    const bool active = q < n;
     const int b = blockIdx.y;
-    const float* __restrict__ qp = query_all + b * qv.sb + q * qv.sp;
-    int64_t* __restrict__ out = idx_all + ((size_t)b * n + q) * k;
-    const float ux = __ldg(qp), uy = __ldg(qp + qv.sd), uz = (D == 3) ? __ldg(qp + 2 * qv.sd) : 0.f;
-
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (active) {
+        const float* __restrict__ qp = query_all + b * qv.sb + q * qv.sp;
+        ux = __ldg(qp); uy = __ldg(qp + qv.sd); uz = (D == 3) ? __ldg(qp + 2 * qv.sd) : 0.f;
+    }
     const KnnPlainPoints<D> pts{input_all + b * iv.sb, iv.sp, iv.sd};
-    const KnnList r = knn_warp_search<SLOTS>(pts, m, k, ux, uy, uz);
+    KnnList r;
+    knn_cta_search<D, SLOTS>(r, tile, pts, m, k, active, ux, uy, uz);
+    if (!active) return;
+    int64_t* __restrict__ out = idx_all + ((size_t)b * n + q) * k;
     if (lane < k) out[lane] = (int64_t)r.i0;
     if (SLOTS == 2 && lane + 32 < k) out[lane + 32] = (int64_t)r.i1;
 }
@@ -40,8 +43,8 @@ knn_warp_kernel(int n, int m, int k, const float* __restrict__ query_all, KnnVie
 template <int D>
 int knn_launch(int B, int n, int m, int k, const float* query, KnnView qv, const float* input, KnnView iv,
                int64_t* idx, cudaStream_t st) {
-    dim3 grid(camli_div_up(n, KNN_WARPS_PER_CTA), B);
-    dim3 block(KNN_WARPS_PER_CTA * 32);
+    dim3 grid(camli_div_up(n, KNN_WARPS), B);
+    dim3 block(KNN_WARPS * 32);
     if (k <= 32) knn_warp_kernel<D, 1><<<grid, block, 0, st>>>(n, m, k, query, qv, input, iv, idx);
     else         knn_warp_kernel<D, 2><<<grid, block, 0, st>>>(n, m, k, query, qv, input, iv, idx);
     CAMLI_RETURN_LAUNCH_STATUS();

@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int TNN_WARPS = 8;
+constexpr int TNN_WARPS = KNN_WARPS;
 
 // Weights of the k neighbours held one per lane (lanes >= k get 0).
 __device__ __forceinline__ float tnn_weight(int lane, int k, float px, float py, float pz,
@@ -32,15 +32,21 @@ three_nn_interp_kernel(int n, int m, int k, int F,
                        const float* __restrict__ query, KnnView qv, const float* __restrict__ input, KnnView iv,
                        const float* __restrict__ feat, long long f_sb, long long f_sc, long long f_sp,
                        float* __restrict__ out, long long o_sb, long long o_sc, long long o_sp) {
+    __shared__ KnnTile tile;
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * TNN_WARPS + (threadIdx.x >> 5);
-    if (q >= n) return;
+    const bool active = q < n;
     const int b = blockIdx.y;
-    const float* qp = query + b * qv.sb + q * qv.sp;
-    const float ux = __ldg(qp), uy = __ldg(qp + qv.sd), uz = __ldg(qp + 2 * qv.sd);
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (active) {
+        const float* qp = query + b * qv.sb + q * qv.sp;
+        ux = __ldg(qp); uy = __ldg(qp + qv.sd); uz = __ldg(qp + 2 * qv.sd);
+    }
     const float* in = input + b * iv.sb;
     const KnnPlainPoints<3> pts{in, iv.sp, iv.sd};
-    const KnnList r = knn_warp_search<1>(pts, m, k, ux, uy, uz);
+    KnnList r;
+    knn_cta_search<3, 1>(r, tile, pts, m, k, active, ux, uy, uz);
+    if (!active) return;
 
     float px = 0.f, py = 0.f, pz = 0.f;
     if (lane < k) {
@@ -67,16 +73,22 @@ three_nn_interp_kernel(int n, int m, int k, int F,
 __global__ void __launch_bounds__(TNN_WARPS * 32)
 backwarp3d_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __restrict__ flow,
                   const float* __restrict__ xyz2, float* __restrict__ out) {
+    __shared__ KnnTile tile;
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * TNN_WARPS + (threadIdx.x >> 5);
-    if (q >= n) return;
+    const bool active = q < n;
     const int b = blockIdx.y;
-    const float* qp = xyz2 + (size_t)b * 3 * n + q;
-    const float ux = __ldg(qp), uy = __ldg(qp + n), uz = __ldg(qp + 2 * n);
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (active) {
+        const float* qp = xyz2 + (size_t)b * 3 * n + q;
+        ux = __ldg(qp); uy = __ldg(qp + n); uz = __ldg(qp + 2 * n);
+    }
     const float* p1 = xyz1 + (size_t)b * 3 * m;
     const float* fl = flow + (size_t)b * 3 * m;
-    const KnnDisplacedPoints pts{p1, fl, 1, m};
-    const KnnList r = knn_warp_search<1>(pts, m, k, ux, uy, uz);
+    const KnnDisplacedPoints pts{p1, fl, m};
+    KnnList r;
+    knn_cta_search<3, 1>(r, tile, pts, m, k, active, ux, uy, uz);
+    if (!active) return;
 
     float px = 0.f, py = 0.f, pz = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
     if (lane < k) {

@@ -44,11 +44,15 @@ const char* camli_strerror(int code);
  * xyz [B,N,3] f32, out [B,S] i64.  First sample is index 0; ties are resolved
  * exactly as the reference's 1024-thread shared-memory tree does (largest
  * bit-reversed (i mod 1024), then smallest i).
- * dists_tmp: [B,N] f32 scratch, only touched when N > 8192 (may be NULL
- * otherwise); contents on entry are ignored (the library initialises it).
+ * dists_tmp: [B,N] f32 scratch, only touched when N > 16384 (or N > 8192 with the cluster
+ * path disabled); may be NULL otherwise; contents on entry are ignored.
  */
 int camli_furthest_point_sampling(const float* xyz, float* dists_tmp,
                                   int B, int N, int S, int64_t* out, void* stream);
+
+/* Selects the FPS kernel for 2048 < N <= 16384: 1 = 8-CTA thread-block-cluster kernel (default),
+ * 0 = single-CTA register kernel.  Returns the previous setting.  Results are identical. */
+int camli_fps_set_cluster_path(int enable);
 
 /*
  * Brute-force exact k nearest neighbours, ascending distance.

@@ -41,14 +41,25 @@ FPS_CASES = [
     ("duplicates_with_replacement", lambda: _util.synthetic_pc(1, 5000, seed=8)[:, torch.randint(
         0, 5000, (8192,), generator=torch.Generator().manual_seed(9))], 4096),
     ("streaming_n10000", lambda: _util.synthetic_pc(2, 10000, seed=10), 1500),
+    ("n16384", lambda: _util.synthetic_pc(1, 16384, seed=12), 1000),
+    ("streaming_n17000", lambda: _util.synthetic_pc(1, 17000, seed=13), 600),
+    ("n2049", lambda: _util.rand_cloud(3, 2049, 3, seed=14), 2048),
     ("streaming_ties_n9000", lambda: _util.tied_cloud(1, 9000, 3, levels=10, seed=11), 1200),
 ]
 
 
+@pytest.mark.parametrize("cluster", [1, 0], ids=["cluster", "single_cta"])
 @pytest.mark.parametrize("name,make,S", FPS_CASES, ids=[c[0] for c in FPS_CASES])
-def test_fps_bit_exact(dev, name, make, S):
+def test_fps_bit_exact(dev, name, make, S, cluster):
+    """Both kernels behind camli_furthest_point_sampling (8-CTA cluster / single CTA)."""
+    from camliflow_b200 import native
     xyz = make().contiguous()
-    got = _csrc().furthest_point_sampling(xyz.to(dev), S)
+    old = native.lib().camli_fps_set_cluster_path(cluster)
+    try:
+        got = _csrc().furthest_point_sampling(xyz.to(dev), S)
+        torch.cuda.synchronize()
+    finally:
+        native.lib().camli_fps_set_cluster_path(old)
     assert got.dtype == torch.int64 and got.shape == (xyz.shape[0], S)
     want = _util.oracle_fps(xyz.numpy(), S)
     assert np.array_equal(got.cpu().numpy(), want), "vs C oracle: %d mismatches" % (got.cpu().numpy() != want).sum()
