@@ -10,6 +10,7 @@ There is no CPU path and no eager-PyTorch fallback: CUDA tensors and a built lib
 required.  Forward only for now: calling these with tensors that require grad raises.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -135,6 +136,32 @@ def convex_upsample(flow, mask, s=8):
     return up.reshape(B, 2, H * s, W * s)
 
 
+# ---------------------------------------------------------------- all-pairs inner products
+# "tcgen05": the hand-written TMA + tcgen05 3xTF32 kernel (default); "cublas": torch.bmm (library fp32
+# SGEMM), kept only as the A/B comparison point for benchmarks.
+ALLPAIRS_IMPL = os.environ.get("CAMLI_ALLPAIRS", "tcgen05")
+
+
+def allpairs(a_rows, b_rows, scale):
+    """out[b,m,n] = scale * <a_rows[b,m,:], b_rows[b,n,:]>: a_rows [B,M,K], b_rows [B,N,K] -> [B,M,N]."""
+    _need_cuda(a_rows, b_rows)
+    _no_grad("allpairs", a_rows, b_rows)
+    B, M, K = a_rows.shape
+    N = b_rows.shape[1]
+    if ALLPAIRS_IMPL == "cublas" or K % 32 != 0:
+        return torch.bmm(a_rows * scale, b_rows.transpose(1, 2))
+    a_rows, b_rows = a_rows.contiguous(), b_rows.contiguous()
+    out = torch.empty((B, M, N), dtype=torch.float32, device=a_rows.device)
+    lib = native.lib()
+    lib.camli_allpairs_workspace_floats.restype = ctypes.c_int64
+    ws = torch.empty((lib.camli_allpairs_workspace_floats(B, M, N, K),), dtype=torch.float32, device=a_rows.device)
+    with torch.cuda.device(out.device):
+        native.call("camli_allpairs_correlation", ptr(a_rows), ptr(b_rows), ptr(ws), ptr(out), i32(B), i32(M), i32(N),
+                    i32(K), ctypes.c_float(scale), stream(),
+                    algo_bytes=B * ((M + N) * K * 4 + M * N * 4), flops=2 * B * M * N * K)
+    return out
+
+
 # ---------------------------------------------------------------- RAFT all-pairs correlation
 def corr2d_build(fmap1, fmap2, num_levels):
     """All-pairs volume of two [B,C,H,W] maps scaled by 1/sqrt(C) and its 2x2 average-pooled pyramid
@@ -145,7 +172,7 @@ def corr2d_build(fmap1, fmap2, num_levels):
     B, C, H, W = fmap1.shape
     a = nhwc_rows(fmap1).view(B, H * W, C)
     b = nhwc_rows(fmap2).view(B, H * W, C)
-    vol = torch.bmm(a * (1.0 / C ** 0.5), b.transpose(1, 2)).view(B, H * W, H, W)
+    vol = allpairs(a, b, 1.0 / C ** 0.5).view(B, H * W, H, W)
     pyr = [vol]
     h, w = H, W
     for _ in range(num_levels - 1):
@@ -186,7 +213,7 @@ def corr3d_build(feat1, feat2, xyzs2, k=3):
     _need_cuda(feat1, feat2)
     _no_grad("corr3d_build", feat1, feat2)
     B, C, n1 = feat1.shape
-    vol = torch.bmm(rows_of(feat1.float()), feat2.float()) / C
+    vol = allpairs(rows_of(feat1.float()), rows_of(feat2.float()), 1.0 / C)
     pyr = [vol]
     for i in range(1, len(xyzs2)):
         idx = k_nearest_neighbor(xyzs2[i - 1], xyzs2[i], k)

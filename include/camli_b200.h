@@ -225,6 +225,20 @@ int camli_pointconv_group(int B, int N, int S, int K, int k, int C,
                           const int64_t* knn_idx, const float* W1, const float* b1, const float* W2,
                           const float* b2, float negative_slope, float* out, void* stream);
 
+/*
+ * All-pairs feature inner product on the tcgen05 tensor cores (TMA-fed, TMEM accumulators),
+ * fp32-accurate through a 3xTF32 operand split:
+ *     out[b,m,n] = scale * sum_k a_rows[b,m,k] * b_rows[b,n,k]
+ * Replaces torch.matmul(fmap1^T, fmap2) / sqrt(C) (models/raft_core.py:56-63) and
+ * torch.bmm(feat1^T, feat2) / C (models/camliraft_l_core.py:52-53).
+ * a_rows [B*M, K], b_rows [B*N, K] row-major f32 (16-byte aligned); K % 32 == 0;
+ * workspace: camli_allpairs_workspace_floats(B,M,N,K) floats of scratch (the hi/lo operand
+ * copies); out [B,M,N] f32.
+ */
+int64_t camli_allpairs_workspace_floats(int B, int M, int N, int K);
+int camli_allpairs_correlation(const float* a_rows, const float* b_rows, float* workspace, float* out,
+                               int B, int M, int N, int K, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

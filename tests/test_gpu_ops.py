@@ -188,3 +188,22 @@ def test_pointconv_group(dev, B, N, S, C, k, act):
         ref = R.pointconv_group(xyz, feat, centre, idx, wn.convs[0].conv_fn.weight.flatten(1), wn.convs[0].conv_fn.bias,
                                 wn.convs[1].conv_fn.weight.flatten(1), wn.convs[1].conv_fn.bias, slope)
     _close(out, ref, 1e-4, rtol=1e-4, what="pointconv_group")
+
+
+@pytest.mark.parametrize("B,M,N,K", [(1, 8160, 8160, 256), (2, 300, 500, 64), (1, 2048, 2048, 128), (3, 128, 128, 32),
+                                     (1, 129, 257, 96)])
+def test_allpairs_tcgen05(dev, B, M, N, K):
+    """3xTF32 tensor-core product vs an fp64 reference: fp32-level accuracy is the bar (the reference
+    computes this product in fp32), so the error must be no worse than ~2x a true fp32 SGEMM's."""
+    g = torch.Generator().manual_seed(16)
+    a = torch.randn(B, M, K, generator=g).to(dev)
+    b = torch.randn(B, N, K, generator=g).to(dev)
+    scale = 1.0 / K ** 0.5
+    out = _ops().allpairs(a, b, scale)
+    torch.cuda.synchronize()
+    ref64 = torch.bmm(a.double(), b.double().transpose(1, 2)) * scale
+    sgemm = torch.bmm(a, b.transpose(1, 2)) * scale
+    err = (out.double() - ref64).abs().max().item()
+    err_sgemm = (sgemm.double() - ref64).abs().max().item()
+    print("allpairs %s: max err %.3e (fp32 SGEMM %.3e)" % ((B, M, N, K), err, err_sgemm))
+    assert err <= max(4 * err_sgemm, 2e-6), (err, err_sgemm)
