@@ -14,6 +14,7 @@ class CamLiRAFT(nn.Module):
         super().__init__()
         self.cfgs = cfgs
         self.core = CamLiRAFT_Core(cfgs)
+        self.channels_last = False      # set by FlowEngine: run the 2-D branch in NHWC (cuDNN's native layout)
         self.register_buffer("_mean", torch.tensor([123.675, 116.280, 103.530]).view(1, 3, 1, 1), persistent=False)
         self.register_buffer("_std", torch.tensor([58.395, 57.120, 57.375]).view(1, 3, 1, 1), persistent=False)
 
@@ -34,6 +35,9 @@ class CamLiRAFT(nn.Module):
         image1, image2 = padder.pad(images[:, :3], images[:, 3:])
         image1 = (image1 - self._mean) / self._std
         image2 = (image2 - self._mean) / self._std
+        if self.channels_last:
+            image1 = image1.contiguous(memory_format=torch.channels_last)
+            image2 = image2.contiguous(memory_format=torch.channels_last)
         H, W = image1.shape[-2:]
         persp = {"projection_mode": "perspective", "sensor_h": H, "sensor_w": W,
                  "f": intr[:, 0], "cx": intr[:, 1], "cy": intr[:, 2]}

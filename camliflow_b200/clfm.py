@@ -54,9 +54,17 @@ class SKFusion(nn.Module):
         B, C = pooled.shape
         return torch.softmax(self.fc_out(self.fc_mid(pooled)).view(B, C, 2), dim=-1)
 
+    def _fused_tail_ok(self, a):
+        return a.is_cuda and not (torch.is_grad_enabled() and (a.requires_grad or self.fc_mid[0].weight.requires_grad))
+
     def forward(self, feat_2d, feat_3d):
         a, b = self.align1(feat_2d), self.align2(feat_3d)
         B, C = a.shape[:2]
+        if a.dim() == 4 and self._fused_tail_ok(a):        # pool + FCs + softmax + blend in 3 launches
+            H, W = a.shape[-2:]
+            out = ops.sk_fusion_tail(ops.nhwc_rows(a).view(B, H * W, C), ops.nhwc_rows(b).view(B, H * W, C), 1.0,
+                                     self.fc_mid[0].weight, self.fc_out[0].weight)
+            return ops.nchw_view(out.view(B, H, W, C))
         w = self._blend_weights((a + b).flatten(2).mean(-1))
         shape = (B, C) + (1,) * (a.dim() - 2)
         return a * w[..., 0].reshape(shape) + b * w[..., 1].reshape(shape)
@@ -64,6 +72,8 @@ class SKFusion(nn.Module):
     def forward_rows(self, rows_2d, rows_3d):
         """'ncm' variant on channel-last point features [B,N,C]."""
         a, b = self.align1.forward_rows(rows_2d), self.align2.forward_rows(rows_3d)
+        if self._fused_tail_ok(a):
+            return ops.sk_fusion_tail(a.contiguous(), b.contiguous(), 1.0, self.fc_mid[0].weight, self.fc_out[0].weight)
         w = self._blend_weights((a + b).mean(1))
         return a * w[:, None, :, 0] + b * w[:, None, :, 1]
 

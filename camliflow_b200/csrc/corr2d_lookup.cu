@@ -66,16 +66,25 @@ corr2d_lookup_kernel(const __grid_constant__ LookupLevels lv, const float* __res
     }
     __syncthreads();
 
-    // ---- phase 1: footprints -> shared memory
-    for (int e = t; e < LK_TP * LK_FP * LK_FP; e += LK_THREADS) {
-        const int px = e / (LK_FP * LK_FP), a = e - px * (LK_FP * LK_FP);
+    // ---- phase 1: footprints -> shared memory.  All of a thread's loads are issued before the first
+    // shared-memory store, so 13 independent requests per thread are in flight (latency-bound otherwise).
+    constexpr int LK_PER_THREAD = (LK_TP * LK_FP * LK_FP + LK_THREADS - 1) / LK_THREADS;   // 13
+    float v[LK_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < LK_PER_THREAD; ++i) {
+        const int e = t + i * LK_THREADS;
+        const int px = min(e / (LK_FP * LK_FP), LK_TP - 1), a = e - (e / (LK_FP * LK_FP)) * (LK_FP * LK_FP);
         const int ry = a / LK_FP, rx = a - ry * LK_FP;
         const int p = p0 + px;
         const int yy = s_y0[px] + ry, xx = s_x0[px] + rx;
-        float v = 0.f;
-        if (p < HW && yy >= 0 && yy < h && xx >= 0 && xx < w)
-            v = __ldg(vol + ((size_t)p * h + yy) * w + xx);
-        s_fp[px * LK_STRIDE + a] = v;
+        v[i] = 0.f;
+        if (e < LK_TP * LK_FP * LK_FP && p < HW && yy >= 0 && yy < h && xx >= 0 && xx < w)
+            v[i] = __ldg(vol + ((size_t)p * h + yy) * w + xx);
+    }
+#pragma unroll
+    for (int i = 0; i < LK_PER_THREAD; ++i) {
+        const int e = t + i * LK_THREADS;
+        if (e < LK_TP * LK_FP * LK_FP) s_fp[(e / (LK_FP * LK_FP)) * LK_STRIDE + e % (LK_FP * LK_FP)] = v[i];
     }
     __syncthreads();
 

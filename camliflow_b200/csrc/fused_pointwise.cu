@@ -1,0 +1,178 @@
+// Fused pointwise / small-reduction kernels of the update block for sm_100a.
+//
+// (1) SK fusion tail (reference models/clfm.py:195-214, after the two `align` convolutions):
+//     avg-pool of (a+b) -> Linear -> ReLU -> Linear -> Sigmoid -> softmax over the branch pair ->
+//     a*w1 + b*w2.  The reference spends ~13 launches on it, twice per CLFM, four CLFMs per GRU
+//     iteration; here it is three: partial sums, one tiny per-sample FC kernel, one blend pass.
+//     Inputs are the PRE-activation outputs of the align layers; their leaky-ReLU is applied on load.
+// (2) ConvGRU gates (reference models/raft_core.py:123-139): after the merged z|r convolution
+//     z = sigmoid(.), r = sigmoid(.), and [r*h | x] is assembled for the q convolution in one pass;
+//     after the q convolution h' = (1-z)*h + z*tanh(q) (+ nan_to_num on the last half).
+// All tensors are channel-last rows [B, P, C] (NHWC maps or point rows).
+#include "common.cuh"
+
+namespace {
+
+constexpr int SK_SPLITS = 32;
+
+// partial[b, s, c] = sum over the s-th slice of positions of leaky(a) + leaky(b)
+__global__ void __launch_bounds__(256)
+sk_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int P, int C, float slope,
+                  float* __restrict__ partial) {
+    __shared__ float s_red[8][33];
+    const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane, s = blockIdx.y, bi = blockIdx.z;
+    const int per = (P + SK_SPLITS - 1) / SK_SPLITS;
+    const int p0 = s * per, p1 = min(P, p0 + per);
+    float acc = 0.f;
+    if (c < C) {
+        const float* pa = a + (size_t)bi * P * C + c;
+        const float* pb = b + (size_t)bi * P * C + c;
+        for (int p = p0 + ry; p < p1; p += 8)
+            acc += camli_leaky(__ldg(pa + (size_t)p * C), slope) + camli_leaky(__ldg(pb + (size_t)p * C), slope);
+    }
+    s_red[ry][lane] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_red[i][lane];
+        partial[((size_t)bi * SK_SPLITS + s) * C + c] = t;
+    }
+}
+
+// one CTA per sample: pooled mean -> fc_mid (ReLU) -> fc_out (sigmoid) -> softmax over pairs
+__global__ void __launch_bounds__(256)
+sk_weights_kernel(const float* __restrict__ partial, int P, int C, int Cm,
+                  const float* __restrict__ w_mid,    // [Cm, C]
+                  const float* __restrict__ w_out,    // [2C, Cm]
+                  float* __restrict__ weights) {      // [B, C, 2]
+    extern __shared__ float s_buf[];                  // pooled [C], mid [Cm], logits [2C]
+    float* s_pool = s_buf;
+    float* s_mid = s_buf + C;
+    float* s_out = s_mid + Cm;
+    const int bi = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int s = 0; s < SK_SPLITS; ++s) t += partial[((size_t)bi * SK_SPLITS + s) * C + c];
+        s_pool[c] = t / (float)P;
+    }
+    __syncthreads();
+    for (int j = warp; j < Cm; j += 8) {
+        float t = 0.f;
+        for (int c = lane; c < C; c += 32) t = fmaf(__ldg(w_mid + (size_t)j * C + c), s_pool[c], t);
+        t = camli_warp_sum(t);
+        if (lane == 0) s_mid[j] = fmaxf(t, 0.f);
+    }
+    __syncthreads();
+    for (int o = warp; o < 2 * C; o += 8) {
+        float t = 0.f;
+        for (int j = lane; j < Cm; j += 32) t = fmaf(__ldg(w_out + (size_t)o * Cm + j), s_mid[j], t);
+        t = camli_warp_sum(t);
+        if (lane == 0) s_out[o] = 1.f / (1.f + expf(-t));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float u = s_out[2 * c], v = s_out[2 * c + 1];
+        const float m = fmaxf(u, v);
+        const float eu = expf(u - m), ev = expf(v - m);
+        const float inv = 1.f / (eu + ev);
+        weights[((size_t)bi * C + c) * 2] = eu * inv;
+        weights[((size_t)bi * C + c) * 2 + 1] = ev * inv;
+    }
+}
+
+// out = leaky(a) * w[b,c,0] + leaky(b) * w[b,c,1]
+__global__ void __launch_bounds__(256)
+sk_blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ weights,
+                size_t PC, int C, float slope, float* __restrict__ out) {
+    const int bi = blockIdx.y;
+    const float* w = weights + (size_t)bi * C * 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < PC; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t g = (size_t)bi * PC + i;
+        out[g] = camli_leaky(__ldg(a + g), slope) * __ldg(w + 2 * c) + camli_leaky(__ldg(b + g), slope) * __ldg(w + 2 * c + 1);
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// zr [R, 2H] (z then r, pre-activation), h [R, H], x [R, X]  ->  z [R, H], rhx [R, H+X] = [r*h | x]
+__global__ void __launch_bounds__(256)
+gru_gate_kernel(const float* __restrict__ zr, const float* __restrict__ h, const float* __restrict__ x,
+                size_t R, int H, int X, float* __restrict__ z, float* __restrict__ rhx) {
+    const int W = H + X;
+    const size_t total = R * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / W;
+        const int c = (int)(i - r * W);
+        if (c < H) {
+            const float hv = __ldg(h + r * H + c);
+            z[r * H + c] = sigmoidf_(__ldg(zr + r * 2 * H + c));
+            rhx[i] = sigmoidf_(__ldg(zr + r * 2 * H + H + c)) * hv;
+        } else {
+            rhx[i] = __ldg(x + r * X + (c - H));
+        }
+    }
+}
+
+// h' = (1 - z) * h + z * tanh(q)   (optionally nan_to_num: nan -> 0, +-inf -> +-FLT_MAX)
+__global__ void __launch_bounds__(256)
+gru_update_kernel(const float* __restrict__ z, const float* __restrict__ h, const float* __restrict__ q, size_t n,
+                  int fix_nonfinite, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float zv = __ldg(z + i), hv = __ldg(h + i);
+        float v = (1.f - zv) * hv + zv * tanhf(__ldg(q + i));
+        if (fix_nonfinite) {
+            if (isnan(v)) v = 0.f;
+            else if (isinf(v)) v = v > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+        }
+        out[i] = v;
+    }
+}
+
+inline unsigned grid_for(size_t n) {
+    const size_t blocks = (n + 255) / 256;
+    return (unsigned)(blocks < 148u * 16u ? (blocks ? blocks : 1) : 148u * 16u);
+}
+
+}  // namespace
+
+extern "C" int camli_sk_fusion_tail(int B, int P, int C, int C_mid, const float* a_rows, const float* b_rows,
+                                    float negative_slope, const float* w_mid, const float* w_out,
+                                    float* partial_scratch, float* weights_scratch, float* out_rows, void* stream) {
+    if (B < 0 || P < 1 || C < 1 || C_mid < 1) return CAMLI_EINVAL;
+    if (B > 65535 || (size_t)(3 * C + C_mid) * sizeof(float) > 200 * 1024) return CAMLI_EUNSUPPORTED;
+    if (B == 0) return CAMLI_OK;
+    if (!a_rows || !b_rows || !w_mid || !w_out || !partial_scratch || !weights_scratch || !out_rows) return CAMLI_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    sk_partial_kernel<<<dim3(camli_div_up(C, 32), SK_SPLITS, B), 256, 0, st>>>(a_rows, b_rows, P, C, negative_slope,
+                                                                            partial_scratch);
+    const size_t smem = (size_t)(3 * C + C_mid) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sk_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    sk_weights_kernel<<<B, 256, smem, st>>>(partial_scratch, P, C, C_mid, w_mid, w_out, weights_scratch);
+    const size_t PC = (size_t)P * C;
+    sk_blend_kernel<<<dim3(grid_for(PC), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int camli_gru_gate(int64_t rows, int H, int X, const float* zr, const float* h, const float* x, float* z,
+                              float* rhx, void* stream) {
+    if (rows < 0 || H < 1 || X < 0) return CAMLI_EINVAL;
+    if (rows == 0) return CAMLI_OK;
+    if (!zr || !h || (X > 0 && !x) || !z || !rhx) return CAMLI_EINVAL;
+    gru_gate_kernel<<<grid_for((size_t)rows * (H + X)), 256, 0, (cudaStream_t)stream>>>(zr, h, x, (size_t)rows, H, X, z, rhx);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int camli_gru_update(int64_t n, const float* z, const float* h, const float* q, int fix_nonfinite,
+                                float* h_out, void* stream) {
+    if (n < 0) return CAMLI_EINVAL;
+    if (n == 0) return CAMLI_OK;
+    if (!z || !h || !q || !h_out) return CAMLI_EINVAL;
+    gru_update_kernel<<<grid_for((size_t)n), 256, 0, (cudaStream_t)stream>>>(z, h, q, (size_t)n, fix_nonfinite, h_out);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}

@@ -103,16 +103,29 @@ dw_gather_max_kernel(int N, int S, int K, int k, int O, int chunks,
     const float* fb = feat + (size_t)b * N * ldf;
     const float* wp = wc + ((size_t)b * S + s) * k * O;
     float best = -INFINITY;
-    if (o < O) {
-#pragma unroll 8
-        for (int j = 0; j < k; ++j) {
-            const int ij = __shfl_sync(CAMLI_FULL_MASK, my, j);
-            best = fmaxf(best, __ldg(fb + (size_t)ij * ldf + o) * __ldcs(wp + (size_t)j * O + o));
+    // k is a multiple of 4 in every layer of the model; batches of 4 neighbours keep 8 independent
+    // 128-byte requests in flight per warp
+    int j = 0;
+    for (; j + 4 <= k; j += 4) {
+        int ij[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ij[u] = __shfl_sync(CAMLI_FULL_MASK, my, j + u);
+        if (o < O) {
+            float f[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                f[u] = __ldg(fb + (size_t)ij[u] * ldf + o);
+                w[u] = __ldcs(wp + (size_t)(j + u) * O + o);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) best = fmaxf(best, f[u] * w[u]);
         }
-        out[((size_t)b * S + s) * ldo + o] = best;
-    } else {
-        for (int j = 0; j < k; ++j) (void)__shfl_sync(CAMLI_FULL_MASK, my, j);
     }
+    for (; j < k; ++j) {
+        const int ij = __shfl_sync(CAMLI_FULL_MASK, my, j);
+        if (o < O) best = fmaxf(best, __ldg(fb + (size_t)ij * ldf + o) * __ldcs(wp + (size_t)j * O + o));
+    }
+    if (o < O) out[((size_t)b * S + s) * ldo + o] = best;
 }
 
 }  // namespace

@@ -8,9 +8,13 @@ from . import native
 
 
 class FlowEngine:
-    def __init__(self, model, batch, height, width, n_points, device="cuda:0", use_graph=True, warmup=2):
+    def __init__(self, model, batch, height, width, n_points, device="cuda:0", use_graph=True, warmup=2,
+                 channels_last=True):
         self.device = torch.device(device)
         self.model = model.to(self.device).eval()
+        if channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
+            self.model.channels_last = True
         self.shape = (batch, height, width, n_points)
         mk = lambda *s: torch.zeros(*s, dtype=torch.float32)   # noqa: E731
         self.host_in = {"images": mk(batch, 6, height, width).pin_memory(), "pcs": mk(batch, 6, n_points).pin_memory(),

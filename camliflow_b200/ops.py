@@ -340,6 +340,55 @@ def clfm_interp(uv, nn_idx, feat3d_rows, score_net, H, W):
     return nchw_view(store)
 
 
+# ---------------------------------------------------------------- fused pointwise stages
+def sk_fusion_tail(a_rows, b_rows, negative_slope, w_mid, w_out):
+    """SKFusion after the align layers (models/clfm.py:199-214) on rows [B,P,C]: activation of the two
+    inputs (leaky, slope 1 = already activated), pooled mean, two bias-free FCs, pair softmax, blend."""
+    _need_cuda(a_rows, b_rows, w_mid, w_out)
+    _no_grad("sk_fusion_tail", a_rows, b_rows, w_mid, w_out)
+    assert a_rows.is_contiguous() and b_rows.is_contiguous() and a_rows.shape == b_rows.shape
+    B, P, C = a_rows.shape
+    Cm = w_mid.shape[0]
+    assert w_mid.shape == (Cm, C) and w_out.shape == (2 * C, Cm)
+    out = torch.empty_like(a_rows)
+    partial = torch.empty((B, 32, C), dtype=torch.float32, device=out.device)
+    weights = torch.empty((B, C, 2), dtype=torch.float32, device=out.device)
+    with torch.cuda.device(out.device):
+        native.call("camli_sk_fusion_tail", i32(B), i32(P), i32(C), i32(Cm), ptr(a_rows), ptr(b_rows),
+                    ctypes.c_float(negative_slope), ptr(w_mid.contiguous()), ptr(w_out.contiguous()), ptr(partial),
+                    ptr(weights), ptr(out), stream(), algo_bytes=B * P * C * 4 * 5)
+    return out
+
+
+def gru_gate(zr, h, x):
+    """ConvGRU gates (models/raft_core.py:125-128): zr [B,2H,..] pre-activation z|r, h [B,H,..], x [B,X,..]
+    (logical channel-first maps) -> z [B,H,..], rhx = [r*h | x] [B,H+X,..], NHWC storage."""
+    _need_cuda(zr, h, x)
+    _no_grad("gru_gate", zr, h, x)
+    B, Hc, Hh, Ww = h.shape
+    X = x.shape[1]
+    zr_r, h_r, x_r = nhwc_rows(zr), nhwc_rows(h), nhwc_rows(x)
+    z = torch.empty((B, Hh, Ww, Hc), dtype=torch.float32, device=h.device)
+    rhx = torch.empty((B, Hh, Ww, Hc + X), dtype=torch.float32, device=h.device)
+    rows = B * Hh * Ww
+    with torch.cuda.device(h.device):
+        native.call("camli_gru_gate", i64(rows), i32(Hc), i32(X), ptr(zr_r), ptr(h_r), ptr(x_r), ptr(z), ptr(rhx), stream(),
+                    algo_bytes=rows * (2 * Hc + Hc + X + Hc + Hc + X) * 4)
+    return nchw_view(z), nchw_view(rhx)
+
+
+def gru_update(z, h, q, fix_nonfinite=False):
+    """h' = (1-z)*h + z*tanh(q) (models/raft_core.py:129,136), optionally followed by nan_to_num (:138)."""
+    _need_cuda(z, h, q)
+    _no_grad("gru_update", z, h, q)
+    z_r, h_r, q_r = nhwc_rows(z), nhwc_rows(h), nhwc_rows(q)
+    out = torch.empty_like(h_r)
+    with torch.cuda.device(h.device):
+        native.call("camli_gru_update", i64(out.numel()), ptr(z_r), ptr(h_r), ptr(q_r), i32(1 if fix_nonfinite else 0),
+                    ptr(out), stream(), algo_bytes=out.numel() * 16)
+    return nchw_view(out)
+
+
 # ---------------------------------------------------------------- per-launch profiling (bench.py)
 def profile_begin():
     native.profile_begin()

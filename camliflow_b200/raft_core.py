@@ -104,7 +104,32 @@ class GRU2D(nn.Module):
         q = torch.tanh(convq(torch.cat([r * h, x], dim=1)))
         return (1 - z) * h + z * q
 
+    def _merged_zr(self, convz, convr):
+        """Weights of the z and r convolutions stacked into one 256-output convolution (they read the
+        same input); rebuilt only when a parameter changes."""
+        key = tuple((p.data_ptr(), p._version) for p in (convz.weight, convz.bias, convr.weight, convr.bias))
+        cache = self.__dict__.setdefault("_zr_cache", {})
+        hit = cache.get(id(convz))
+        if hit is None or hit[0] != key:
+            w = torch.cat([convz.weight, convr.weight], 0)
+            if convz.weight.is_contiguous(memory_format=torch.channels_last):
+                w = w.contiguous(memory_format=torch.channels_last)
+            hit = (key, w, torch.cat([convz.bias, convr.bias], 0))
+            cache[id(convz)] = hit
+        return hit[1], hit[2]
+
+    def _half_fused(self, h, x, convz, convr, convq, last):
+        """One merged z|r convolution, one gate kernel (sigmoids, r*h, [r*h | x] assembly), the q
+        convolution and one update kernel -- 5 launches instead of ~12."""
+        w, b = self._merged_zr(convz, convr)
+        zr = F.conv2d(torch.cat([h, x], dim=1), w, b, padding=convz.padding)
+        z, rhx = ops.gru_gate(zr, h, x)
+        return ops.gru_update(z, h, convq(rhx), fix_nonfinite=last)
+
     def forward(self, h, x):
+        if h.is_cuda and not (torch.is_grad_enabled() and (h.requires_grad or x.requires_grad or self.convz1.weight.requires_grad)):
+            h = self._half_fused(h, x, self.convz1, self.convr1, self.convq1, False)
+            return self._half_fused(h, x, self.convz2, self.convr2, self.convq2, True)
         h = self._half(h, x, self.convz1, self.convr1, self.convq1)
         h = self._half(h, x, self.convz2, self.convr2, self.convq2)
         return torch.nan_to_num(h)

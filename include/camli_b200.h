@@ -239,6 +239,33 @@ int64_t camli_allpairs_workspace_floats(int B, int M, int N, int K);
 int camli_allpairs_correlation(const float* a_rows, const float* b_rows, float* workspace, float* out,
                                int B, int M, int N, int K, float scale, void* stream);
 
+/*
+ * SK fusion tail (SKFusion.forward after the align layers, models/clfm.py:199-214):
+ *   a = leaky(a_rows), b = leaky(b_rows)   (negative_slope; 1 => inputs already activated)
+ *   w = softmax_pair(sigmoid(W_out relu(W_mid mean_p(a + b))))      [B,C,2]
+ *   out_rows = a * w[..,0] + b * w[..,1]
+ * a_rows, b_rows, out_rows [B,P,C] rows; w_mid [C_mid,C]; w_out [2C,C_mid];
+ * partial_scratch [B,32,C] and weights_scratch [B,C,2] f32 scratch.  Deterministic (no atomics).
+ */
+int camli_sk_fusion_tail(int B, int P, int C, int C_mid, const float* a_rows, const float* b_rows,
+                         float negative_slope, const float* w_mid, const float* w_out,
+                         float* partial_scratch, float* weights_scratch, float* out_rows, void* stream);
+
+/*
+ * ConvGRU gate stage (models/raft_core.py:125-128 / :132-135): zr [rows,2H] = pre-activation output
+ * of the merged z|r convolution, h [rows,H], x [rows,X] (all channel-last rows):
+ *   z = sigmoid(zr[:, :H]);  rhx = [ sigmoid(zr[:, H:]) * h | x ]   ([rows,H], [rows,H+X]).
+ */
+int camli_gru_gate(int64_t rows, int H, int X, const float* zr, const float* h, const float* x, float* z,
+                   float* rhx, void* stream);
+
+/*
+ * ConvGRU state update (models/raft_core.py:129,136-138): h_out = (1-z)*h + z*tanh(q) over n
+ * elements; fix_nonfinite != 0 additionally applies torch.nan_to_num.
+ */
+int camli_gru_update(int64_t n, const float* z, const float* h, const float* q, int fix_nonfinite,
+                     float* h_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

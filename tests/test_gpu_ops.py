@@ -207,3 +207,30 @@ def test_allpairs_tcgen05(dev, B, M, N, K):
     err_sgemm = (sgemm.double() - ref64).abs().max().item()
     print("allpairs %s: max err %.3e (fp32 SGEMM %.3e)" % ((B, M, N, K), err, err_sgemm))
     assert err <= max(4 * err_sgemm, 2e-6), (err, err_sgemm)
+
+
+@pytest.mark.parametrize("B,P,C", [(1, 8160, 324), (2, 2048, 128), (1, 100, 20)])
+def test_sk_fusion_tail(dev, B, P, C):
+    g = torch.Generator().manual_seed(17)
+    a, b = torch.randn(B, P, C, generator=g).to(dev), torch.randn(B, P, C, generator=g).to(dev)
+    w_mid = (torch.randn(C // 2, C, generator=g) * 0.2).to(dev)
+    w_out = (torch.randn(2 * C, C // 2, generator=g) * 0.2).to(dev)
+    for slope in (1.0, 0.1):
+        out = _ops().sk_fusion_tail(a, b, slope, w_mid, w_out)
+        _close(out, R.sk_fusion_tail(a, b, slope, w_mid, w_out), 2e-5, what="sk_fusion_tail")
+
+
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_gru_gates(dev, channels_last):
+    g = torch.Generator().manual_seed(18)
+    B, H, X, hh, ww = 2, 128, 256, 17, 30
+    zr, h, x, q = (torch.randn(B, c, hh, ww, generator=g).to(dev) for c in (2 * H, H, X, H))
+    if channels_last:
+        zr, h, x, q = (t.contiguous(memory_format=torch.channels_last) for t in (zr, h, x, q))
+    z, rhx = _ops().gru_gate(zr, h, x)
+    _close(z, torch.sigmoid(zr[:, :H]), 1e-6, what="gru z")
+    _close(rhx, torch.cat([torch.sigmoid(zr[:, H:]) * h, x], 1), 1e-6, what="gru rhx")
+    q[0, 0, 0, 0] = float("nan")
+    q[0, 1, 0, 0] = float("inf")
+    out = _ops().gru_update(z, h, q, fix_nonfinite=True)
+    _close(out, torch.nan_to_num((1 - z) * h + z * torch.tanh(q)), 1e-6, what="gru update")

@@ -110,3 +110,13 @@ def pointconv_group(xyz, feat, sampled_xyz, idx, W1, b1, W2, b2, slope):
     w = F.leaky_relu(F.conv2d(w, W2[:, :, None, None], b2), slope).transpose(1, 2)      # [B,S,16,k]
     g = gather_cf(torch.cat([xyz, feat], 1), idx).permute(0, 2, 3, 1)                   # [B,S,k,3+C]
     return torch.matmul(w, g).reshape(B, S, -1)
+
+
+def sk_fusion_tail(a, b, slope, w_mid, w_out):
+    """models/clfm.py:199-214 on rows [B,P,C]."""
+    a, b = F.leaky_relu(a, slope), F.leaky_relu(b, slope)
+    B, P, C = a.shape
+    w = (a + b).mean(1)
+    w = torch.sigmoid(F.linear(F.relu(F.linear(w, w_mid)), w_out)).view(B, C, 2)
+    w = torch.softmax(w, -1)
+    return a * w[:, None, :, 0] + b * w[:, None, :, 1]
