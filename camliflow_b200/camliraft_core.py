@@ -32,15 +32,23 @@ class CamLiRAFT_Core(nn.Module):
         # Inference only needs the last refinement; the reference also materialises the
         # up-sampled prediction of every earlier iteration (needed by the training loss).
         self.all_predictions = None   # None: follow self.training
+        self.two_streams = True       # overlap the image and the point branch on two CUDA streams (inference)
 
     def forward(self, image1, image2, pc1, pc2, camera_info):
         cfgs, b2, b3 = self.cfgs, self.branch_2d, self.branch_3d
-        xyzs1, xyzs2, _, _ = build_pc_pyramid(pc1, pc2, [4096, 2048, 1024, 512, 256])
+        par = _TwoStreams(self.two_streams and image1.is_cuda and not torch.is_grad_enabled())
 
-        feat1_2d, feat2_2d, featc_2d = b2.fnet(image1), b2.fnet(image2), b2.cnet(image1)
-        feat1_3d = b3.fnet(xyzs1[:3])[2]
-        feat2_3d = b3.fnet(xyzs2[:3])[2]
-        featc_3d = b3.cnet(xyzs1[:3])[2]
+        # ---- encoders: the image branch and the point branch (FPS pyramid + PointConv encoders) are
+        # independent until the first fusion site
+        def encode_2d():
+            return b2.fnet(image1), b2.fnet(image2), b2.cnet(image1)
+
+        def encode_3d():
+            xyzs1, xyzs2, _, _ = build_pc_pyramid(pc1, pc2, [4096, 2048, 1024, 512, 256])
+            feats = b3.fnet(xyzs1[:3])[2], b3.fnet(xyzs2[:3])[2], b3.cnet(xyzs1[:3])[2]
+            return xyzs1, xyzs2, [ops.rows_of(f) for f in feats]      # channel-last point features from here on
+
+        (feat1_2d, feat2_2d, featc_2d), (xyzs1, xyzs2, (feat1_3d, feat2_3d, featc_3d)) = par.run(encode_2d, encode_3d)
 
         xyzs1, xyzs2 = xyzs1[2:], xyzs2[2:]        # working pyramid 2048 / 1024 / 512 / 256
         xyz1, xyz2 = xyzs1[0], xyzs2[0]
@@ -53,25 +61,27 @@ class CamLiRAFT_Core(nn.Module):
         uv1 = torch.stack([uv1[:, 0] * sx, uv1[:, 1] * sy], dim=1)
         uv2 = torch.stack([uv2[:, 0] * sx, uv2[:, 1] * sy], dim=1)
 
-        # channel-last point features from here on; pixel -> nearest projected point tables are
-        # computed once per cloud (the reference repeats the search at every fusion site and iteration)
-        feat1_3d, feat2_3d, featc_3d = ops.rows_of(feat1_3d), ops.rows_of(feat2_3d), ops.rows_of(featc_3d)
+        # pixel -> nearest projected point tables, computed once per cloud (the reference repeats the
+        # search at every fusion site and iteration)
         nn1 = ops.nearest_point_2d(uv1, fh, fw)
         if cfgs.fuse_fnet:
             nn2 = ops.nearest_point_2d(uv2, fh, fw)
-            feat1_2d, feat1_3d = self.clfm_fnet.forward_rows(uv1, feat1_2d, feat1_3d, nn1)
-            feat2_2d, feat2_3d = self.clfm_fnet.forward_rows(uv2, feat2_2d, feat2_3d, nn2)
+            feat1_2d, feat1_3d = self.clfm_fnet.forward_rows(uv1, feat1_2d, feat1_3d, nn1, par)
+            feat2_2d, feat2_3d = self.clfm_fnet.forward_rows(uv2, feat2_2d, feat2_3d, nn2, par)
         if cfgs.fuse_cnet:
-            featc_2d, featc_3d = self.clfm_cnet.forward_rows(uv1, featc_2d, featc_3d, nn1)
+            featc_2d, featc_3d = self.clfm_cnet.forward_rows(uv1, featc_2d, featc_3d, nn1, par)
 
-        h_2d, x_2d = torch.split(b2.cnet_aligner(featc_2d), [128, 128], dim=1)
-        h_2d, x_2d = torch.tanh(h_2d), torch.relu(x_2d)
-        hx_3d = F.linear(featc_3d, b3.cnet_aligner.weight.flatten(1), b3.cnet_aligner.bias)
-        h_3d, x_3d = torch.tanh(hx_3d[..., :128]), torch.relu(hx_3d[..., 128:])
+        def init_2d():
+            h, x = torch.split(b2.cnet_aligner(featc_2d), [128, 128], dim=1)
+            b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
+            return torch.tanh(h), torch.relu(x)
 
-        b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
-        b3.correlation.build_cost_volume_pyramid(ops.cf_of(feat1_3d), ops.cf_of(feat2_3d), xyzs2)
-        nbr = k_nearest_neighbor(xyz1, xyz1, k=32)
+        def init_3d():
+            hx = F.linear(featc_3d, b3.cnet_aligner.weight.flatten(1), b3.cnet_aligner.bias)
+            b3.correlation.build_cost_volume_pyramid(ops.cf_of(feat1_3d), ops.cf_of(feat2_3d), xyzs2)
+            return torch.tanh(hx[..., :128]), torch.relu(hx[..., 128:]), k_nearest_neighbor(xyz1, xyz1, k=32)
+
+        (h_2d, x_2d), (h_3d, x_3d, nbr) = par.run(init_2d, init_3d)
 
         n_iters = cfgs.n_iters_train if self.training else cfgs.n_iters_eval
         every = self.training if self.all_predictions is None else self.all_predictions
@@ -79,32 +89,78 @@ class CamLiRAFT_Core(nn.Module):
         grid = mesh_grid(B, H // 8, W // 8, device=image1.device)
         flow_2d = torch.zeros_like(grid)
         flow_3d = torch.zeros_like(xyz1)
-        xyzs2_warp = xyzs2
         dw_cache = {}                  # iteration-invariant WeightNet outputs of the PointConvDW layers
         preds_2d, preds_3d = [], []
         for it in range(n_iters):
             if it > 0:
                 flow_2d, flow_3d = flow_2d.detach(), flow_3d.detach()
-                xyzs2_warp = warp_pyramid(xyz1, xyzs2, flow_3d)
 
-            corr_2d = b2.correlation(grid + flow_2d)
-            corr_3d = b3.correlation.forward_rows(xyz1, xyzs2_warp)
+            def corr_3d_fn():
+                warped = warp_pyramid(xyz1, xyzs2, flow_3d) if it > 0 else xyzs2
+                return b3.correlation.forward_rows(xyz1, warped)
+
+            corr_2d, corr_3d = par.run(lambda: b2.correlation(grid + flow_2d), corr_3d_fn)
             if cfgs.fuse_corr:
-                corr_2d, corr_3d = self.clfm_corr.forward_rows(uv1, corr_2d, corr_3d, nn1)
+                corr_2d, corr_3d = self.clfm_corr.forward_rows(uv1, corr_2d, corr_3d, nn1, par)
 
-            motion_2d = b2.motion_encoder(flow_2d, corr_2d)
-            motion_3d = b3.motion_encoder.forward_rows(xyz1, ops.rows_of(flow_3d), corr_3d, nbr, dw_cache)
+            motion_2d, motion_3d = par.run(
+                lambda: b2.motion_encoder(flow_2d, corr_2d),
+                lambda: b3.motion_encoder.forward_rows(xyz1, ops.rows_of(flow_3d), corr_3d, nbr, dw_cache))
             if cfgs.fuse_motion:
-                motion_2d, motion_3d = self.clfm_motion.forward_rows(uv1, motion_2d, motion_3d, nn1)
+                motion_2d, motion_3d = self.clfm_motion.forward_rows(uv1, motion_2d, motion_3d, nn1, par)
 
-            h_2d = b2.gru(h=h_2d, x=torch.cat([x_2d, motion_2d], dim=1))
-            h_3d = b3.gru.forward_rows(xyz1, h_3d, torch.cat([x_3d, motion_3d], dim=-1), nbr, dw_cache)
-            if cfgs.fuse_hidden:
-                h_2d, h_3d = self.clfm_hidden.forward_rows(uv1, h_2d, h_3d, nn1)
+            last = every or it == n_iters - 1
 
-            flow_2d = flow_2d + b2.flow_head(h_2d)
-            flow_3d = flow_3d + ops.cf_of(b3.flow_head.forward_rows(xyz1, h_3d, nbr, dw_cache))
-            if every or it == n_iters - 1:
-                preds_2d.append(b2.convex_upsampler(h_2d, flow_2d))
-                preds_3d.append(knn_interpolation(xyz1, flow_3d, pc1, k=3))
+            def update_2d():
+                h = b2.gru(h=h_2d, x=torch.cat([x_2d, motion_2d], dim=1))
+                flow = flow_2d + b2.flow_head(h)
+                return h, flow, (b2.convex_upsampler(h, flow) if last and not cfgs.fuse_hidden else None)
+
+            def update_3d():
+                h = b3.gru.forward_rows(xyz1, h_3d, torch.cat([x_3d, motion_3d], dim=-1), nbr, dw_cache)
+                if cfgs.fuse_hidden:
+                    return h, None, None
+                flow = flow_3d + ops.cf_of(b3.flow_head.forward_rows(xyz1, h, nbr, dw_cache))
+                return h, flow, (knn_interpolation(xyz1, flow, pc1, k=3) if last else None)
+
+            if cfgs.fuse_hidden:       # hidden-state fusion sits between the GRUs and the flow heads
+                h_2d, h_3d = b2.gru(h=h_2d, x=torch.cat([x_2d, motion_2d], dim=1)), update_3d()[0]
+                h_2d, h_3d = self.clfm_hidden.forward_rows(uv1, h_2d, h_3d, nn1, par)
+                flow_2d = flow_2d + b2.flow_head(h_2d)
+                flow_3d = flow_3d + ops.cf_of(b3.flow_head.forward_rows(xyz1, h_3d, nbr, dw_cache))
+                up_2d = b2.convex_upsampler(h_2d, flow_2d) if last else None
+                up_3d = knn_interpolation(xyz1, flow_3d, pc1, k=3) if last else None
+            else:
+                (h_2d, flow_2d, up_2d), (h_3d, flow_3d, up_3d) = par.run(update_2d, update_3d)
+            if last:
+                preds_2d.append(up_2d)
+                preds_3d.append(up_3d)
         return preds_2d, preds_3d
+
+
+class _TwoStreams:
+    """Runs two independent pieces of the forward concurrently: the first on the current stream,
+    the second on a side stream, joined before returning (fork/join is graph-capturable).  At batch 1
+    every kernel of the update block is far too small to fill 148 SMs, so overlapping the image and
+    the point branch is worth more than any single-kernel optimisation.  Tensors that cross streams
+    are kept referenced by the caller until after the join, which is what the caching allocator needs."""
+    _side = {}
+
+    def __init__(self, enabled):
+        self.enabled = enabled
+        if enabled:
+            dev = torch.cuda.current_device()
+            if dev not in _TwoStreams._side:
+                _TwoStreams._side[dev] = torch.cuda.Stream(dev)
+            self.side = _TwoStreams._side[dev]
+
+    def run(self, fn_main, fn_side):
+        if not self.enabled:
+            return fn_main(), fn_side()
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            b = fn_side()
+        a = fn_main()
+        main.wait_stream(self.side)
+        return a, b

@@ -95,11 +95,19 @@ class CLFM(nn.Module):
         out2d, out3d_rows = self.forward_rows(uv, feat_2d, ops.rows_of(feat_3d.float()), nn_idx)
         return out2d, ops.cf_of(out3d_rows)
 
-    def forward_rows(self, uv, feat_2d, feat3d_rows, nn_idx=None):
-        """Same with channel-last point features in and out."""
+    def forward_rows(self, uv, feat_2d, feat3d_rows, nn_idx=None, par=None):
+        """Same with channel-last point features in and out.  The two directions only read the
+        inputs, so `par` (a fork/join helper with .run(fn_a, fn_b)) may execute them concurrently."""
         feat_2d = feat_2d.float()
-        interp = self.interp.forward_rows(uv, feat_2d.shape[-2:], feat3d_rows.detach(), nn_idx)
-        out2d = self.fuse2d(feat_2d, interp)
-        sampled = ops.bilinear_sample_rows(feat_2d.detach(), uv)
-        out3d = self.fuse3d.forward_rows(self.mlps3d.forward_rows(sampled), feat3d_rows)
-        return out2d, out3d
+
+        def to_2d():
+            interp = self.interp.forward_rows(uv, feat_2d.shape[-2:], feat3d_rows.detach(), nn_idx)
+            return self.fuse2d(feat_2d, interp)
+
+        def to_3d():
+            sampled = ops.bilinear_sample_rows(feat_2d.detach(), uv)
+            return self.fuse3d.forward_rows(self.mlps3d.forward_rows(sampled), feat3d_rows)
+
+        if par is None:
+            return to_2d(), to_3d()
+        return par.run(to_2d, to_3d)

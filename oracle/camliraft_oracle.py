@@ -25,6 +25,7 @@ Two index semantics are provided because the reference itself has two:
 """
 import json
 import os
+import re
 import zlib
 
 import numpy as np
@@ -40,14 +41,24 @@ def param_spec(model="camliraft"):
         return {k: tuple(v) for k, v in json.load(f).items()}
 
 
-FLOW_HEAD_LAST = ("flow_head.conv2.weight", "flow_head.fc.weight")
+DAMPING = {
+    # CamLiRAFT: last layer of each flow head
+    r"flow_head\.conv2\.weight$": 0.05, r"flow_head\.fc\.weight$": 0.05,
+    # CamLiPWC: un-normalised point-geometry features grow ~5x per PointConv level and ~100x through the
+    # learnable cost volume; keep activations O(1-10) and the coarse-to-fine flow updates small
+    r"conv_last\.weight$": 0.01,
+    r"branch_3d_fnet\.level0_mlp\.convs\.0\.conv_fn\.weight$": 0.1,
+    r"pyramid_convs\.\d\.linear\.weight$": 0.2, r"point_conv[12]\.linear\.weight$": 0.2,
+    r"weight_net[12]\.convs\.2\.conv_fn\.weight$": 0.1,
+}
 
 
 def make_params(spec, seed=0):
     """Deterministic weights keyed on the parameter NAME (independent of construction order):
     conv / linear weights ~ U(+-sqrt(3/fan_in)), biases ~ N(0, 0.05), norm scales ~ U(0.8, 1.2),
     running_mean ~ N(0, 0.1), running_var ~ U(0.5, 1.5).  The last layer of every flow head is
-    damped (x0.05) so that the recurrent refinement of a random-weight network stays in the
+    damped (x0.05 in CamLiRAFT, x0.002 for the `conv_last` layers of CamLiPWC, whose un-normalised
+    point-geometry features are O(100)) so that the recurrent refinement of a random-weight network stays in the
     contractive, small-flow regime a trained network works in (undamped, 12 iterations amplify
     a 1-ulp perturbation to whole pixels, which would make any parity tolerance meaningless)."""
     out = {}
@@ -68,8 +79,9 @@ def make_params(spec, seed=0):
         else:
             fan_in = int(np.prod(shape[1:]))
             t = (torch.rand(shape, generator=g) * 2 - 1) * (3.0 / fan_in) ** 0.5
-            if name.endswith(FLOW_HEAD_LAST):
-                t = t * 0.05
+            for pattern, gain in DAMPING.items():
+                if re.search(pattern, name):
+                    t = t * gain
         out[name] = t
     return out
 

@@ -29,8 +29,11 @@ def _folded(layers):
 
 @contextlib.contextmanager
 def cpu_kernels():
+    import camliflow_b200.camlipwc_core as pwc
+    import camliflow_b200.camlipwc_l_core as pwl
     import camliflow_b200.camliraft_core as cc
     import camliflow_b200.camliraft_l_core as cl
+    import camliflow_b200.pwc_core as pw2
     import camliflow_b200.ops as ops
     import camliflow_b200.point_conv as pc
     import camliflow_b200.utils as ut
@@ -68,6 +71,8 @@ def cpu_kernels():
         (ops, "clfm_interp"): lambda uv, nn, f, sn, H, W: R.clfm_interp(uv, nn, ops.cf_of(f), *_folded(sn), H, W),
         (ut, "k_nearest_neighbor"): _knn, (ut, "furthest_point_sampling"): _fps,
         (pc, "k_nearest_neighbor"): _knn, (cc, "k_nearest_neighbor"): _knn, (cl, "k_nearest_neighbor"): _knn,
+        (pwc, "k_nearest_neighbor"): _knn, (pwl, "k_nearest_neighbor"): _knn,
+        (pwc, "correlation2d"): R.correlation2d, (pw2, "correlation2d"): R.correlation2d,
     }
     saved = {key: getattr(*key) for key in patches}
     try:

@@ -34,7 +34,7 @@ def patch_indices(models, on):
     """Answer the reference's FPS / k-NN calls with the kernel-semantics C oracle."""
     import importlib
     mods = [importlib.import_module("models." + m) for m in
-            ("utils", "point_conv", "clfm", "camliraft_core", "camliraft_l_core")]
+            ("utils", "point_conv", "clfm", "camliraft_core", "camliraft_l_core", "camlipwc_core", "camlipwc_l_core")]
     wrapper = importlib.import_module("models.csrc.wrapper")
     if not on:
         for m in mods:
@@ -78,6 +78,23 @@ def main():
             out["%s_%s_flow3d" % (name, mode)] = f3[0, :, ::s3].numpy().astype(np.float32)
         patch_indices(models, False)
     np.savez_compressed(os.path.join(HERE, "model_camliraft.npz"), **out)
+
+    # ---- CamLiPWC (BASELINE config[2] shape; kernel index semantics only)
+    P = co.make_params(co.param_spec("camlipwc"), seed=0)
+    net = models.camlipwc.CamLiPWC(rh.camlipwc_cfg()).eval()
+    print("camlipwc", net.load_state_dict(P, strict=True))
+    out = {}
+    for name, (H, W, N, seed, s2, s3) in {"small": (128, 192, 8192, 21, 4, 4), "c3": (540, 960, 8192, 1, 8, 4)}.items():
+        inputs = co.synthetic_inputs(1, H, W, N, seed)
+        patch_indices(models, True)
+        with torch.no_grad():
+            res = net(inputs)
+        patch_indices(models, False)
+        f2, f3 = res["flow_2d"], res["flow_3d"]
+        print("camlipwc", name, tuple(f2.shape), tuple(f3.shape), float(f2.abs().mean()), float(f3.abs().mean()))
+        out["%s_kernel_flow2d" % name] = f2[0, :, ::s2, ::s2].numpy().astype(np.float32)
+        out["%s_kernel_flow3d" % name] = f3[0, :, ::s3].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "model_camlipwc.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -97,3 +97,37 @@ def test_bench_inputs_equal_oracle_inputs():
     from oracle import camliraft_oracle as co
     a, b = bench.synthetic_inputs(1, 64, 96, 5000, 3), co.synthetic_inputs(1, 64, 96, 5000, 3)
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def _pwc_model():
+    from camliflow_b200.camlipwc import CamLiPWC
+    from camliflow_b200.config import camlipwc_config
+    from camliflow_b200.init import seed_module_
+    return seed_module_(CamLiPWC(camlipwc_config()), seed=0).cuda().eval()
+
+
+@pytest.mark.parametrize("case,H,W,seed,s2", [("small", 128, 192, 21, 4), ("c3", 540, 960, 1, 8)])
+def test_camlipwc_vs_reference_golden(case, H, W, seed, s2):
+    """CamLiPWC (5-level PWC cost volume + PointPWC cost volume + CLFM) against the reference model's
+    golden output; c3 = BASELINE config[2] geometry (960x540 -> 576x960, 8192 points)."""
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    G = np.load(os.path.join(GOLDEN, "model_camlipwc.npz"))
+    inputs = co.synthetic_inputs(1, H, W, 8192, seed=seed)
+    f2, f3 = _run(_pwc_model(), inputs)
+    e2 = epe(f2[0, :, ::s2, ::s2].numpy(), G["%s_kernel_flow2d" % case])
+    e3 = epe(f3[0, :, ::4].numpy(), G["%s_kernel_flow3d" % case])
+    print("camlipwc %s vs reference golden: EPE2D %.3e EPE3D %.3e" % (case, e2, e3))
+    assert e2 <= TOL_EPE2D and e3 <= TOL_EPE3D, (e2, e3)
+
+
+def test_camlipwc_batch4():
+    """Config[2] runs batch 4: each sample of a batch equals its single-sample result."""
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    model = _pwc_model()
+    inputs = co.synthetic_inputs(4, 128, 192, 8192, seed=33)
+    f2, f3 = _run(model, inputs)
+    one = {k: v[2:3] for k, v in inputs.items()}
+    g2, g3 = _run(model, one)
+    assert epe(f2[2].numpy(), g2[0].numpy()) <= 1e-4 and epe(f3[2].numpy(), g3[0].numpy()) <= 1e-5

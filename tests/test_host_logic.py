@@ -71,3 +71,24 @@ def test_ops_refuse_cpu_tensors():
         ops.knn_interpolate(torch.rand(1, 3, 10), torch.rand(1, 3, 10), torch.rand(1, 3, 5))
     with pytest.raises(RuntimeError):
         ops.corr2d_lookup([torch.rand(1, 4, 2, 2)], torch.rand(1, 2, 2, 2), 4)
+
+
+def test_camlipwc_state_dict_and_graph_match_reference_golden():
+    """CamLiPWC (BASELINE config[2] model): reference state_dict names/shapes, and the product graph
+    (kernels answered by formulas) against the reference model's golden output."""
+    from camliflow_b200.camlipwc import CamLiPWC
+    from camliflow_b200.config import camlipwc_config
+    from camliflow_b200.init import seed_module_
+    net = seed_module_(CamLiPWC(camlipwc_config()), seed=0).eval()
+    spec = co.param_spec("camlipwc")
+    sd = net.state_dict()
+    assert set(sd) == set(spec) and all(tuple(sd[k].shape) == spec[k] for k in spec)
+    P = co.make_params(spec, seed=0)
+    assert all(torch.equal(sd[k], P[k]) for k in spec)
+    G = np.load(os.path.join(GOLDEN, "model_camlipwc.npz"))
+    inputs = co.synthetic_inputs(1, 128, 192, 8192, seed=21)
+    with cpu_kernels(), torch.no_grad():
+        out = net(inputs)
+    e2 = epe(out["flow_2d"][0, :, ::4, ::4].numpy(), G["small_kernel_flow2d"])
+    e3 = epe(out["flow_3d"][0, :, ::4].numpy(), G["small_kernel_flow3d"])
+    assert e2 <= 1e-3 and e3 <= 1e-4, (e2, e3)

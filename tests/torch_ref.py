@@ -120,3 +120,15 @@ def sk_fusion_tail(a, b, slope, w_mid, w_out):
     w = torch.sigmoid(F.linear(F.relu(F.linear(w, w_mid)), w_out)).view(B, C, 2)
     w = torch.softmax(w, -1)
     return a * w[:, None, :, 0] + b * w[:, None, :, 1]
+
+
+def correlation2d(input1, input2, max_displacement):
+    """models/csrc/wrapper.py:41-50 (the reference's own fallback): NCHW -> [B,(2d+1)^2,H,W]."""
+    H, W = input1.shape[2:]
+    d = max_displacement
+    padded = F.pad(input2, [d] * 4)
+    vols = []
+    for i in range(2 * d + 1):
+        for j in range(2 * d + 1):
+            vols.append(torch.mean(input1 * padded[:, :, i:i + H, j:j + W], 1, keepdim=True))
+    return torch.cat(vols, 1)
