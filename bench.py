@@ -113,6 +113,22 @@ def l2_flush(buf):
     buf.add_(1.0)
 
 
+def shard_seed(rank, base_seed=0):
+    """Every rank owns its own frame pairs (weak scaling over independent pairs): the generator seed
+    of rank r's shard."""
+    return base_seed + rank
+
+
+def max_over_ranks(ms, world, device=None):
+    """Device-timed milliseconds, reduced with MAX over the ranks (identity for one rank)."""
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from camliflow_b200 import native, ops
@@ -127,7 +143,7 @@ def run_ours(args, rank, world, local_rank):
     torch.backends.cudnn.benchmark = True
     model = seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=iters)), seed=0)
     engine = FlowEngine(model, B, H, W, N, device=dev, use_graph=not args.no_graph)
-    inputs = synthetic_inputs(B, H, W, N, seed=rank)          # per-rank shard of the batch of pairs
+    inputs = synthetic_inputs(B, H, W, N, seed=shard_seed(rank))   # per-rank shard of the batch of pairs
     pinned = {k: v.pin_memory() for k, v in inputs.items()}
     flush = torch.zeros(192 * 1024 * 1024 // 4, device=dev)   # 192 MiB > 126 MB L2
 
@@ -150,12 +166,7 @@ def run_ours(args, rank, world, local_rank):
                 e.record(engine.stream)
                 evs.append((s, e))
         barrier()
-        ms = sum(s.elapsed_time(e) for s, e in evs)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks(sum(s.elapsed_time(e) for s, e in evs), world, dev)
 
     engine.load(pinned)
     sampler = ClockSampler(local_rank)
