@@ -141,6 +141,9 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
+    strict = args.conv_precision == "fp32"
+    torch.backends.cudnn.allow_tf32 = not strict
+    torch.backends.cuda.matmul.allow_tf32 = False      # GEMMs (1x1 layers, Linear) are always fp32
     model = seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=iters)), seed=0)
     engine = FlowEngine(model, B, H, W, N, device=dev, use_graph=not args.no_graph)
     inputs = synthetic_inputs(B, H, W, N, seed=shard_seed(rank))   # per-rank shard of the batch of pairs
@@ -197,7 +200,8 @@ def run_ours(args, rank, world, local_rank):
                                % (args.workload, W, H, N, iters, B),
                    "pairs_per_step": pairs, "cuda_graph": engine.graph is not None,
                    "l2": "192 MiB flush write before every timed step (outside the event pair)",
-                   "conv_precision": "cuDNN default (TF32 allowed, as torch default in the reference)",
+                   "conv_precision": ("fp32 (cudnn.allow_tf32=False: the mode the parity tests run in)" if strict else
+                                      "cuDNN default (TF32 allowed, as torch default in the reference)"),
                    "intermediate_predictions": False},
         "e2e": {"value": pairs * args.steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -216,6 +220,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--conv-precision", default="fp32", choices=["fp32", "tf32"],
+                    help="fp32: cuDNN convolutions in strict fp32, the mode the EPE parity tests run in (default); "
+                         "tf32: torch's default (cudnn.allow_tf32=True), what the reference gets out of the box")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

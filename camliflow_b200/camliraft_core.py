@@ -41,7 +41,10 @@ class CamLiRAFT_Core(nn.Module):
         # ---- encoders: the image branch and the point branch (FPS pyramid + PointConv encoders) are
         # independent until the first fusion site
         def encode_2d():
-            return b2.fnet(image1), b2.fnet(image2), b2.cnet(image1)
+            # both frames through the feature encoder as one batch (its BatchNorms use running statistics,
+            # so samples stay independent)
+            f12 = b2.fnet(torch.cat([image1, image2], dim=0))
+            return f12[:image1.shape[0]], f12[image1.shape[0]:], b2.cnet(image1)
 
         def encode_3d():
             xyzs1, xyzs2, _, _ = build_pc_pyramid(pc1, pc2, [4096, 2048, 1024, 512, 256])

@@ -71,8 +71,10 @@ bilinear_sample_rows_kernel(int H, int W, int N, int C, const float* __restrict_
     const int b = blockIdx.y;
     float x = __ldg(uv + ((size_t)b * 2 + 0) * N + n), y = __ldg(uv + ((size_t)b * 2 + 1) * N + n);
     // grid_sample round trip of utils.py:262-267: normalise to [-1,1], then un-normalise (align_corners)
-    x = ((2.0f * x / (float)(W - 1) - 1.0f) + 1.f) * 0.5f * (float)(W - 1);
-    y = ((2.0f * y / (float)(H - 1) - 1.0f) + 1.f) * 0.5f * (float)(H - 1);
+    // (torch divides a CUDA tensor by a host scalar as a multiplication by its fp32 reciprocal, and every
+    // step of the reference is a separately rounded elementwise kernel: no FMA contraction here)
+    x = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(2.0f * x, __frcp_rn((float)(W - 1))), 1.0f), 1.f), 0.5f), (float)(W - 1));
+    y = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(2.0f * y, __frcp_rn((float)(H - 1))), 1.0f), 1.f), 0.5f), (float)(H - 1));
     x = fminf(fmaxf(x, -2.f), (float)W + 1.f);
     y = fminf(fmaxf(y, -2.f), (float)H + 1.f);
     const float xf = floorf(x), yf = floorf(y);

@@ -41,39 +41,50 @@ sk_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int 
     }
 }
 
-// one CTA per sample: pooled mean -> fc_mid (ReLU) -> fc_out (sigmoid) -> softmax over pairs
+// The two tiny FCs are latency-bound when one CTA walks the whole weight matrix (420 KB for the
+// 324-channel correlation CLFM), so each gets a grid of its own: one warp per output row.
+//
+// mid[b, j] = relu( <w_mid[j, :], pooled[b, :]> ),  pooled = sum of the partial slices / P
 __global__ void __launch_bounds__(256)
-sk_weights_kernel(const float* __restrict__ partial, int P, int C, int Cm,
-                  const float* __restrict__ w_mid,    // [Cm, C]
-                  const float* __restrict__ w_out,    // [2C, Cm]
-                  float* __restrict__ weights) {      // [B, C, 2]
-    extern __shared__ float s_buf[];                  // pooled [C], mid [Cm], logits [2C]
-    float* s_pool = s_buf;
-    float* s_mid = s_buf + C;
-    float* s_out = s_mid + Cm;
-    const int bi = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+sk_mid_kernel(const float* __restrict__ partial, int P, int C, int Cm, const float* __restrict__ w_mid,   // [Cm, C]
+              float* __restrict__ mid) {                                                                  // [B, Cm]
+    extern __shared__ float s_pool[];                 // [C]
+    const int bi = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inv_p = 1.f / (float)P;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float t = 0.f;
-        for (int s = 0; s < SK_SPLITS; ++s) t += partial[((size_t)bi * SK_SPLITS + s) * C + c];
-        s_pool[c] = t / (float)P;
+#pragma unroll 8
+        for (int s = 0; s < SK_SPLITS; ++s) t += __ldg(partial + ((size_t)bi * SK_SPLITS + s) * C + c);
+        s_pool[c] = t * inv_p;
     }
     __syncthreads();
-    for (int j = warp; j < Cm; j += 8) {
-        float t = 0.f;
-        for (int c = lane; c < C; c += 32) t = fmaf(__ldg(w_mid + (size_t)j * C + c), s_pool[c], t);
-        t = camli_warp_sum(t);
-        if (lane == 0) s_mid[j] = fmaxf(t, 0.f);
-    }
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= Cm) return;
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t = fmaf(__ldg(w_mid + (size_t)j * C + c), s_pool[c], t);
+    t = camli_warp_sum(t);
+    if (lane == 0) mid[(size_t)bi * Cm + j] = fmaxf(t, 0.f);
+}
+
+// weights[b, c, :] = softmax( sigmoid(<w_out[2c, :], mid>), sigmoid(<w_out[2c+1, :], mid>) )
+__global__ void __launch_bounds__(256)
+sk_out_kernel(const float* __restrict__ mid, int C, int Cm, const float* __restrict__ w_out,   // [2C, Cm]
+              float* __restrict__ weights) {                                                   // [B, C, 2]
+    extern __shared__ float s_mid[];                  // [Cm]
+    const int bi = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = threadIdx.x; j < Cm; j += blockDim.x) s_mid[j] = __ldg(mid + (size_t)bi * Cm + j);
     __syncthreads();
-    for (int o = warp; o < 2 * C; o += 8) {
-        float t = 0.f;
-        for (int j = lane; j < Cm; j += 32) t = fmaf(__ldg(w_out + (size_t)o * Cm + j), s_mid[j], t);
-        t = camli_warp_sum(t);
-        if (lane == 0) s_out[o] = 1.f / (1.f + expf(-t));
+    const int c = blockIdx.x * 8 + warp;
+    if (c >= C) return;
+    float tu = 0.f, tv = 0.f;
+    for (int j = lane; j < Cm; j += 32) {
+        tu = fmaf(__ldg(w_out + (size_t)(2 * c) * Cm + j), s_mid[j], tu);
+        tv = fmaf(__ldg(w_out + (size_t)(2 * c + 1) * Cm + j), s_mid[j], tv);
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float u = s_out[2 * c], v = s_out[2 * c + 1];
+    tu = camli_warp_sum(tu);
+    tv = camli_warp_sum(tv);
+    if (lane == 0) {
+        const float u = 1.f / (1.f + expf(-tu)), v = 1.f / (1.f + expf(-tv));
         const float m = fmaxf(u, v);
         const float eu = expf(u - m), ev = expf(v - m);
         const float inv = 1.f / (eu + ev);
@@ -82,16 +93,30 @@ sk_weights_kernel(const float* __restrict__ partial, int P, int C, int Cm,
     }
 }
 
-// out = leaky(a) * w[b,c,0] + leaky(b) * w[b,c,1]
+// out = leaky(a) * w[b,c,0] + leaky(b) * w[b,c,1]; VEC = 4 when C % 4 == 0 (128-bit accesses)
+template <int VEC>
 __global__ void __launch_bounds__(256)
 sk_blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ weights,
                 size_t PC, int C, float slope, float* __restrict__ out) {
     const int bi = blockIdx.y;
-    const float* w = weights + (size_t)bi * C * 2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < PC; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const size_t g = (size_t)bi * PC + i;
-        out[g] = camli_leaky(__ldg(a + g), slope) * __ldg(w + 2 * c) + camli_leaky(__ldg(b + g), slope) * __ldg(w + 2 * c + 1);
+    const float2* w = reinterpret_cast<const float2*>(weights) + (size_t)bi * C;
+    const size_t nv = PC / VEC;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)((i * VEC) % C);
+        const size_t g = (size_t)bi * PC + i * VEC;
+        if (VEC == 4) {
+            const float4 av = __ldcs(reinterpret_cast<const float4*>(a + g)), bv = __ldcs(reinterpret_cast<const float4*>(b + g));
+            const float2 w0 = __ldg(w + c), w1 = __ldg(w + c + 1), w2 = __ldg(w + c + 2), w3 = __ldg(w + c + 3);
+            float4 o;
+            o.x = camli_leaky(av.x, slope) * w0.x + camli_leaky(bv.x, slope) * w0.y;
+            o.y = camli_leaky(av.y, slope) * w1.x + camli_leaky(bv.y, slope) * w1.y;
+            o.z = camli_leaky(av.z, slope) * w2.x + camli_leaky(bv.z, slope) * w2.y;
+            o.w = camli_leaky(av.w, slope) * w3.x + camli_leaky(bv.w, slope) * w3.y;
+            *reinterpret_cast<float4*>(out + g) = o;
+        } else {
+            const float2 w0 = __ldg(w + c);
+            out[g] = camli_leaky(__ldg(a + g), slope) * w0.x + camli_leaky(__ldg(b + g), slope) * w0.y;
+        }
     }
 }
 
@@ -142,20 +167,21 @@ extern "C" int camli_sk_fusion_tail(int B, int P, int C, int C_mid, const float*
                                     float negative_slope, const float* w_mid, const float* w_out,
                                     float* partial_scratch, float* weights_scratch, float* out_rows, void* stream) {
     if (B < 0 || P < 1 || C < 1 || C_mid < 1) return CAMLI_EINVAL;
-    if (B > 65535 || (size_t)(3 * C + C_mid) * sizeof(float) > 200 * 1024) return CAMLI_EUNSUPPORTED;
+    if (B > 65535 || (size_t)(C > C_mid ? C : C_mid) * sizeof(float) > 48 * 1024) return CAMLI_EUNSUPPORTED;
     if (B == 0) return CAMLI_OK;
     if (!a_rows || !b_rows || !w_mid || !w_out || !partial_scratch || !weights_scratch || !out_rows) return CAMLI_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     sk_partial_kernel<<<dim3(camli_div_up(C, 32), SK_SPLITS, B), 256, 0, st>>>(a_rows, b_rows, P, C, negative_slope,
                                                                             partial_scratch);
-    const size_t smem = (size_t)(3 * C + C_mid) * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sk_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    sk_weights_kernel<<<B, 256, smem, st>>>(partial_scratch, P, C, C_mid, w_mid, w_out, weights_scratch);
+    // weights_scratch: [B, C, 2] blend weights followed by the [B, C_mid] hidden layer
+    float* mid = weights_scratch + (size_t)B * C * 2;
+    sk_mid_kernel<<<dim3(camli_div_up(C_mid, 8), B), 256, (size_t)C * sizeof(float), st>>>(partial_scratch, P, C, C_mid, w_mid, mid);
+    sk_out_kernel<<<dim3(camli_div_up(C, 8), B), 256, (size_t)C_mid * sizeof(float), st>>>(mid, C, C_mid, w_out, weights_scratch);
     const size_t PC = (size_t)P * C;
-    sk_blend_kernel<<<dim3(grid_for(PC), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows);
+    const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(a_rows) | reinterpret_cast<uintptr_t>(b_rows) |
+                                       reinterpret_cast<uintptr_t>(out_rows)) % 16 == 0);
+    if (vec) sk_blend_kernel<4><<<dim3(grid_for(PC / 4), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows);
+    else     sk_blend_kernel<1><<<dim3(grid_for(PC), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows);
     CAMLI_RETURN_LAUNCH_STATUS();
 }
 

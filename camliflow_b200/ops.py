@@ -352,7 +352,7 @@ def sk_fusion_tail(a_rows, b_rows, negative_slope, w_mid, w_out):
     assert w_mid.shape == (Cm, C) and w_out.shape == (2 * C, Cm)
     out = torch.empty_like(a_rows)
     partial = torch.empty((B, 32, C), dtype=torch.float32, device=out.device)
-    weights = torch.empty((B, C, 2), dtype=torch.float32, device=out.device)
+    weights = torch.empty((B * (2 * C + Cm),), dtype=torch.float32, device=out.device)
     with torch.cuda.device(out.device):
         native.call("camli_sk_fusion_tail", i32(B), i32(P), i32(C), i32(Cm), ptr(a_rows), ptr(b_rows),
                     ctypes.c_float(negative_slope), ptr(w_mid.contiguous()), ptr(w_out.contiguous()), ptr(partial),

@@ -14,6 +14,30 @@ from .mlp import Conv2dNormRelu
 from .utils import convex_upsample, mesh_grid
 
 
+def _folded(owner, name, conv, bn):
+    """(weight, bias) of `conv` followed by an eval-mode BatchNorm, folded once and cached on `owner`
+    (rebuilt when a parameter changes).  Inference only."""
+    key = tuple((p.data_ptr(), p._version) for p in (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var))
+    cache = owner.__dict__.setdefault("_fold_cache", {})
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = conv.weight * scale[:, None, None, None]
+            if conv.weight.is_contiguous(memory_format=torch.channels_last):
+                w = w.contiguous(memory_format=torch.channels_last)
+            hit = (key, w, (bn.bias - bn.running_mean * scale).contiguous())
+        cache[name] = hit
+    return hit[1], hit[2]
+
+
+def _fused_inference(x):
+    """The encoder's BatchNorms always run on their running statistics (norm_eval), so without autograd
+    every conv+BN(+residual)+ReLU group is ONE cuDNN call with a bias / add / ReLU epilogue instead of
+    conv, batch-norm, add and ReLU kernels (the BN pass alone re-read and re-wrote every activation)."""
+    return x.is_cuda and not torch.is_grad_enabled()
+
+
 class _Bottleneck(nn.Module):
     def __init__(self, c_in, c_mid, stride):
         super().__init__()
@@ -28,7 +52,19 @@ class _Bottleneck(nn.Module):
         if stride != 1 or c_in != c_out:
             self.downsample = nn.Sequential(nn.Conv2d(c_in, c_out, 1, stride, bias=False), nn.BatchNorm2d(c_out))
 
+    def _forward_fused(self, x):
+        one, zero = (1, 1), (0, 0)
+        y = torch.cudnn_convolution_relu(x, *_folded(self, "1", self.conv1, self.bn1), one, zero, one, 1)
+        y = torch.cudnn_convolution_relu(y, *_folded(self, "2", self.conv2, self.bn2), self.conv2.stride, one, one, 1)
+        if self.downsample is not None:
+            w, b = _folded(self, "d", self.downsample[0], self.downsample[1])
+            x = F.conv2d(x, w, b, self.downsample[0].stride)
+        w, b = _folded(self, "3", self.conv3, self.bn3)
+        return torch.cudnn_convolution_add_relu(y, w, x, 1.0, b, one, zero, one, 1)
+
     def forward(self, x):
+        if _fused_inference(x):
+            return self._forward_fused(x)
         y = F.relu(self.bn1(self.conv1(x)), inplace=True)
         y = F.relu(self.bn2(self.conv2(y)), inplace=True)
         y = self.bn3(self.conv3(y))
@@ -60,7 +96,11 @@ class Encoder2D(nn.Module):
         return self
 
     def forward(self, x):
-        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x)), inplace=True), 3, 2, 1)
+        if _fused_inference(x):
+            x = torch.cudnn_convolution_relu(x, *_folded(self, "stem", self.conv1, self.bn1), (2, 2), (3, 3), (1, 1), 1)
+        else:
+            x = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        x = F.max_pool2d(x, 3, 2, 1)
         return self.align(self.layer2(self.layer1(x)))
 
 

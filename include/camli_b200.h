@@ -245,7 +245,8 @@ int camli_allpairs_correlation(const float* a_rows, const float* b_rows, float* 
  *   w = softmax_pair(sigmoid(W_out relu(W_mid mean_p(a + b))))      [B,C,2]
  *   out_rows = a * w[..,0] + b * w[..,1]
  * a_rows, b_rows, out_rows [B,P,C] rows; w_mid [C_mid,C]; w_out [2C,C_mid];
- * partial_scratch [B,32,C] and weights_scratch [B,C,2] f32 scratch.  Deterministic (no atomics).
+ * partial_scratch [B,32,C] and weights_scratch [B, 2*C + C_mid] f32 scratch (the [B,C,2] blend weights, then the
+ * hidden layer).  Deterministic (no atomics).
  */
 int camli_sk_fusion_tail(int B, int P, int C, int C_mid, const float* a_rows, const float* b_rows,
                          float negative_slope, const float* w_mid, const float* w_out,

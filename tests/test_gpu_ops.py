@@ -234,3 +234,28 @@ def test_gru_gates(dev, channels_last):
     q[0, 1, 0, 0] = float("inf")
     out = _ops().gru_update(z, h, q, fix_nonfinite=True)
     _close(out, torch.nan_to_num((1 - z) * h + z * torch.tanh(q)), 1e-6, what="gru update")
+
+
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_encoder2d_fused_epilogues(dev, channels_last):
+    """Inference path of Encoder2D (BatchNorm folded, conv+bias(+residual)+ReLU as single cuDNN calls)
+    against the module-by-module path autograd uses (conv, BatchNorm, add, ReLU)."""
+    from camliflow_b200.raft_core import Encoder2D
+    g = torch.Generator().manual_seed(21)
+    enc = Encoder2D().eval()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    enc = enc.to(dev)
+    x = torch.randn(2, 3, 96, 128, generator=g).to(dev)
+    if channels_last:
+        enc, x = enc.to(memory_format=torch.channels_last), x.contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        fused = enc(x)
+    with torch.enable_grad():
+        plain = enc(x).detach()
+    scale = plain.abs().max().item()
+    _close(fused, plain, 2e-5 * max(scale, 1.0), rtol=1e-4, what="Encoder2D fused epilogues")
