@@ -244,6 +244,142 @@ fps_cluster_kernel(const float* __restrict__ xyz_all, int N, int S, int64_t* __r
     cluster.sync();                                               // no CTA exits while peers may still store to it
 }
 
+// ---------------------------------------------------------------------------------------------
+// Async-exchange cluster path (default for 2048 < N <= 16384).  Same partition of one cloud over an
+// 8-CTA cluster, but the per-round exchange costs one remote store instead of a shared-memory hop,
+// a CTA barrier, a DSMEM store and a cluster barrier (~380 cycles + an L1 flush each round):
+//   * every CTA keeps the WHOLE cloud in its shared memory (SoA, 12 B/point), so a record is just
+//     the 64-bit key (distance bits, tie key) -- the winner's coordinates are a local LDS;
+//   * every WARP reduces its points with two redux.sync and lanes 0..7 push the warp's key straight
+//     into the 8 CTAs' record tables with `st.async ... mbarrier::complete_tx` -- the store itself
+//     signals the destination's mbarrier, so there is no barrier instruction in the loop at all;
+//   * every warp then waits on its own CTA's mbarrier (64 records x 8 B expected per round) and
+//     picks the global winner from the 64 records (2 per lane + two redux.sync).
+// Tables and mbarriers are double-buffered by round parity.  A CTA can run at most one round ahead
+// of its peers (it needs all of round s's records to produce round s+1's), and a peer only sends
+// round s+1 after it consumed round s-1's table, so the parity buffer is always free when written.
+constexpr int FPSA_CTAS = 8;
+constexpr int FPSA_THREADS = 256;
+constexpr int FPSA_WARPS = FPSA_THREADS / 32;
+constexpr int FPSA_RECORDS = FPSA_CTAS * FPSA_WARPS;        // 64 per round
+constexpr int FPSA_MAX_N = FPSA_CTAS * FPSA_THREADS * 8;    // 16384 (196 KB of shared memory)
+static_assert(FPSA_RECORDS == 64, "winner pick reads two records per lane");
+
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int PPT>
+__global__ void __cluster_dims__(FPSA_CTAS, 1, 1) __launch_bounds__(FPSA_THREADS, 1)
+fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_t* __restrict__ out_all) {
+    extern __shared__ float s_xyz[];                              // x[N] | y[N] | z[N]: the whole cloud
+    __shared__ __align__(16) uint2 s_rec[2][FPSA_RECORDS];        // written by every warp of the cluster
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / FPSA_CTAS;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float* __restrict__ xyz = xyz_all + (size_t)cloud * N * 3;
+    int64_t* __restrict__ out = out_all + (size_t)cloud * S;
+    float* sx = s_xyz;
+    float* sy = s_xyz + N;
+    float* sz = s_xyz + 2 * N;
+
+    for (int i = t; i < N; i += FPSA_THREADS) {
+        sx[i] = __ldg(xyz + i * 3 + 0); sy[i] = __ldg(xyz + i * 3 + 1); sz[i] = __ldg(xyz + i * 3 + 2);
+    }
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // point i = (j * CTAS + rank) * THREADS + t  (coalesced 256-point chunks, round-robin over CTAs)
+    float px[PPT], py[PPT], pz[PPT], pd[PPT];
+    unsigned plo[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int i = (j * FPSA_CTAS + rank) * FPSA_THREADS + t;
+        if (i < N) {
+            px[j] = sx[i]; py[j] = sy[i]; pz[j] = sz[i];
+            pd[j] = 1e10f;                                        // furthest_point_sampling.cpp:12
+            plo[j] = fps_key_lo(i);
+        } else {
+            px[j] = py[j] = pz[j] = 0.f;
+            pd[j] = -2.f;                                         // never beats a real point
+            plo[j] = 0u;
+        }
+    }
+    // remote addresses of "my warp's" slot and of the mbarriers in CTA `lane` (lanes 0..7 send)
+    uint32_t r_rec[2] = {0u, 0u}, r_bar[2] = {0u, 0u};
+    if (lane < FPSA_CTAS) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                         : "=r"(r_rec[p]) : "r"(fps_smem_u32(&s_rec[p][rank * FPSA_WARPS + warp])), "r"(lane));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r_bar[p]) : "r"(fps_smem_u32(&s_bar[p])), "r"(lane));
+        }
+    }
+    const uint32_t l_bar[2] = {fps_smem_u32(&s_bar[0]), fps_smem_u32(&s_bar[1])};
+    cluster.sync();                                               // every CTA's barriers exist before any remote store
+
+    int cur = 0;
+    for (int s = 0; s < S; ++s) {
+        if (rank == 0 && t == 0) out[s] = (int64_t)cur;
+        if (s == S - 1) break;
+        const int par = s & 1;
+        if (t == 0)                                               // arm this round's barrier (remote stores may already have landed)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         ::"r"(l_bar[par]), "r"((uint32_t)(FPSA_RECORDS * sizeof(uint2))) : "memory");
+        const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+        // ---- this thread's points: update running distances, thread-local best
+        float best_d = -3.f;
+        unsigned best_lo = 0u;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = camli_sqdist3(px[j] - cx, py[j] - cy, pz[j] - cz);
+            const float nd = fminf(pd[j], d);
+            pd[j] = nd;
+            if (nd > best_d || (nd == best_d && plo[j] > best_lo)) { best_d = nd; best_lo = plo[j]; }
+        }
+        // ---- warp key, pushed to all 8 CTAs
+        const int hi = __float_as_int(best_d);
+        const int hmax = __reduce_max_sync(CAMLI_FULL_MASK, hi);
+        const unsigned lmax = __reduce_max_sync(CAMLI_FULL_MASK, hi == hmax ? best_lo : 0u);
+        if (lane < FPSA_CTAS)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                         ::"r"(r_rec[par]), "r"(hmax), "r"(lmax), "r"(r_bar[par]) : "memory");
+        // ---- wait for the 64 records of this round (bounded: a protocol bug traps instead of hanging)
+        const uint32_t phase = (uint32_t)(s >> 1) & 1u;
+        for (uint32_t spin = 0;; ++spin) {
+            uint32_t done;
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(l_bar[par]), "r"(phase) : "memory");
+            if (done) break;
+            if (spin > (1u << 24)) __trap();
+        }
+        // ---- global winner: max over the 64 (hi, lo) keys
+        const uint2 r0 = s_rec[par][lane], r1 = s_rec[par][lane + 32];
+        const bool second = (int)r1.x > (int)r0.x || (r1.x == r0.x && r1.y > r0.y);
+        const int mh = second ? (int)r1.x : (int)r0.x;
+        const unsigned ml = second ? r1.y : r0.y;
+        const int gh = __reduce_max_sync(CAMLI_FULL_MASK, mh);
+        const unsigned gl = __reduce_max_sync(CAMLI_FULL_MASK, mh == gh ? ml : 0u);
+        cur = (int)(0x3FFFFFu - (gl & 0x3FFFFFu));
+    }
+    cluster.sync();                                               // no CTA exits while peers may still store to it
+}
+
+template <int PPT>
+int fps_launch_cluster_async(const float* xyz, int B, int N, int S, int64_t* out, cudaStream_t st) {
+    const size_t smem = (size_t)N * 3 * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fps_cluster_async_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fps_cluster_async_kernel<PPT><<<B * FPSA_CTAS, FPSA_THREADS, smem, st>>>(xyz, N, S, out);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
 template <int PPT>
 int fps_launch_cluster(const float* xyz, int B, int N, int S, int64_t* out, cudaStream_t st) {
     fps_cluster_kernel<PPT><<<B * FPSC_CTAS, FPSC_THREADS, 0, st>>>(xyz, N, S, out);
@@ -262,11 +398,12 @@ int fps_launch_register(const float* xyz, int B, int N, int S, int64_t* out, cud
 
 }  // namespace
 
-// Tuning switch (tests exercise both paths): 1 = cluster kernel for 2048 < N <= 16384.
-static int camli_fps_use_cluster = 1;
-extern "C" int camli_fps_set_cluster_path(int enable) {
+// Tuning switch (tests exercise every path) for 2048 < N <= 16384: 0 = single-CTA register kernel,
+// 1 = cluster kernel with a cluster barrier per round, 2 = cluster kernel with the st.async exchange (default).
+static int camli_fps_use_cluster = 2;
+extern "C" int camli_fps_set_cluster_path(int mode) {
     const int old = camli_fps_use_cluster;
-    camli_fps_use_cluster = enable ? 1 : 0;
+    camli_fps_use_cluster = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
     return old;
 }
 
@@ -278,7 +415,13 @@ extern "C" int camli_furthest_point_sampling(const float* xyz, float* dists_tmp,
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 1 * FPS_THREADS) return fps_launch_register<1>(xyz, B, N, S, out, st);
     if (N <= 2 * FPS_THREADS) return fps_launch_register<2>(xyz, B, N, S, out, st);
-    if (camli_fps_use_cluster) {
+    if (camli_fps_use_cluster == 2) {
+        const int per = FPSA_CTAS * FPSA_THREADS;
+        if (N <= 2 * per) return fps_launch_cluster_async<2>(xyz, B, N, S, out, st);
+        if (N <= 4 * per) return fps_launch_cluster_async<4>(xyz, B, N, S, out, st);
+        if (N <= FPSA_MAX_N) return fps_launch_cluster_async<8>(xyz, B, N, S, out, st);
+    }
+    if (camli_fps_use_cluster == 1) {
         const int per = FPSC_CTAS * FPSC_THREADS;
         if (N <= 2 * per) return fps_launch_cluster<2>(xyz, B, N, S, out, st);
         if (N <= 4 * per) return fps_launch_cluster<4>(xyz, B, N, S, out, st);

@@ -50,9 +50,10 @@ const char* camli_strerror(int code);
 int camli_furthest_point_sampling(const float* xyz, float* dists_tmp,
                                   int B, int N, int S, int64_t* out, void* stream);
 
-/* Selects the FPS kernel for 2048 < N <= 16384: 1 = 8-CTA thread-block-cluster kernel (default),
+/* Selects the FPS kernel for 2048 < N <= 16384: 2 = 8-CTA thread-block cluster exchanging the per-round
+ * records with st.async + mbarrier (default), 1 = 8-CTA cluster with a cluster barrier per round,
  * 0 = single-CTA register kernel.  Returns the previous setting.  Results are identical. */
-int camli_fps_set_cluster_path(int enable);
+int camli_fps_set_cluster_path(int mode);
 
 /*
  * Brute-force exact k nearest neighbours, ascending distance.
