@@ -1,0 +1,422 @@
+// Linear layers and stride-1 "same" convolutions on channel-last activations as ONE implicit GEMM on
+// the 5th-generation tensor cores (TMA + tcgen05 + TMEM), fp32-accurate through 3xTF32, with the
+// bias / residual / activation of the layer fused into the epilogue.
+//
+// Replaces, on the hot path, every `MLP1d` / `nn.Linear` / 1x1 `Conv1d|Conv2d` of the point branch
+// (reference models/point_conv.py:29,62,106; models/mlp.py:41-128; models/camliraft_l_core.py:46,163)
+// and the k x k convolutions of the update block and encoder (models/raft_core.py:110-197): in the
+// reference each is a cuBLAS/cuDNN call followed by separate bias, norm and activation kernels.
+//
+//   out[p, n] = act( sum_{tap} sum_c X[p (+) tap, c] * W[n, tap, c] + bias[n] + residual[p, n] )
+//
+// p runs over the B*H*W pixels (rows) of a channel-last tensor; a linear layer is the H = 1, 1x1 case.
+//
+// A operand (activations): a 4-D tensor map (C, W, H, B) with a (32 ch, TW, TH, 1) box, TH*TW = 128:
+// each k-block is the box at (c0, x0 + dx, y0 + dy, b) -- the tap shift is just a coordinate offset and
+// the zero padding of the convolution is TMA's out-of-bounds fill.  No im2col buffer exists anywhere.
+// B operand (weights): [Cout, taps*Cin] row-major (= the OHWI / channels_last weight layout), split once
+// on the host side into tf32 hi / lo parts; 2-D map, (32, BN) box at column tap*Cin + c0.
+//
+// 3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); result = hi*hi + (lo*hi + hi*lo), the dropped lo*lo
+// being ~2^-22.  The tensor core TRUNCATES its fp32 accumulator after every instruction (measured: the error
+// of a long accumulation is a bias that grows linearly with the number of MMAs, ~0.5 ulp of the running sum
+// each), so a plain in-TMEM accumulation over K = 2304 is ~50x less accurate than an fp32 SGEMM.  Two
+// measures bring it back to SGEMM level: (1) the correction terms go to their OWN accumulator (2^-11 of the
+// main one, so their truncations are harmless); (2) the main term is accumulated in chunks of CG_CHUNK
+// k-blocks -- each chunk starts from a zeroed accumulator, and the epilogue warps add the chunks in
+// registers with round-to-nearest while the next chunk's MMAs run (two main accumulators ping-pong).  The activation split happens INSIDE the kernel: four converter
+// warps rewrite each landed fp32 tile in place as `hi` and emit `lo` into a sibling buffer (conflict-free
+// 16-byte chunks; the 128-byte swizzle is position-preserving), so activations make exactly one trip
+// from HBM and no split tensors are ever materialised.
+//
+// Warp roles (one persistent CTA per SM, 448 threads):
+//   warp 0     TMA producer: A (raw fp32), W_hi, W_lo of one k-block per pipeline stage;
+//   warp 1     MMA issuer: 12 x tcgen05.mma kind::tf32 (M=128, N=BN, K=8) per k-block (4 main, 8 correction);
+//              tcgen05.commit frees the stage / publishes a chunk or the tile's corrections;
+//   warps 2-5  converters (hi/lo split of the A tile, generic -> async proxy fence, arrive);
+//   warps 6-13 epilogue (two per TMEM lane quarter, half of the columns each): tcgen05.ld of every chunk (register sum), + corrections, bias + residual +
+//              activation, 128-bit stores to [rows, ldo].
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace {
+
+using namespace camli_tc;
+
+constexpr int CG_BM = 128, CG_BK = 32;
+constexpr int CG_THREADS = 448;                   // 14 warps: TMA, MMA, 4 converters, 8 epilogue
+constexpr int CG_A_BYTES = CG_BM * CG_BK * 4;     // 16 KB
+constexpr int CG_CHUNK = 2;                       // k-blocks (of 32 channels) accumulated in TMEM before a drain
+
+template <int BN> struct CgCfg {
+    static constexpr int kStageBytes = 2 * CG_A_BYTES + 2 * BN * CG_BK * 4;
+    static constexpr int kStages = (BN >= 128) ? 3 : 4;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kTmemCols = 4 * BN;      // main x2 (per chunk) + correction x2 (per tile)
+};
+
+struct CgParams {
+    int B, H, W, Cin, Cout;        // activation geometry, channels
+    int kh, kw;                    // window (odd), "same" padding, stride 1
+    int th, tw;                    // pixel tile: th * tw = 128
+    int tiles_y, tiles_x, tiles_n;
+    const float* bias;             // [Cout] or null
+    const float* residual;         // [rows, ldr] or null
+    long long ldr;
+    float* out;                    // [rows, ldo]
+    long long ldo;
+    int act;                       // CAMLI_ACT_*
+    float slope;
+};
+
+__device__ __forceinline__ float cg_activate(float v, int act, float slope) {
+    switch (act) {
+        case CAMLI_ACT_RELU: return fmaxf(v, 0.f);
+        case CAMLI_ACT_LEAKY: return v > 0.f ? v : v * slope;
+        case CAMLI_ACT_TANH: return tanhf(v);
+        case CAMLI_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(CG_THREADS, 1)
+conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                        const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CgParams P) {
+    using Cfg = CgCfg<BN>;
+    constexpr int STAGES = Cfg::kStages;
+    constexpr int W_BYTES = BN * CG_BK * 4;
+    // epilogue: two warps per TMEM lane quarter, each owning half of the accumulator columns (a 32-column
+    // tile is not worth splitting: only the first group of four warps works then)
+    constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
+    constexpr int CW = BN >= 64 ? BN / 2 : BN;        // columns per epilogue warp
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    // full[s] (TMA landed), conv[s] (A split done), empty[s] (MMAs retired); mfull/mempty[2]: main accumulators
+    // (one hand-off per chunk); cfull/cempty[2]: correction accumulators (one hand-off per tile)
+    const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + STAGES), bar_empty = smem_u32(bars + 2 * STAGES);
+    const uint32_t bar_mfull = smem_u32(bars + 3 * STAGES), bar_mempty = smem_u32(bars + 3 * STAGES + 2);
+    const uint32_t bar_cfull = smem_u32(bars + 3 * STAGES + 4), bar_cempty = smem_u32(bars + 3 * STAGES + 6);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 8);
+    const uint32_t tiles_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 128);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_mfull + 8 * a, 1); mbar_init(bar_mempty + 8 * a, EPI_WARPS);
+            mbar_init(bar_cfull + 8 * a, 1); mbar_init(bar_cempty + 8 * a, EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cblocks = (P.Cin + CG_BK - 1) / CG_BK;
+    const int kblocks = P.kh * P.kw * cblocks;
+    const int tiles_per_img = P.tiles_y * P.tiles_x * P.tiles_n;
+    const int total = P.B * tiles_per_img;
+    const int pad_y = P.kh / 2, pad_x = P.kw / 2;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int b = tile / tiles_per_img;
+                int r = tile - b * tiles_per_img;
+                const int nt = r % P.tiles_n; r /= P.tiles_n;
+                const int x0 = (r % P.tiles_x) * P.tw, y0 = (r / P.tiles_x) * P.th;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * CG_BK;
+                    const int dy = tap / P.kw - pad_y, dx = tap % P.kw - pad_x;
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t dst = tiles_base + stage * Cfg::kStageBytes;
+                    mbar_expect_tx(full, CG_A_BYTES + 2 * W_BYTES);
+                    tma_load_4d(dst, &map_x, full, c0, x0 + dx, y0 + dy, b);
+                    tma_load_2d(dst + 2 * CG_A_BYTES, &map_whi, full, tap * P.Cin + c0, nt * BN);
+                    tma_load_2d(dst + 2 * CG_A_BYTES + W_BYTES, &map_wlo, full, tap * P.Cin + c0, nt * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t IDESC = tf32_idesc(CG_BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0, ch = 0;                                          // tiles / chunks handled by this CTA so far
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+                const int cacc = it & 1;
+                mbar_wait(bar_cempty + 8 * cacc, ((it >> 1) & 1) ^ 1);
+                const uint32_t tmem_corr = tmem_base + (2 + cacc) * BN;
+                for (int kb0 = 0; kb0 < kblocks; kb0 += CG_CHUNK, ++ch) {
+                    const int macc = ch & 1;
+                    mbar_wait(bar_mempty + 8 * macc, ((ch >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_main = tmem_base + macc * BN;
+                    const int kb1 = min(kb0 + CG_CHUNK, kblocks);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        mbar_wait(bar_conv + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t src = tiles_base + stage * Cfg::kStageBytes;
+                        const uint64_t a_hi = make_kmajor_sw128_desc(src), a_lo = make_kmajor_sw128_desc(src + CG_A_BYTES);
+                        const uint64_t b_hi = make_kmajor_sw128_desc(src + 2 * CG_A_BYTES),
+                                       b_lo = make_kmajor_sw128_desc(src + 2 * CG_A_BYTES + W_BYTES);
+#pragma unroll
+                        for (int k = 0; k < CG_BK / 8; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            mma_tf32(tmem_main, a_hi + adv, b_hi + adv, IDESC, ((kb - kb0) | k) ? 1u : 0u);
+                            mma_tf32(tmem_corr, a_lo + adv, b_hi + adv, IDESC, (kb | k) ? 1u : 0u);
+                            mma_tf32(tmem_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
+                        }
+                        mma_commit(bar_empty + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    mma_commit(bar_mfull + 8 * macc);                    // this chunk of the main term is complete
+                }
+                mma_commit(bar_cfull + 8 * cacc);                        // corrections of the tile are complete
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== converters (warps 2..5): fp32 tile -> tf32 hi (in place) + lo =====================
+        const int t = threadIdx.x - 64;                                 // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                float4* a_hi = reinterpret_cast<float4*>(smem + stage * Cfg::kStageBytes);
+                float4* a_lo = reinterpret_cast<float4*>(smem + stage * Cfg::kStageBytes + CG_A_BYTES);
+#pragma unroll
+                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i) {       // 8 chunks of 16 bytes per thread
+                    const float4 v = a_hi[t + i * 128];
+                    float4 h, l;
+                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    a_hi[t + i * 128] = h;
+                    a_lo[t + i * 128] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to UMMA
+                mbar_arrive(bar_conv + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 6..13) =====================
+        const int q = warp & 3;                                         // TMEM lane quarter of this warp
+        const int half = (warp - 6) >> 2;                               // which half of the columns
+        if (half * CW >= BN) goto done;                                 // (second group idle for 32-column tiles)
+        const int row = q * 32 + lane;                                  // accumulator row = pixel of the tile
+        const int ty = row / P.tw, tx = row - ty * P.tw;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + half * CW;
+        int it = 0, ch = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const int b = tile / tiles_per_img;
+            int r = tile - b * tiles_per_img;
+            const int nt = r % P.tiles_n; r /= P.tiles_n;
+            const int x = (r % P.tiles_x) * P.tw + tx, y = (r / P.tiles_x) * P.th + ty;
+            const int n0 = nt * BN + half * CW;
+            // ---- sum of the main-term chunks, round-to-nearest, in registers
+            float sum[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) sum[j] = 0.f;
+            for (int kb0 = 0; kb0 < kblocks; kb0 += CG_CHUNK, ++ch) {
+                const int macc = ch & 1;
+                mbar_wait(bar_mfull + 8 * macc, (ch >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < CW / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(lane_base + macc * BN + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_mempty + 8 * macc);
+            }
+            // ---- + corrections, then bias / residual / activation / store
+            const int cacc = it & 1;
+            mbar_wait(bar_cfull + 8 * cacc, (it >> 1) & 1);
+            tc_fence_after();
+            const bool live = x < P.W && y < P.H;
+            const size_t pix = ((size_t)b * P.H + y) * P.W + x;
+            float* __restrict__ orow = P.out + pix * P.ldo + n0;
+            const float* __restrict__ rrow = P.residual ? P.residual + pix * P.ldr + n0 : nullptr;
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
+                                (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+#pragma unroll
+            for (int c = 0; c < CW / 32; ++c) {
+                float v[32];
+                tmem_ld32(lane_base + (2 + cacc) * BN + c * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += sum[c * 32 + j];
+                const int col0 = n0 + c * 32;
+                if (live && col0 < P.Cout) {
+                    const bool full = col0 + 32 <= P.Cout;
+                    if (P.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += (full || col0 + j < P.Cout) ? __ldg(P.bias + col0 + j) : 0.f;
+                    }
+                    if (full && vec_ok) {
+                        if (rrow) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + c * 32 + j));
+                                v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(orow + c * 32 + j) =
+                                make_float4(cg_activate(v[j], P.act, P.slope), cg_activate(v[j + 1], P.act, P.slope),
+                                            cg_activate(v[j + 2], P.act, P.slope), cg_activate(v[j + 3], P.act, P.slope));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < P.Cout) {
+                                const float rv = rrow ? __ldg(rrow + c * 32 + j) : 0.f;
+                                orow[c * 32 + j] = cg_activate(v[j] + rv, P.act, P.slope);
+                            }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cempty + 8 * cacc);
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256)
+split_tf32_pair_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float h, l;
+    split_tf32(__ldg(x + i), h, l);
+    hi[i] = h;
+    lo[i] = l;
+}
+
+int encode_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides_bytes,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int BN>
+int launch_conv_gemm(const CUtensorMap& mx, const CUtensorMap& mwh, const CUtensorMap& mwl, const CgParams& P, int total,
+                     cudaStream_t st) {
+    using Cfg = CgCfg<BN>;
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    const int n_sms = sm_count();
+    const int grid = total < n_sms ? total : n_sms;
+    conv_gemm_tf32x3_kernel<BN><<<grid, CG_THREADS, Cfg::kSmem, st>>>(mx, mwh, mwl, P);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace
+
+extern "C" int camli_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+    if (n < 0) return CAMLI_EINVAL;
+    if (n == 0) return CAMLI_OK;
+    if (!x || !hi || !lo) return CAMLI_EINVAL;
+    split_tf32_pair_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, (size_t)n);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int64_t ldx,
+                               const float* w_hi, const float* w_lo, int Cout, int kh, int kw,
+                               const float* bias, const float* residual, int64_t ldr,
+                               int act, float slope, float* out, int64_t ldo, int tile_n, void* stream) {
+    if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin || ldo < Cout) return CAMLI_EINVAL;
+    if (residual && ldr < Cout) return CAMLI_EINVAL;
+    if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
+    // TMA: 16-byte aligned bases and strides; odd windows only ("same" padding)
+    if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (Cin & 3) || (ldx & 3)) return CAMLI_EUNSUPPORTED;
+    if (B == 0) return CAMLI_OK;
+    if (!x || !w_hi || !w_lo || !out) return CAMLI_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 15)
+        return CAMLI_EINVAL;
+    if ((long long)B * H * W > 2147483647LL) return CAMLI_EUNSUPPORTED;
+
+    CgParams P;
+    P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.kh = kh; P.kw = kw;
+    // pixel tile th x tw = 128 with the least padding waste (a linear layer, H = 1, gets 1 x 128)
+    int best_th = 1;
+    long long best = -1;
+    for (int th = 1; th <= 16; th *= 2) {
+        const int tw = CG_BM / th;
+        const long long tiles = (long long)camli_div_up(H, th) * camli_div_up(W, tw);
+        if (best < 0 || tiles < best) { best = tiles; best_th = th; }
+    }
+    P.th = best_th; P.tw = CG_BM / best_th;
+    P.tiles_y = camli_div_up(H, P.th); P.tiles_x = camli_div_up(W, P.tw);
+    // N tile: wide tiles amortise the activation split; small problems take narrow tiles to fill the SMs
+    int bn = tile_n;
+    if (bn == 0) {
+        const long long mt = (long long)B * P.tiles_y * P.tiles_x;
+        bn = 128;
+        while (bn > 32 && (Cout <= bn / 2 || mt * camli_div_up(Cout, bn) * 10 < (long long)sm_count() * 6)) bn /= 2;
+    }
+    if (bn != 32 && bn != 64 && bn != 128) return CAMLI_EINVAL;
+    P.tiles_n = camli_div_up(Cout, bn);
+    P.bias = bias; P.residual = residual; P.ldr = ldr; P.out = out; P.ldo = ldo; P.act = act; P.slope = slope;
+    const long long total = (long long)B * P.tiles_y * P.tiles_x * P.tiles_n;
+    if (total > 2147483647LL) return CAMLI_EUNSUPPORTED;
+
+    CUtensorMap mx, mwh, mwl;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * W * 4, (cuuint64_t)ldx * W * H * 4};
+        const cuuint32_t box[4] = {CG_BK, (cuuint32_t)P.tw, (cuuint32_t)P.th, 1};
+        int rc = encode_map(&mx, x, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)kh * kw * Cin;
+        const cuuint64_t dims[2] = {ktot, (cuuint64_t)Cout};
+        const cuuint64_t strides[1] = {ktot * 4};
+        const cuuint32_t box[2] = {CG_BK, (cuuint32_t)bn};
+        int rc = encode_map(&mwh, w_hi, 2, dims, strides, box);
+        if (rc) return rc;
+        rc = encode_map(&mwl, w_lo, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 32: return launch_conv_gemm<32>(mx, mwh, mwl, P, (int)total, st);
+        case 64: return launch_conv_gemm<64>(mx, mwh, mwl, P, (int)total, st);
+        default: return launch_conv_gemm<128>(mx, mwh, mwl, P, (int)total, st);
+    }
+}

@@ -162,6 +162,88 @@ def allpairs(a_rows, b_rows, scale):
     return out
 
 
+# ---------------------------------------------------------------- tensor-core linear / convolution
+ACT_CODES = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "tanh": 3, "sigmoid": 4}
+_TC_WEIGHTS = {}
+
+
+def tc_weight(key_params, builder):
+    """(w_hi, w_lo, bias) of a layer for conv_gemm: `builder()` returns the effective (weight [N, taps*Cin] in
+    OHWI order, bias [N] or None) -- e.g. with an eval BatchNorm folded in -- which is split into its tf32
+    hi / lo parts ONCE and cached until one of `key_params` changes (data_ptr, version)."""
+    import weakref
+    live = [p for p in key_params if p is not None]
+    key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in live)
+    slot = _TC_WEIGHTS.get(key[0][0])
+    if slot is None or slot[0] != key or slot[1]() is not live[0]:      # (a freed tensor's address may be reused)
+        with torch.no_grad():
+            w2d, bias = builder()
+            w2d = w2d.float().contiguous()
+            hi, lo = torch.empty_like(w2d), torch.empty_like(w2d)
+            with torch.cuda.device(w2d.device):
+                native.call("camli_split_tf32", ptr(w2d), ptr(hi), ptr(lo), i64(w2d.numel()), stream())
+            slot = (key, weakref.ref(live[0]), hi, lo, None if bias is None else bias.float().contiguous())
+        _TC_WEIGHTS[key[0][0]] = slot
+    return slot[2], slot[3], slot[4]
+
+
+def _pixel_layout(t):
+    """(ld, ok) of a channel-last [B,H,W,C] view whose pixels are `ld` floats apart (channel slices of a wider
+    NHWC buffer qualify); ok = the TMA / vector-store alignment rules hold."""
+    B, H, W, C = t.shape
+    sb, sh, sw, sc = t.stride()
+    ld = sw if W > 1 else (sh if H > 1 else (sb if B > 1 else C))
+    ok = (sc == 1 or C == 1) and (W == 1 or sw == ld) and (H == 1 or sh == W * ld) and (B == 1 or sb == H * W * ld)
+    return ld, ok and ld % 4 == 0 and t.data_ptr() % 16 == 0
+
+
+def conv_gemm_ok(x_bhwc, kh=1, kw=1):
+    """Whether conv_gemm can take this input directly (else callers keep the cuDNN / cuBLAS route)."""
+    if not (x_bhwc.is_cuda and x_bhwc.dtype == torch.float32 and x_bhwc.dim() == 4):
+        return False
+    ld, ok = _pixel_layout(x_bhwc)
+    return ok and x_bhwc.shape[-1] % 4 == 0 and kh % 2 == 1 and kw % 2 == 1
+
+
+def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residual=None, out=None, tile_n=0):
+    """Linear layer / stride-1 "same" convolution + bias + residual + activation in one tcgen05 kernel
+    (include/camli_b200.h: camli_conv_gemm).  x_bhwc [B,H,W,Cin] channel-last view (a linear layer over rows
+    is [1,1,R,K]); w_hi/w_lo [Cout, kh*kw*Cin] from tc_weight(); residual / out [B,H,W,Cout] channel-last views
+    (out may be a channel slice of a wider buffer).  Returns out."""
+    _need_cuda(x_bhwc, w_hi, w_lo)
+    _no_grad("conv_gemm", x_bhwc, w_hi)
+    B, H, W, Cin = x_bhwc.shape
+    Cout = w_hi.shape[0]
+    assert w_hi.shape[1] == kh * kw * Cin, (tuple(w_hi.shape), kh, kw, Cin)
+    ldx, ok = _pixel_layout(x_bhwc)
+    if not ok or Cin % 4:
+        raise RuntimeError("conv_gemm: input must be a 16-byte aligned channel-last view with Cin % 4 == 0")
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x_bhwc.device)
+    ldo = _pixel_layout(out)[0] if out.shape[-1] == Cout else None
+    assert tuple(out.shape) == (B, H, W, Cout) and ldo is not None
+    ldr = 0
+    if residual is not None:
+        assert tuple(residual.shape) == (B, H, W, Cout)
+        ldr = _pixel_layout(residual)[0]
+    with torch.cuda.device(x_bhwc.device):
+        native.call("camli_conv_gemm", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w_hi), ptr(w_lo),
+                    i32(Cout), i32(kh), i32(kw), ptr(bias), ptr(residual), i64(ldr), i32(ACT_CODES[act]),
+                    ctypes.c_float(slope), ptr(out), i64(ldo), i32(tile_n), stream(),
+                    algo_bytes=B * H * W * (Cin + Cout) * 4 + Cout * kh * kw * Cin * 4,
+                    flops=2 * B * H * W * Cout * kh * kw * Cin)
+    return out
+
+
+def linear_rows(x, w_hi, w_lo, bias=None, act=None, slope=0.1, residual=None):
+    """x [..., K] contiguous rows -> [..., N] through conv_gemm (1x1)."""
+    K = x.shape[-1]
+    x2 = x.reshape(1, 1, -1, K)
+    r2 = None if residual is None else residual.reshape(1, 1, -1, w_hi.shape[0])
+    out = conv_gemm(x2, w_hi, w_lo, 1, 1, bias, act, slope, r2)
+    return out.view(*x.shape[:-1], w_hi.shape[0])
+
+
 # ---------------------------------------------------------------- RAFT all-pairs correlation
 def corr2d_build(fmap1, fmap2, num_levels):
     """All-pairs volume of two [B,C,H,W] maps scaled by 1/sqrt(C) and its 2x2 average-pooled pyramid

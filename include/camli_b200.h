@@ -268,6 +268,35 @@ int camli_gru_gate(int64_t rows, int H, int X, const float* zr, const float* h, 
 int camli_gru_update(int64_t n, const float* z, const float* h, const float* q, int fix_nonfinite,
                      float* h_out, void* stream);
 
+/* Epilogue activations of camli_conv_gemm. */
+#define CAMLI_ACT_NONE    0
+#define CAMLI_ACT_RELU    1
+#define CAMLI_ACT_LEAKY   2   /* v > 0 ? v : v * slope */
+#define CAMLI_ACT_TANH    3
+#define CAMLI_ACT_SIGMOID 4
+
+/* x -> (hi, lo) with hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand split of the 3xTF32
+ * tensor-core kernels; used once per weight tensor. */
+int camli_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+
+/*
+ * Linear layer / stride-1 "same" convolution on channel-last activations as one TMA + tcgen05 implicit
+ * GEMM with fp32-level accuracy (3xTF32) and a fused epilogue.  Replaces the cuBLAS/cuDNN call + bias +
+ * norm(folded) + activation kernels behind nn.Linear / MLP1d / Conv1d(1) / Conv2d of the hot path
+ * (models/mlp.py:41-128, models/point_conv.py:29,62,106, models/raft_core.py:110-197):
+ *   out[p, n] = act( sum_{ky,kx,c} x[b, y+ky-kh/2, x+kx-kw/2, c] * w[n, ky, kx, c] + bias[n] + residual[p, n] )
+ * x        [B,H,W,ldx] f32 (first Cin channels of every pixel are read; zero padding outside the map);
+ *          a linear layer over R rows is B=1, H=1, W=R.  Cin % 4 == 0, ldx % 4 == 0, 16-byte aligned.
+ * w_hi/lo  [Cout, kh*kw*Cin] f32 = camli_split_tf32 of the OHWI (channels_last) weight; kh, kw odd.
+ * bias     [Cout] or NULL; residual [B*H*W, ldr] or NULL; act = CAMLI_ACT_*.
+ * out      [B*H*W, ldo] f32: ldo >= Cout lets the layer write a channel slice of a wider tensor.
+ * tile_n   0 = automatic; else 32 / 64 / 128 (accumulator tile width).
+ */
+int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int64_t ldx,
+                    const float* w_hi, const float* w_lo, int Cout, int kh, int kw,
+                    const float* bias, const float* residual, int64_t ldr,
+                    int act, float slope, float* out, int64_t ldo, int tile_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

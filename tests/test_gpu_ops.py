@@ -259,3 +259,64 @@ def test_encoder2d_fused_epilogues(dev, channels_last):
         plain = enc(x).detach()
     scale = plain.abs().max().item()
     _close(fused, plain, 2e-5 * max(scale, 1.0), rtol=1e-4, what="Encoder2D fused epilogues")
+
+
+def _tc_weight(w_oihw, bias):
+    """Weight [O,I,kh,kw] -> the OHWI hi/lo split camli_conv_gemm consumes."""
+    O = w_oihw.shape[0]
+    return _ops().tc_weight([w_oihw], lambda: (w_oihw.permute(0, 2, 3, 1).reshape(O, -1), bias))
+
+
+CONV_GEMM_CASES = [
+    # B, H, W, Cin, Cout, kh, kw, act, residual, tile_n
+    (1, 1, 2048, 384, 128, 1, 1, None, False, 0),            # PointConvDW mlp of the 3-D GRU
+    (1, 1, 2048, 144, 125, 1, 1, "leaky_relu", False, 0),    # ragged Cout, K tail (144 = 4.5 k-blocks)
+    (2, 1, 300, 36, 3, 1, 1, None, False, 0),                # tiny head
+    (1, 1, 4096, 1584, 96, 1, 1, "leaky_relu", False, 0),    # PointConv Linear of the encoder
+    (1, 68, 120, 256, 192, 3, 3, "relu", False, 0),          # MotionEncoder2D.conv_c2
+    (1, 68, 120, 384, 256, 1, 5, None, False, 0),            # merged z|r convolution of the ConvGRU
+    (1, 68, 120, 384, 128, 5, 1, "tanh", False, 64),
+    (2, 30, 44, 64, 64, 3, 3, "relu", True, 0),              # bottleneck tail: conv + residual + ReLU
+    (1, 17, 23, 8, 40, 7, 7, "sigmoid", False, 32),          # Cin below one k-block, wide window
+    (1, 136, 240, 64, 256, 1, 1, "relu", True, 128),         # encoder 1x1, widest accumulator tile
+    (1, 20, 36, 128, 256, 3, 3, None, False, 128),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw,act,res,tile_n", CONV_GEMM_CASES)
+def test_conv_gemm_tcgen05(dev, B, H, W, Cin, Cout, kh, kw, act, res, tile_n):
+    """3xTF32 implicit-GEMM convolution / linear layer against an fp64 convolution: the error must stay at
+    the level of an fp32 SGEMM (a plain TF32 product is ~1000x worse)."""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    r = torch.randn(B, Cout, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last) if res else None
+    w_hi, w_lo, bias = _tc_weight(w, b)
+    out = _ops().conv_gemm(x.permute(0, 2, 3, 1), w_hi, w_lo, kh, kw, bias, act, 0.1,
+                           None if r is None else r.permute(0, 2, 3, 1), tile_n=tile_n).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))
+    if r is not None:
+        ref = ref + r.double()
+    ref = {None: lambda v: v, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid,
+           "leaky_relu": lambda v: torch.nn.functional.leaky_relu(v, 0.1)}[act](ref)
+    err = (out.double() - ref).abs().max().item()
+    fp32 = torch.nn.functional.conv2d(x, w, b, padding=(kh // 2, kw // 2))
+    print("conv_gemm %s: max err %.3e" % ((B, H, W, Cin, Cout, kh, kw), err))
+    assert err <= 2e-5, err
+    assert out.shape == fp32.shape
+
+
+def test_conv_gemm_channel_slices(dev):
+    """Input read from, and output written into, channel slices of wider channel-last buffers (how the
+    update block avoids torch.cat)."""
+    g = torch.Generator().manual_seed(32)
+    wide_in = torch.randn(1, 20, 28, 96, generator=g).to(dev)
+    wide_out = torch.zeros(1, 20, 28, 80, device=dev)
+    w = (torch.randn(48, 64, 3, 3, generator=g) / 24.0).to(dev)
+    w_hi, w_lo, _ = _tc_weight(w, None)
+    x = wide_in[..., 32:]                       # 64 channels at offset 32
+    _ops().conv_gemm(x, w_hi, w_lo, 3, 3, None, "relu", out=wide_out[..., 16:64])
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1)).permute(0, 2, 3, 1)
+    assert (wide_out[..., 16:64].double() - ref).abs().max().item() <= 2e-5
+    assert wide_out[..., :16].abs().max().item() == 0 and wide_out[..., 64:].abs().max().item() == 0
