@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, tc
 
 from .camliraft_l_core import CamLiRAFT_L_Core, warp_pyramid
 from .clfm import CLFM
@@ -75,12 +75,12 @@ class CamLiRAFT_Core(nn.Module):
             featc_2d, featc_3d = self.clfm_cnet.forward_rows(uv1, featc_2d, featc_3d, nn1, par)
 
         def init_2d():
-            h, x = torch.split(b2.cnet_aligner(featc_2d), [128, 128], dim=1)
+            h, x = torch.split(tc.conv2d(featc_2d, b2.cnet_aligner), [128, 128], dim=1)
             b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
             return torch.tanh(h), torch.relu(x)
 
         def init_3d():
-            hx = F.linear(featc_3d, b3.cnet_aligner.weight.flatten(1), b3.cnet_aligner.bias)
+            hx = tc.linear(featc_3d, b3.cnet_aligner.weight, b3.cnet_aligner.bias)
             b3.correlation.build_cost_volume_pyramid(ops.cf_of(feat1_3d), ops.cf_of(feat2_3d), xyzs2)
             return torch.tanh(hx[..., :128]), torch.relu(hx[..., 128:]), k_nearest_neighbor(xyz1, xyz1, k=32)
 

@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, tc
 from .mlp import Conv1dNormRelu, MLP1d, MLP2d
 from .point_conv import PointConv, PointConvDW
 from .utils import backwarp_3d, build_pc_pyramid, k_nearest_neighbor, knn_interpolation
@@ -72,7 +72,7 @@ class FlowHead3D(nn.Module):
     def forward_rows(self, xyz, feat_rows, knn_indices=None, cache=None):
         f = self.conv1.forward_rows(xyz, feat_rows, knn_indices=knn_indices, cache=cache)
         f = self.conv2.forward_rows(xyz, f, knn_indices=knn_indices, cache=cache)
-        return F.linear(f, self.fc.weight.flatten(1), self.fc.bias)
+        return tc.linear(f, self.fc.weight, self.fc.bias)
 
 
 class GRU3D(nn.Module):

@@ -18,13 +18,14 @@
 // on the host side into tf32 hi / lo parts; 2-D map, (32, BN) box at column tap*Cin + c0.
 //
 // 3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); result = hi*hi + (lo*hi + hi*lo), the dropped lo*lo
-// being ~2^-22.  The tensor core TRUNCATES its fp32 accumulator after every instruction (measured: the error
+// being ~2^-22.  Issued as TWO instructions per k-step: A_hi x [W_hi ; W_lo]^T into adjacent [main | corr]
+// column ranges (N = 2 BN, the efficient wide shape) and A_lo x W_hi^T into the corr range.  The tensor core TRUNCATES its fp32 accumulator after every instruction (measured: the error
 // of a long accumulation is a bias that grows linearly with the number of MMAs, ~0.5 ulp of the running sum
 // each), so a plain in-TMEM accumulation over K = 2304 is ~50x less accurate than an fp32 SGEMM.  Two
-// measures bring it back to SGEMM level: (1) the correction terms go to their OWN accumulator (2^-11 of the
-// main one, so their truncations are harmless); (2) the main term is accumulated in chunks of CG_CHUNK
+// measures bring it back to SGEMM level: (1) the correction terms go to their OWN accumulator columns (2^-11
+// of the main ones, so their truncations are harmless); (2) accumulation in TMEM runs in chunks of CG_CHUNK
 // k-blocks -- each chunk starts from a zeroed accumulator, and the epilogue warps add the chunks in
-// registers with round-to-nearest while the next chunk's MMAs run (two main accumulators ping-pong).  The activation split happens INSIDE the kernel: four converter
+// registers with round-to-nearest while the next chunk's MMAs run (two accumulator buffers ping-pong).  The activation split happens INSIDE the kernel: four converter
 // warps rewrite each landed fp32 tile in place as `hi` and emit `lo` into a sibling buffer (conflict-free
 // 16-byte chunks; the 128-byte swizzle is position-preserving), so activations make exactly one trip
 // from HBM and no split tensors are ever materialised.
@@ -52,7 +53,7 @@ template <int BN> struct CgCfg {
     static constexpr int kStageBytes = 2 * CG_A_BYTES + 2 * BN * CG_BK * 4;
     static constexpr int kStages = (BN >= 128) ? 3 : 4;
     static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int kTmemCols = 4 * BN;      // main x2 (per chunk) + correction x2 (per tile)
+    static constexpr int kTmemCols = 4 * BN;      // two [main | correction] accumulator buffers (ping-pong per chunk)
 };
 
 struct CgParams {
@@ -67,16 +68,56 @@ struct CgParams {
     long long ldo;
     int act;                       // CAMLI_ACT_*
     float slope;
+    long long* timeline;           // diagnostics: SM-clock stamps of CTA 0's pipeline events (null in production)
 };
 
-__device__ __forceinline__ float cg_activate(float v, int act, float slope) {
-    switch (act) {
-        case CAMLI_ACT_RELU: return fmaxf(v, 0.f);
-        case CAMLI_ACT_LEAKY: return v > 0.f ? v : v * slope;
-        case CAMLI_ACT_TANH: return tanhf(v);
-        case CAMLI_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-        default: return v;
+// stamp slot `i` with the SM clock (CTA 0 only, when a timeline buffer is attached)
+#define CG_STAMP(i) do { if (P.timeline && blockIdx.x == 0) P.timeline[(i)] = clock64(); } while (0)
+
+template <int ACT>
+__device__ __forceinline__ float cg_activate(float v, float slope) {
+    if (ACT == CAMLI_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == CAMLI_ACT_LEAKY) return v > 0.f ? v : v * slope;
+    if (ACT == CAMLI_ACT_TANH) return tanhf(v);
+    if (ACT == CAMLI_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+// One thread's 32 consecutive output columns: + bias, + residual, activation, store (masked at the ragged edge).
+template <int ACT>
+__device__ __forceinline__ void cg_store32(float (&v)[32], float* __restrict__ orow, const float* __restrict__ rrow,
+                                           const float* __restrict__ bias, int col0, int n_cols, bool vec_ok, float slope) {
+    const bool full = col0 + 32 <= n_cols;
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += (full || col0 + j < n_cols) ? __ldg(bias + col0 + j) : 0.f;
     }
+    if (full && vec_ok) {
+        if (rrow) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + j));
+                v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(orow + j) = make_float4(cg_activate<ACT>(v[j], slope), cg_activate<ACT>(v[j + 1], slope),
+                                                               cg_activate<ACT>(v[j + 2], slope), cg_activate<ACT>(v[j + 3], slope));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < n_cols) orow[j] = cg_activate<ACT>(v[j] + (rrow ? __ldg(rrow + j) : 0.f), slope);
+    }
+}
+
+// tf32 parts of a landed fp32 value: the tensor core reads only the upper 19 bits of an fp32 operand, so `hi`
+// is the value itself as it lies in shared memory (truncation, nothing to write); lo = x - trunc(x) (exact),
+// rounded to tf32 by integer arithmetic (round half away from zero, as cvt.rna.tf32 does, at full ALU rate --
+// the cvt instruction runs on the slow conversion pipe).
+__device__ __forceinline__ float cg_lo_part(float x) {
+    const float r = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
 }
 
 template <int BN>
@@ -93,25 +134,25 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
-    // full[s] (TMA landed), conv[s] (A split done), empty[s] (MMAs retired); mfull/mempty[2]: main accumulators
-    // (one hand-off per chunk); cfull/cempty[2]: correction accumulators (one hand-off per tile)
+    // full[s] (TMA landed), conv[s] (A split done), empty[s] (MMAs retired); afull/aempty[2]: the two
+    // [main | correction] accumulator buffers (one hand-off per chunk)
     const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + STAGES), bar_empty = smem_u32(bars + 2 * STAGES);
-    const uint32_t bar_mfull = smem_u32(bars + 3 * STAGES), bar_mempty = smem_u32(bars + 3 * STAGES + 2);
-    const uint32_t bar_cfull = smem_u32(bars + 3 * STAGES + 4), bar_cempty = smem_u32(bars + 3 * STAGES + 6);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 8);
+    const uint32_t bar_afull = smem_u32(bars + 3 * STAGES), bar_aempty = smem_u32(bars + 3 * STAGES + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
     const uint32_t tiles_base = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) CG_STAMP(0);
     if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 128);
+            mbar_init(bar_conv + 8 * s, 4);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(bar_mfull + 8 * a, 1); mbar_init(bar_mempty + 8 * a, EPI_WARPS);
-            mbar_init(bar_cfull + 8 * a, 1); mbar_init(bar_cempty + 8 * a, EPI_WARPS);
-        }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_afull + 8 * a, 1); mbar_init(bar_aempty + 8 * a, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -123,6 +164,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) CG_STAMP(1);
 
     const int cblocks = (P.Cin + CG_BK - 1) / CG_BK;
     const int kblocks = P.kh * P.kw * cblocks;
@@ -140,36 +182,41 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 int r = tile - b * tiles_per_img;
                 const int nt = r % P.tiles_n; r /= P.tiles_n;
                 const int x0 = (r % P.tiles_x) * P.tw, y0 = (r / P.tiles_x) * P.th;
+                int tap = 0, cb = 0, dy = -pad_y, dx = -pad_x;           // k-block = (tap, channel block), no divisions
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * CG_BK;
-                    const int dy = tap / P.kw - pad_y, dx = tap % P.kw - pad_x;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t dst = tiles_base + stage * Cfg::kStageBytes;
                     mbar_expect_tx(full, CG_A_BYTES + 2 * W_BYTES);
-                    tma_load_4d(dst, &map_x, full, c0, x0 + dx, y0 + dy, b);
-                    tma_load_2d(dst + 2 * CG_A_BYTES, &map_whi, full, tap * P.Cin + c0, nt * BN);
-                    tma_load_2d(dst + 2 * CG_A_BYTES + W_BYTES, &map_wlo, full, tap * P.Cin + c0, nt * BN);
+                    if (tile == blockIdx.x && kb == 0) CG_STAMP(14);
+                    tma_load_4d(dst, &map_x, full, cb * CG_BK, x0 + dx, y0 + dy, b);
+                    if (tile == blockIdx.x && kb == 0) CG_STAMP(15);
+                    tma_load_2d(dst + CG_A_BYTES * 2, &map_whi, full, tap * P.Cin + cb * CG_BK, nt * BN);
+                    tma_load_2d(dst + CG_A_BYTES * 2 + W_BYTES, &map_wlo, full, tap * P.Cin + cb * CG_BK, nt * BN);
+                    if (tile == blockIdx.x && kb < 16) CG_STAMP(16 + kb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++cb == cblocks) {
+                        cb = 0; ++tap;
+                        if (++dx > pad_x) { dx = -pad_x; ++dy; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===================== MMA issuer =====================
-            constexpr uint32_t IDESC = tf32_idesc(CG_BM, BN);
+            // Two instructions per k-step: [main | corr] (+)= A_hi x [W_hi ; W_lo]^T  (N = 2 BN: W_hi and W_lo are
+            // adjacent in the stage, one descriptor spans both), then corr += A_lo x W_hi^T (N = BN).
+            constexpr uint32_t IDESC_2N = tf32_idesc(CG_BM, 2 * BN), IDESC_N = tf32_idesc(CG_BM, BN);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0, ch = 0;                                          // tiles / chunks handled by this CTA so far
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-                const int cacc = it & 1;
-                mbar_wait(bar_cempty + 8 * cacc, ((it >> 1) & 1) ^ 1);
-                const uint32_t tmem_corr = tmem_base + (2 + cacc) * BN;
+            int ch = 0;                                                  // chunks handled by this CTA so far
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 for (int kb0 = 0; kb0 < kblocks; kb0 += CG_CHUNK, ++ch) {
-                    const int macc = ch & 1;
-                    mbar_wait(bar_mempty + 8 * macc, ((ch >> 1) & 1) ^ 1);
+                    const int acc = ch & 1;
+                    mbar_wait(bar_aempty + 8 * acc, ((ch >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t tmem_main = tmem_base + macc * BN;
+                    const uint32_t tmem_main = tmem_base + acc * 2 * BN, tmem_corr = tmem_main + BN;
                     const int kb1 = min(kb0 + CG_CHUNK, kblocks);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(bar_full + 8 * stage, phase);
@@ -177,44 +224,43 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                         tc_fence_after();
                         const uint32_t src = tiles_base + stage * Cfg::kStageBytes;
                         const uint64_t a_hi = make_kmajor_sw128_desc(src), a_lo = make_kmajor_sw128_desc(src + CG_A_BYTES);
-                        const uint64_t b_hi = make_kmajor_sw128_desc(src + 2 * CG_A_BYTES),
-                                       b_lo = make_kmajor_sw128_desc(src + 2 * CG_A_BYTES + W_BYTES);
+                        const uint64_t b_hl = make_kmajor_sw128_desc(src + 2 * CG_A_BYTES);     // W_hi rows, then W_lo rows
 #pragma unroll
                         for (int k = 0; k < CG_BK / 8; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);
-                            mma_tf32(tmem_main, a_hi + adv, b_hi + adv, IDESC, ((kb - kb0) | k) ? 1u : 0u);
-                            mma_tf32(tmem_corr, a_lo + adv, b_hi + adv, IDESC, (kb | k) ? 1u : 0u);
-                            mma_tf32(tmem_corr, a_hi + adv, b_lo + adv, IDESC, 1u);
+                            mma_tf32(tmem_main, a_hi + adv, b_hl + adv, IDESC_2N, ((kb - kb0) | k) ? 1u : 0u);
+                            mma_tf32(tmem_corr, a_lo + adv, b_hl + adv, IDESC_N, 1u);
                         }
                         mma_commit(bar_empty + 8 * stage);
+                        if (tile == blockIdx.x && kb < 16) CG_STAMP(48 + kb);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    mma_commit(bar_mfull + 8 * macc);                    // this chunk of the main term is complete
+                    mma_commit(bar_afull + 8 * acc);                     // this chunk (main + corrections) is complete
                 }
-                mma_commit(bar_cfull + 8 * cacc);                        // corrections of the tile are complete
+                if (tile == blockIdx.x) CG_STAMP(8);
             }
         }
     } else if (warp < 6) {
-        // ===================== converters (warps 2..5): fp32 tile -> tf32 hi (in place) + lo =====================
+        // ===================== converters (warps 2..5): lo part of the landed fp32 tile =====================
         const int t = threadIdx.x - 64;                                 // 0..127
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(bar_full + 8 * stage, phase);
-                float4* a_hi = reinterpret_cast<float4*>(smem + stage * Cfg::kStageBytes);
+                if (t == 0 && tile == blockIdx.x && kb < 16) CG_STAMP(32 + kb);
+                const float4* a_hi = reinterpret_cast<const float4*>(smem + stage * Cfg::kStageBytes);
                 float4* a_lo = reinterpret_cast<float4*>(smem + stage * Cfg::kStageBytes + CG_A_BYTES);
+                float4 v[CG_A_BYTES / 16 / 128];                        // 8 chunks of 16 bytes per thread
 #pragma unroll
-                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i) {       // 8 chunks of 16 bytes per thread
-                    const float4 v = a_hi[t + i * 128];
-                    float4 h, l;
-                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                    a_hi[t + i * 128] = h;
-                    a_lo[t + i * 128] = l;
-                }
+                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i) v[i] = a_hi[t + i * 128];
+#pragma unroll
+                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i)
+                    a_lo[t + i * 128] = make_float4(cg_lo_part(v[i].x), cg_lo_part(v[i].y), cg_lo_part(v[i].z), cg_lo_part(v[i].w));
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to UMMA
-                mbar_arrive(bar_conv + 8 * stage);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_conv + 8 * stage);              // one arrival per converter warp
+                if (t == 0 && tile == blockIdx.x && kb < 16) CG_STAMP(64 + kb);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -226,86 +272,66 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int row = q * 32 + lane;                                  // accumulator row = pixel of the tile
         const int ty = row / P.tw, tx = row - ty * P.tw;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + half * CW;
-        int it = 0, ch = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        int ch = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int b = tile / tiles_per_img;
             int r = tile - b * tiles_per_img;
             const int nt = r % P.tiles_n; r /= P.tiles_n;
             const int x = (r % P.tiles_x) * P.tw + tx, y = (r / P.tiles_x) * P.th + ty;
             const int n0 = nt * BN + half * CW;
-            // ---- sum of the main-term chunks, round-to-nearest, in registers
+            // ---- sum of the chunks (main + corrections), round-to-nearest, in registers
             float sum[CW];
 #pragma unroll
             for (int j = 0; j < CW; ++j) sum[j] = 0.f;
             for (int kb0 = 0; kb0 < kblocks; kb0 += CG_CHUNK, ++ch) {
-                const int macc = ch & 1;
-                mbar_wait(bar_mfull + 8 * macc, (ch >> 1) & 1);
+                const int acc = ch & 1;
+                mbar_wait(bar_afull + 8 * acc, (ch >> 1) & 1);
                 tc_fence_after();
+                if (warp == 6 && lane == 0 && tile == blockIdx.x && kb0 < 32) CG_STAMP(80 + kb0 / CG_CHUNK);
 #pragma unroll
                 for (int c = 0; c < CW / 32; ++c) {
                     float v[32];
-                    tmem_ld32(lane_base + macc * BN + c * 32, v);
+                    tmem_ld32(lane_base + acc * 2 * BN + BN + c * 32, v);           // corrections first (small)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
+                    tmem_ld32(lane_base + acc * 2 * BN + c * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_mempty + 8 * macc);
+                if (lane == 0) mbar_arrive(bar_aempty + 8 * acc);
             }
-            // ---- + corrections, then bias / residual / activation / store
-            const int cacc = it & 1;
-            mbar_wait(bar_cfull + 8 * cacc, (it >> 1) & 1);
-            tc_fence_after();
-            const bool live = x < P.W && y < P.H;
-            const size_t pix = ((size_t)b * P.H + y) * P.W + x;
-            float* __restrict__ orow = P.out + pix * P.ldo + n0;
-            const float* __restrict__ rrow = P.residual ? P.residual + pix * P.ldr + n0 : nullptr;
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
-                                (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+            if (warp == 6 && lane == 0 && tile == blockIdx.x) CG_STAMP(9);
+            // ---- bias / residual / activation / store
+            if (x < P.W && y < P.H) {
+                const size_t pix = ((size_t)b * P.H + y) * P.W + x;
+                float* __restrict__ orow = P.out + pix * P.ldo + n0;
+                const float* __restrict__ rrow = P.residual ? P.residual + pix * P.ldr + n0 : nullptr;
+                const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
+                                    (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
 #pragma unroll
-            for (int c = 0; c < CW / 32; ++c) {
-                float v[32];
-                tmem_ld32(lane_base + (2 + cacc) * BN + c * 32, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += sum[c * 32 + j];
-                const int col0 = n0 + c * 32;
-                if (live && col0 < P.Cout) {
-                    const bool full = col0 + 32 <= P.Cout;
-                    if (P.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += (full || col0 + j < P.Cout) ? __ldg(P.bias + col0 + j) : 0.f;
-                    }
-                    if (full && vec_ok) {
-                        if (rrow) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + c * 32 + j));
-                                v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(orow + c * 32 + j) =
-                                make_float4(cg_activate(v[j], P.act, P.slope), cg_activate(v[j + 1], P.act, P.slope),
-                                            cg_activate(v[j + 2], P.act, P.slope), cg_activate(v[j + 3], P.act, P.slope));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < P.Cout) {
-                                const float rv = rrow ? __ldg(rrow + c * 32 + j) : 0.f;
-                                orow[c * 32 + j] = cg_activate(v[j] + rv, P.act, P.slope);
-                            }
+                for (int c = 0; c < CW / 32; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= P.Cout) break;
+                    float (&v)[32] = *reinterpret_cast<float (*)[32]>(&sum[c * 32]);
+                    const float* rr = rrow ? rrow + c * 32 : nullptr;
+                    switch (P.act) {
+                        case CAMLI_ACT_RELU: cg_store32<CAMLI_ACT_RELU>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
+                        case CAMLI_ACT_LEAKY: cg_store32<CAMLI_ACT_LEAKY>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
+                        case CAMLI_ACT_TANH: cg_store32<CAMLI_ACT_TANH>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
+                        case CAMLI_ACT_SIGMOID: cg_store32<CAMLI_ACT_SIGMOID>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
+                        default: cg_store32<CAMLI_ACT_NONE>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_cempty + 8 * cacc);
+            if (warp == 6 && lane == 0 && tile == blockIdx.x) CG_STAMP(10);
         }
     }
 done:
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) CG_STAMP(11);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
@@ -346,6 +372,14 @@ int launch_conv_gemm(const CUtensorMap& mx, const CUtensorMap& mwh, const CUtens
 }
 
 }  // namespace
+
+// Diagnostics: attach a device buffer of >= 128 int64 that CTA 0 of every following camli_conv_gemm launch
+// stamps with SM-clock values of its pipeline events (scripts/conv_gemm_timeline.py); NULL detaches.
+static long long* camli_cg_timeline = nullptr;
+extern "C" int camli_conv_gemm_set_timeline(long long* device_buffer) {
+    camli_cg_timeline = device_buffer;
+    return CAMLI_OK;
+}
 
 extern "C" int camli_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
     if (n < 0) return CAMLI_EINVAL;
@@ -391,7 +425,7 @@ extern "C" int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int
     }
     if (bn != 32 && bn != 64 && bn != 128) return CAMLI_EINVAL;
     P.tiles_n = camli_div_up(Cout, bn);
-    P.bias = bias; P.residual = residual; P.ldr = ldr; P.out = out; P.ldo = ldo; P.act = act; P.slope = slope;
+    P.bias = bias; P.residual = residual; P.ldr = ldr; P.out = out; P.ldo = ldo; P.act = act; P.slope = slope; P.timeline = camli_cg_timeline;
     const long long total = (long long)B * P.tiles_y * P.tiles_x * P.tiles_n;
     if (total > 2147483647LL) return CAMLI_EUNSUPPORTED;
 

@@ -6,6 +6,8 @@ out separately (mlp.py:41-128)."""
 import torch
 import torch.nn as nn
 
+from . import tc
+
 
 class LayerNormCF(nn.Module):
     """LayerNorm over the channel axis of a channel-first tensor (mlp.py:5-38)."""
@@ -61,17 +63,20 @@ class _ConvNormAct(nn.Module):
         self.act_fn = _ACTS[act]()
         self.act = act
 
+    def _foldable(self):
+        n = self.norm_fn
+        return isinstance(n, nn.Identity) or (isinstance(n, nn.modules.batchnorm._BatchNorm) and not n.training)
+
     def forward(self, x):
+        if self.ND == 2 and tc.fused(x) and self._foldable():          # conv + norm + activation: one tcgen05 kernel
+            return tc.conv2d(x, self.conv_fn, self.act, 0.1, bn=self.norm_fn)
         return self.act_fn(self.norm_fn(self.conv_fn(x)))
 
     def forward_rows(self, x):
         """Channel-last evaluation of a 1x1 layer: x [..., C_in] -> [..., C_out] (one GEMM + epilogue)."""
-        n = self.norm_fn
-        foldable = isinstance(n, nn.Identity) or (isinstance(n, nn.modules.batchnorm._BatchNorm) and not n.training)
-        if not foldable or self.conv_fn.weight[0, 0].numel() != 1:     # training-mode norm or a real kernel window
+        if not self._foldable() or self.conv_fn.weight[0, 0].numel() != 1:     # training-mode norm or a real kernel window
             return self.forward(x.movedim(-1, 1)).movedim(1, -1)
-        w, b = self.folded()
-        return self.act_fn(torch.nn.functional.linear(x, w, b))
+        return tc.linear(x, self.conv_fn.weight, self.conv_fn.bias, self.act, 0.1, bn=self.norm_fn)
 
     def folded(self):
         """(weight [O,I], bias [O]) of the 1x1 convolution with an eval-mode BatchNorm folded in."""

@@ -4,7 +4,7 @@ computed by the fused grouping kernels of camliflow_b200.ops."""
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, tc
 from .csrc import k_nearest_neighbor
 from .mlp import MLP1d, MLP2d, LayerNormCF, _ACTS
 
@@ -42,6 +42,7 @@ class PointConv(nn.Module):
         if act not in ("relu", "leaky_relu", None):
             raise NotImplementedError("Unknown activation function: %s" % act)
         self.act_fn = _ACTS[act]()
+        self.act = act
         self._slope = {"relu": 0.0, "leaky_relu": 0.1, None: 1.0}[act]
 
     def forward(self, xyz, features, sampled_xyz=None, knn_indices=None):
@@ -51,6 +52,10 @@ class PointConv(nn.Module):
         table = _neighbor_table(xyz, sampled_xyz, knn_indices, self.k)
         rows = ops.rows_of(torch.cat([xyz, features], dim=1))                      # [B,N,3+C]
         grouped = ops.pointconv_group(rows, sampled_xyz, table, self.k, self.weight_net, self._slope)
+        n = self.norm_fn
+        if tc.fused(grouped) and (isinstance(n, nn.Identity) or (isinstance(n, nn.BatchNorm1d) and not n.training)):
+            # Linear + BatchNorm (running statistics, folded) + activation: one tensor-core kernel
+            return tc.linear(grouped, self.linear.weight, self.linear.bias, self.act, 0.1, bn=n).transpose(1, 2)
         out = self.linear(grouped).transpose(1, 2)                                 # [B,O,S]
         return self.act_fn(self.norm_fn(out))
 

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, tc
 from .mlp import Conv2dNormRelu
 from .utils import convex_upsample, mesh_grid
 
@@ -53,14 +53,21 @@ class _Bottleneck(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(c_in, c_out, 1, stride, bias=False), nn.BatchNorm2d(c_out))
 
     def _forward_fused(self, x):
+        """conv+BN(+residual)+ReLU groups as single kernels: the stride-1 ones on the tcgen05 implicit-GEMM
+        kernel (fp32-accurate 3xTF32), the two stride-2 ones of layer2.0 through cuDNN's fused epilogues."""
         one, zero = (1, 1), (0, 0)
-        y = torch.cudnn_convolution_relu(x, *_folded(self, "1", self.conv1, self.bn1), one, zero, one, 1)
-        y = torch.cudnn_convolution_relu(y, *_folded(self, "2", self.conv2, self.bn2), self.conv2.stride, one, one, 1)
+        y = tc.conv2d(x, self.conv1, "relu", bn=self.bn1)
+        if self.conv2.stride == one:
+            y = tc.conv2d(y, self.conv2, "relu", bn=self.bn2)
+        else:
+            y = torch.cudnn_convolution_relu(y, *_folded(self, "2", self.conv2, self.bn2), self.conv2.stride, one, one, 1)
         if self.downsample is not None:
-            w, b = _folded(self, "d", self.downsample[0], self.downsample[1])
-            x = F.conv2d(x, w, b, self.downsample[0].stride)
-        w, b = _folded(self, "3", self.conv3, self.bn3)
-        return torch.cudnn_convolution_add_relu(y, w, x, 1.0, b, one, zero, one, 1)
+            if self.downsample[0].stride == one:
+                x = tc.conv2d(x, self.downsample[0], None, bn=self.downsample[1])
+            else:
+                w, b = _folded(self, "d", self.downsample[0], self.downsample[1])
+                x = F.conv2d(x, w, b, self.downsample[0].stride)
+        return tc.conv2d(y, self.conv3, "relu", bn=self.bn3, residual=x)
 
     def forward(self, x):
         if _fused_inference(x):
@@ -116,8 +123,8 @@ class Correlation2D(nn.Module):
         self.cost_volume_pyramid = None
 
     def build_cost_volume_pyramid(self, fmap1, fmap2):
-        fmap1 = self.fnet_aligner(fmap1.float())
-        fmap2 = self.fnet_aligner(fmap2.float())
+        fmap1 = tc.conv2d(fmap1.float(), self.fnet_aligner)
+        fmap2 = tc.conv2d(fmap2.float(), self.fnet_aligner)
         self.cost_volume_pyramid = ops.corr2d_build(fmap1, fmap2, self.num_levels)
 
     def forward(self, coords):
@@ -162,9 +169,9 @@ class GRU2D(nn.Module):
         """One merged z|r convolution, one gate kernel (sigmoids, r*h, [r*h | x] assembly), the q
         convolution and one update kernel -- 5 launches instead of ~12."""
         w, b = self._merged_zr(convz, convr)
-        zr = F.conv2d(torch.cat([h, x], dim=1), w, b, padding=convz.padding)
+        zr = tc.conv2d_weights(torch.cat([h, x], dim=1), w, b, convz.padding)
         z, rhx = ops.gru_gate(zr, h, x)
-        return ops.gru_update(z, h, convq(rhx), fix_nonfinite=last)
+        return ops.gru_update(z, h, tc.conv2d(rhx, convq), fix_nonfinite=last)
 
     def forward(self, h, x):
         if h.is_cuda and not (torch.is_grad_enabled() and (h.requires_grad or x.requires_grad or self.convz1.weight.requires_grad)):
@@ -188,6 +195,15 @@ class MotionEncoder2D(nn.Module):
         self.conv = nn.Conv2d(64 + 192, 128 - 2, kernel_size=3, padding=1)
 
     def forward(self, flow, corr):
+        if tc.fused(corr):
+            # every convolution with its ReLU in one kernel; the two branches write straight into the halves
+            # of one channel-last buffer (no torch.cat)
+            B, _, H, W = corr.shape
+            cf = torch.empty((B, H, W, 192 + 64), dtype=torch.float32, device=corr.device)
+            tc.conv2d(tc.conv2d(corr, self.conv_c1, "relu"), self.conv_c2, "relu", out=cf[..., :192])
+            tc.conv2d(tc.conv2d(flow, self.conv_f1, "relu"), self.conv_f2, "relu", out=cf[..., 192:])
+            out = torch.nan_to_num(tc.conv2d(cf.permute(0, 3, 1, 2), self.conv, "relu"))
+            return torch.cat([out, flow], dim=1)
         c = F.relu(self.conv_c2(F.relu(self.conv_c1(corr))))
         f = F.relu(self.conv_f2(F.relu(self.conv_f1(flow))))
         out = torch.nan_to_num(F.relu(self.conv(torch.cat([c, f], dim=1))))
@@ -203,7 +219,7 @@ class FlowHead2D(nn.Module):
         self.conv2 = nn.Conv2d(hidden_dim, 2, kernel_size=3, padding=1)
 
     def forward(self, x):
-        return torch.nan_to_num(self.conv2(F.relu(self.conv1(x))).float())
+        return torch.nan_to_num(tc.conv2d(tc.conv2d(x, self.conv1, "relu"), self.conv2).float())
 
 
 class ConvexUpsampler2D(nn.Module):
@@ -215,7 +231,8 @@ class ConvexUpsampler2D(nn.Module):
                                   nn.Conv2d(256, 64 * 9, 1, padding=0))
 
     def forward(self, h, flow):
-        return convex_upsample(flow, 0.25 * self.mask(h.float()))
+        mask = tc.conv2d(tc.conv2d(h.float(), self.mask[0], "relu"), self.mask[2])
+        return convex_upsample(flow, 0.25 * mask)
 
 
 class RAFTCore(nn.Module):
@@ -237,7 +254,7 @@ class RAFTCore(nn.Module):
 
     def forward(self, image1, image2):
         self.correlation.build_cost_volume_pyramid(self.fnet(image1), self.fnet(image2))
-        h, x = torch.split(self.cnet_aligner(self.cnet(image1)), [self.hidden_dim, self.context_dim], dim=1)
+        h, x = torch.split(tc.conv2d(self.cnet(image1), self.cnet_aligner), [self.hidden_dim, self.context_dim], dim=1)
         h, x = torch.tanh(h), torch.relu(x)
         B, _, H, W = image1.shape
         grid = mesh_grid(B, H // 8, W // 8, device=image1.device)

@@ -1,0 +1,121 @@
+"""Layer-level doorway to the tensor-core implicit-GEMM kernel (ops.conv_gemm / camli_conv_gemm).
+
+`conv2d` / `linear` evaluate an nn.Conv2d / nn.Conv1d(1) / nn.Linear -- optionally followed by an
+eval-mode BatchNorm (folded), a residual add and an activation -- as ONE kernel on channel-last
+data.  They are inference paths (no autograd): under autograd, or for a layer the kernel does not
+cover (stride 2, C_in % 4 != 0, training-mode norm), the same arithmetic runs through torch
+(cuDNN / cuBLAS) so callers never branch."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+ENABLED = True          # tests / A-B benchmarks flip this to route everything through torch
+
+_TORCH_ACTS = {
+    None: lambda v, s: v,
+    "relu": lambda v, s: torch.relu(v),
+    "leaky_relu": lambda v, s: F.leaky_relu(v, s),
+    "tanh": lambda v, s: torch.tanh(v),
+    "sigmoid": lambda v, s: torch.sigmoid(v),
+}
+
+
+def _bn_foldable(bn):
+    return bn is None or isinstance(bn, nn.Identity) or (isinstance(bn, nn.modules.batchnorm._BatchNorm) and not bn.training)
+
+
+def _fold(weight, bias, bn):
+    """(weight, bias) with an eval-mode BatchNorm folded in (weight: [O, ...])."""
+    if bn is None or isinstance(bn, nn.Identity):
+        return weight, bias
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = weight * scale.view(-1, *([1] * (weight.dim() - 1)))
+    b = bn.bias - bn.running_mean * scale
+    if bias is not None:
+        b = b + bias * scale
+    return w, b
+
+
+def _key_params(weight, bias, bn):
+    if bn is None or isinstance(bn, nn.Identity):
+        return [weight, bias]
+    return [weight, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+
+def fused(x):
+    return ENABLED and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
+
+
+def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
+    """act(bn(conv(x)) + residual) for an nn.Conv2d on a logical [B,C,H,W] tensor.  Fused route: channel-last
+    storage in, channel-last storage out (`out`: optional [B,H,W,Cout] channel-last destination view, e.g. a
+    channel slice of a concatenation buffer).  Returns the logical [B,Cout,H,W] result."""
+    kh, kw = conv.kernel_size
+    if (fused(x) and _bn_foldable(bn) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.padding == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1 and conv.in_channels % 4 == 0):
+        rows = x.permute(0, 2, 3, 1)
+        if not ops.conv_gemm_ok(rows, kh, kw):
+            rows = rows.contiguous()
+        if ops.conv_gemm_ok(rows, kh, kw):
+            O = conv.out_channels
+
+            def build():
+                w, b = _fold(conv.weight, conv.bias, bn)
+                return w.permute(0, 2, 3, 1).reshape(O, -1), b
+
+            w_hi, w_lo, bias = ops.tc_weight(_key_params(conv.weight, conv.bias, bn), build)
+            res = None
+            if residual is not None:
+                res = residual.permute(0, 2, 3, 1)
+                if not ops._pixel_layout(res)[1]:
+                    res = res.contiguous()
+            y = ops.conv_gemm(rows, w_hi, w_lo, kh, kw, bias, act, slope, res, out)
+            return y.permute(0, 3, 1, 2)
+    y = conv(x)
+    if bn is not None:
+        y = bn(y)
+    if residual is not None:
+        y = y + residual
+    y = _TORCH_ACTS[act](y, slope)
+    if out is not None:
+        out.copy_(y.permute(0, 2, 3, 1))
+        return out.permute(0, 3, 1, 2)
+    return y
+
+
+def conv2d_weights(x, weight, bias, padding, act=None, slope=0.1, out=None):
+    """Same for an explicit stride-1 (weight [O,I,kh,kw], bias) pair -- e.g. two convolutions merged into one;
+    `weight` / `bias` must be long-lived tensors (they key the split cache)."""
+    O, I, kh, kw = weight.shape
+    if fused(x) and tuple(padding) == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1 and I % 4 == 0:
+        rows = x.permute(0, 2, 3, 1)
+        if not ops.conv_gemm_ok(rows, kh, kw):
+            rows = rows.contiguous()
+        if ops.conv_gemm_ok(rows, kh, kw):
+            w_hi, w_lo, b = ops.tc_weight([weight, bias], lambda: (weight.permute(0, 2, 3, 1).reshape(O, -1), bias))
+            return ops.conv_gemm(rows, w_hi, w_lo, kh, kw, b, act, slope, None, out).permute(0, 3, 1, 2)
+    y = _TORCH_ACTS[act](F.conv2d(x, weight, bias, padding=padding), slope)
+    if out is not None:
+        out.copy_(y.permute(0, 2, 3, 1))
+        return out.permute(0, 3, 1, 2)
+    return y
+
+
+def linear(x, weight, bias=None, act=None, slope=0.1, bn=None):
+    """act(bn(x @ weight.T + bias)) on channel-last rows x [..., K]; weight [N, K] or a 1x1 conv weight
+    [N, K, 1(, 1)]."""
+    w2 = weight.flatten(1)
+    K = w2.shape[1]
+    if fused(x) and _bn_foldable(bn) and K % 4 == 0 and x.shape[-1] == K:
+        rows = x if x.is_contiguous() else x.contiguous()
+        if rows.data_ptr() % 16 == 0:
+            w_hi, w_lo, b = ops.tc_weight(_key_params(weight, bias, bn), lambda: _fold(weight.flatten(1), bias, bn))
+            return ops.linear_rows(rows, w_hi, w_lo, b, act, slope)
+    if bn is not None and not isinstance(bn, nn.Identity):
+        if not _bn_foldable(bn):
+            y = bn(F.linear(x, w2, bias).movedim(-1, 1)).movedim(1, -1)
+            return _TORCH_ACTS[act](y, slope)
+        w2, bias = _fold(w2, bias, bn)
+    return _TORCH_ACTS[act](F.linear(x, w2, bias), slope)

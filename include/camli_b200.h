@@ -297,6 +297,10 @@ int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int64_t ldx,
                     const float* bias, const float* residual, int64_t ldr,
                     int act, float slope, float* out, int64_t ldo, int tile_n, void* stream);
 
+/* Diagnostics for camli_conv_gemm: a device buffer of >= 128 int64 that CTA 0 of every following launch stamps
+ * with SM-clock values of its pipeline events (scripts/conv_gemm_timeline.py); NULL detaches (default). */
+int camli_conv_gemm_set_timeline(long long* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

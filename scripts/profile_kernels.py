@@ -50,6 +50,18 @@ def main():
             "backwarp_3d_2048": lambda: ops.backwarp_3d(xyz, xyz, flow, 3),
             "fps_2x8192_s4096": lambda: furthest_point_sampling(pc, 4096),
         }
+        # tensor-core linear / convolution kernel at the shapes of the model (B, H, W, Cin, Cout, kh, kw)
+        for (cb, ch, cw, ci, co, kh, kw) in [(1, 1, 2048, 384, 128, 1, 1), (1, 1, 2048, 128, 128, 1, 1),
+                                             (1, 1, 4096, 1584, 96, 1, 1), (1, 68, 120, 324, 256, 1, 1),
+                                             (1, 68, 120, 256, 192, 3, 3), (1, 68, 120, 384, 256, 1, 5),
+                                             (1, 68, 120, 128, 256, 3, 3), (2, 136, 240, 64, 64, 3, 3),
+                                             (2, 136, 240, 256, 64, 1, 1), (2, 136, 240, 64, 256, 1, 1),
+                                             (2, 68, 120, 128, 128, 3, 3), (2, 68, 120, 512, 128, 1, 1)]:
+            xin = torch.randn(cb, ch, cw, ci, generator=g).to(dev)
+            wt = (torch.randn(co, kh * kw * ci, generator=g) / (kh * kw * ci) ** 0.5).to(dev)
+            w_hi, w_lo, _ = ops.tc_weight([wt], lambda wt=wt: (wt, None))
+            cases["conv_gemm_%dx%dx%d_%d->%d_%dx%d" % (cb, ch, cw, ci, co, kh, kw)] = \
+                lambda xin=xin, w_hi=w_hi, w_lo=w_lo, kh=kh, kw=kw: ops.conv_gemm(xin, w_hi, w_lo, kh, kw, None, "relu")
         out = {}
         for name, fn in cases.items():
             fn()
