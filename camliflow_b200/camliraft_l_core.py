@@ -90,10 +90,39 @@ class GRU3D(nn.Module):
     def forward_rows(self, xyz, h, x, knn_indices=None, cache=None):
         kw = dict(knn_indices=knn_indices, cache=cache)
         hx = torch.cat([h, x], dim=-1)
+        if tc.fused(h) and knn_indices is not None and cache is not None and self._mergeable():
+            return self._forward_fused(xyz, h, x, hx, knn_indices, cache)
         z = torch.sigmoid(self.conv_z.forward_rows(xyz, hx, **kw))
         r = torch.sigmoid(self.conv_r.forward_rows(xyz, hx, **kw))
         q = torch.tanh(self.conv_q.forward_rows(xyz, torch.cat([r * h, x], dim=-1), **kw))
         return (1 - z) * h + z * q
+
+    def _mergeable(self):
+        layers = [m.mlp.convs[0] for m in (self.conv_z, self.conv_r)]
+        return all(len(m.mlp.convs) == 1 for m in (self.conv_z, self.conv_r)) and \
+            all(isinstance(c.norm_fn, nn.Identity) and c.act is None for c in layers) and self.conv_z.k == self.conv_r.k
+
+    def _forward_fused(self, xyz, h, x, hx, table, cache):
+        """The z and r point convolutions read the same input over the same neighbours: ONE 256-wide GEMM, ONE
+        gather-max over the concatenated WeightNet caches, then the gate / update kernels of the ConvGRU
+        (6 launches instead of 19)."""
+        cz, cr = self.conv_z.mlp.convs[0].conv_fn, self.conv_r.mlp.convs[0].conv_fn
+        key = tuple((p.data_ptr(), p._version) for p in (cz.weight, cz.bias, cr.weight, cr.bias))
+        hit = self.__dict__.get("_zr_linear")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, torch.cat([cz.weight, cr.weight], 0).contiguous(), torch.cat([cz.bias, cr.bias], 0).contiguous())
+            self.__dict__["_zr_linear"] = hit
+        slot = ("zr", id(self))
+        w_zr = cache.get(slot)
+        if w_zr is None:                       # WeightNet outputs of both layers side by side: [B,S,k,2H]
+            k = self.conv_z.k
+            w_zr = torch.cat([ops.pointconv_dw_weights(xyz, xyz, table, k, m.weight_net) for m in (self.conv_z, self.conv_r)], -1)
+            cache[slot] = w_zr
+        zr = ops.pointconv_dw_gather_max(tc.linear(hx, hit[1], hit[2]), w_zr, table, self.conv_z.k)
+        z, rhx = ops.gru_gate_rows(zr, h, x)
+        q = self.conv_q.forward_rows(xyz, rhx, knn_indices=table, cache=cache)
+        return ops.gru_update_rows(z, h, q)
 
 
 class MotionEncoder3D(nn.Module):

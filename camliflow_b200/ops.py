@@ -235,6 +235,27 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
     return out
 
 
+def conv_small_n(x_bhwc, w2d, kh, kw, bias=None, act=None, slope=0.1, out=None):
+    """Stride-1 "same" convolution / linear layer with Cout <= 4 on the CUDA cores (camli_conv_small_n):
+    x_bhwc [B,H,W,Cin] channel-last view, w2d [Cout, kh*kw*Cin] (OHWI, fp32)."""
+    _need_cuda(x_bhwc, w2d)
+    _no_grad("conv_small_n", x_bhwc, w2d)
+    B, H, W, Cin = x_bhwc.shape
+    Cout = w2d.shape[0]
+    assert w2d.shape[1] == kh * kw * Cin and w2d.is_contiguous()
+    ldx, ok = _pixel_layout(x_bhwc)
+    if not ok or Cin % 4:
+        raise RuntimeError("conv_small_n: input must be a 16-byte aligned channel-last view with Cin % 4 == 0")
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x_bhwc.device)
+    ldo = _pixel_layout(out)[0]
+    with torch.cuda.device(x_bhwc.device):
+        native.call("camli_conv_small_n", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w2d), i32(Cout),
+                    i32(kh), i32(kw), ptr(bias), i32(ACT_CODES[act]), ctypes.c_float(slope), ptr(out), i64(ldo), stream(),
+                    algo_bytes=B * H * W * (Cin + Cout) * 4, flops=2 * B * H * W * Cout * kh * kw * Cin)
+    return out
+
+
 def linear_rows(x, w_hi, w_lo, bias=None, act=None, slope=0.1, residual=None):
     """x [..., K] contiguous rows -> [..., N] through conv_gemm (1x1)."""
     K = x.shape[-1]
@@ -469,6 +490,34 @@ def gru_update(z, h, q, fix_nonfinite=False):
         native.call("camli_gru_update", i64(out.numel()), ptr(z_r), ptr(h_r), ptr(q_r), i32(1 if fix_nonfinite else 0),
                     ptr(out), stream(), algo_bytes=out.numel() * 16)
     return nchw_view(out)
+
+
+def gru_gate_rows(zr, h, x):
+    """Point-branch form of gru_gate on channel-last rows: zr [..., 2H] pre-activation z|r, h [..., H],
+    x [..., X] -> z [..., H], rhx = [sigmoid(r)*h | x] [..., H+X] (models/camliraft_l_core.py:129-132)."""
+    _need_cuda(zr, h, x)
+    _no_grad("gru_gate", zr, h, x)
+    zr, h, x = zr.contiguous(), h.contiguous(), x.contiguous()
+    Hc, X = h.shape[-1], x.shape[-1]
+    rows = h.numel() // Hc
+    z = torch.empty_like(h)
+    rhx = torch.empty(h.shape[:-1] + (Hc + X,), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        native.call("camli_gru_gate", i64(rows), i32(Hc), i32(X), ptr(zr), ptr(h), ptr(x), ptr(z), ptr(rhx), stream(),
+                    algo_bytes=rows * (2 * Hc + Hc + X + Hc + Hc + X) * 4)
+    return z, rhx
+
+
+def gru_update_rows(z, h, q):
+    """h' = (1-z)*h + z*tanh(q) on rows (models/camliraft_l_core.py:133-134)."""
+    _need_cuda(z, h, q)
+    _no_grad("gru_update", z, h, q)
+    z, h, q = z.contiguous(), h.contiguous(), q.contiguous()
+    out = torch.empty_like(h)
+    with torch.cuda.device(h.device):
+        native.call("camli_gru_update", i64(out.numel()), ptr(z), ptr(h), ptr(q), i32(0), ptr(out), stream(),
+                    algo_bytes=out.numel() * 16)
+    return out
 
 
 # ---------------------------------------------------------------- per-launch profiling (bench.py)

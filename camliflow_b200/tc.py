@@ -44,6 +44,23 @@ def _key_params(weight, bias, bn):
     return [weight, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
 
 
+_PLAIN = {}
+
+
+def _plain_weight(key_params, builder):
+    """Cached effective (weight [N, taps*Cin], bias) of a layer for the CUDA-core small-N kernel."""
+    import weakref
+    live = [p for p in key_params if p is not None]
+    key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in live)
+    slot = _PLAIN.get(key[0][0])
+    if slot is None or slot[0] != key or slot[1]() is not live[0]:
+        with torch.no_grad():
+            w2d, bias = builder()
+            slot = (key, weakref.ref(live[0]), w2d.float().contiguous(), None if bias is None else bias.float().contiguous())
+        _PLAIN[key[0][0]] = slot
+    return slot[2], slot[3]
+
+
 def fused(x):
     return ENABLED and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled()
 
@@ -64,6 +81,10 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
             def build():
                 w, b = _fold(conv.weight, conv.bias, bn)
                 return w.permute(0, 2, 3, 1).reshape(O, -1), b
+
+            if O <= 4 and residual is None and O * kh * kw * conv.in_channels * 4 <= 160 * 1024:
+                w2d, bias = _plain_weight(_key_params(conv.weight, conv.bias, bn), build)
+                return ops.conv_small_n(rows, w2d, kh, kw, bias, act, slope, out).permute(0, 3, 1, 2)
 
             w_hi, w_lo, bias = ops.tc_weight(_key_params(conv.weight, conv.bias, bn), build)
             res = None
@@ -108,10 +129,20 @@ def linear(x, weight, bias=None, act=None, slope=0.1, bn=None):
     [N, K, 1(, 1)]."""
     w2 = weight.flatten(1)
     K = w2.shape[1]
-    if fused(x) and _bn_foldable(bn) and K % 4 == 0 and x.shape[-1] == K:
-        rows = x if x.is_contiguous() else x.contiguous()
+    if fused(x) and _bn_foldable(bn) and x.shape[-1] == K:
+        pad = (-K) % 4                          # TMA rows are 16-byte granular: zero-pad ragged inputs (K = 3: flow)
+        rows = F.pad(x, (0, pad)) if pad else (x if x.is_contiguous() else x.contiguous())
         if rows.data_ptr() % 16 == 0:
-            w_hi, w_lo, b = ops.tc_weight(_key_params(weight, bias, bn), lambda: _fold(weight.flatten(1), bias, bn))
+            def build():
+                w, b = _fold(weight.flatten(1), bias, bn)
+                return (F.pad(w, (0, pad)) if pad else w), b
+
+            keys = _key_params(weight, bias, bn)
+            if w2.shape[0] <= 4:
+                w2d, b = _plain_weight(keys, build)
+                out = ops.conv_small_n(rows.reshape(1, 1, -1, K + pad), w2d, 1, 1, b, act, slope)
+                return out.view(*x.shape[:-1], w2.shape[0])
+            w_hi, w_lo, b = ops.tc_weight(keys, build)
             return ops.linear_rows(rows, w_hi, w_lo, b, act, slope)
     if bn is not None and not isinstance(bn, nn.Identity):
         if not _bn_foldable(bn):

@@ -297,6 +297,15 @@ int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int64_t ldx,
                     const float* bias, const float* residual, int64_t ldr,
                     int act, float slope, float* out, int64_t ldo, int tile_n, void* stream);
 
+/*
+ * The same operation for a handful of output channels (Cout <= 4: the last layer of the flow heads,
+ * models/raft_core.py:176, models/camliraft_l_core.py:110) on the CUDA cores, plain fp32 FMA: one warp per
+ * pixel.  w [Cout, kh*kw*Cin] f32 in OHWI order (not split); other arguments as camli_conv_gemm.
+ */
+int camli_conv_small_n(const float* x, int B, int H, int W, int Cin, int64_t ldx, const float* w, int Cout,
+                       int kh, int kw, const float* bias, int act, float slope, float* out, int64_t ldo,
+                       void* stream);
+
 /* Diagnostics for camli_conv_gemm: a device buffer of >= 128 int64 that CTA 0 of every following launch stamps
  * with SM-clock values of its pipeline events (scripts/conv_gemm_timeline.py); NULL detaches (default). */
 int camli_conv_gemm_set_timeline(long long* device_buffer);

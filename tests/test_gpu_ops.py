@@ -320,3 +320,38 @@ def test_conv_gemm_channel_slices(dev):
     ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1)).permute(0, 2, 3, 1)
     assert (wide_out[..., 16:64].double() - ref).abs().max().item() <= 2e-5
     assert wide_out[..., :16].abs().max().item() == 0 and wide_out[..., 64:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw,act", [(1, 68, 120, 256, 2, 3, 3, None), (2, 1, 2048, 64, 3, 1, 1, None),
+                                                      (1, 9, 11, 8, 4, 5, 3, "relu"), (1, 5, 7, 12, 1, 1, 1, "sigmoid")])
+def test_conv_small_n(dev, B, H, W, Cin, Cout, kh, kw, act):
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    out = _ops().conv_small_n(x, w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), kh, kw, b, act)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=(kh // 2, kw // 2))
+    ref = {None: lambda v: v, "relu": torch.relu, "sigmoid": torch.sigmoid}[act](ref).permute(0, 2, 3, 1)
+    assert (out.double() - ref).abs().max().item() <= 5e-6
+
+
+def test_gru3d_fused_matches_layerwise(dev):
+    """GRU3D with the merged z|r point convolution + gate kernels against its layer-by-layer form."""
+    from camliflow_b200 import tc
+    from camliflow_b200.camliraft_l_core import GRU3D
+    g = torch.Generator().manual_seed(34)
+    gru = GRU3D(input_dim=256, hidden_dim=128)
+    for p in gru.parameters():
+        p.data.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    gru = gru.to(dev).eval()
+    xyz = _cloud(1, 700, dev, 35)
+    h, x = torch.randn(1, 700, 128, generator=g).to(dev), torch.randn(1, 700, 256, generator=g).to(dev)
+    nbr = _knn(xyz, xyz, 32)
+    with torch.no_grad():
+        fused = gru.forward_rows(xyz, h, x, nbr, {})
+        tc.ENABLED = False
+        try:
+            plain = gru.forward_rows(xyz, h, x, nbr, {})
+        finally:
+            tc.ENABLED = True
+    _close(fused, plain, 2e-5, rtol=1e-4, what="GRU3D fused")
