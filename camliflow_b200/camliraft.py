@@ -1,11 +1,13 @@
 """CamLiRAFT model wrapper (reference models/camliraft.py:32-73): pad to a multiple of 8,
 ImageNet normalisation, inverse-depth scaling of the clouds, the fused core, and the way back.
-Losses / metric bookkeeping (models/losses.py, models/base.py) are outside this path."""
+The sequence losses of models/losses.py are evaluated when targets are supplied (training step); the metric
+bookkeeping of models/base.py is outside this path."""
 import torch
 import torch.nn as nn
 
 from .camliraft_core import CamLiRAFT_Core
 from .ids import paral2persp, persp2paral
+from .losses import calc_sequence_loss_2d, calc_sequence_loss_3d
 from .utils import InputPadder
 
 
@@ -53,5 +55,11 @@ class CamLiRAFT(nn.Module):
         return preds_2d, preds_3d
 
     def forward(self, inputs):
+        """Inference: the final flows.  With targets in `inputs` (`flow_2d` [B,2|3,H,W], `flow_3d` [B,3|4,N]) also
+        the training loss of the reference (models/camliraft.py:80-86) in `self.loss`, `self.loss2d`, `self.loss3d`."""
         preds_2d, preds_3d = self.predictions(inputs)
+        if "flow_2d" in inputs and "flow_3d" in inputs:
+            self.loss2d = calc_sequence_loss_2d(preds_2d, inputs["flow_2d"].float(), self.cfgs.loss2d)
+            self.loss3d = calc_sequence_loss_3d(preds_3d, inputs["flow_3d"].float(), self.cfgs.loss3d)
+            self.loss = self.loss2d + self.loss3d
         return {"flow_2d": preds_2d[-1], "flow_3d": preds_3d[-1]}

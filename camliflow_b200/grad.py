@@ -1,0 +1,180 @@
+"""Autograd for the fused operators of camliflow_b200.ops (training path, BASELINE config 5).
+
+Forward always runs the fused CUDA kernel.  Backward is one of
+  * a hand-written backward kernel (camli_*_backward in include/camli_b200.h) where the gradient is a
+    scatter / gather the library owns: PointConvDW gather-max, the RAFT correlation lookup, three-NN
+    interpolation, the all-pairs product;
+  * otherwise a *recompute* backward: the operator's formula (the reference's own lines, cited) is
+    re-evaluated with stock differentiable torch ops on the saved inputs and differentiated by autograd.
+    Nothing of the forward's intermediate tensors is kept alive between forward and backward, which is
+    what lets a 10-iteration training graph of two 960x540 pairs fit comfortably.
+
+The neighbour tables (k-NN, nearest projected point) are integer-valued and piecewise constant: they are
+recomputed by the search kernels inside the backward and carry no gradient, exactly like the reference,
+whose `k_nearest_neighbor` is not differentiable either (models/csrc/wrapper.py:106-127)."""
+import torch
+import torch.nn.functional as F
+
+from .csrc import k_nearest_neighbor
+
+
+# --------------------------------------------------------------------------------------- formulas
+def gather_cf(data, idx):
+    """data [B,C,N], idx [B,...] -> [B,C,...] (models/utils.py:62-80)."""
+    B, C = data.shape[:2]
+    flat = idx.reshape(B, 1, -1).expand(B, C, -1)
+    return torch.gather(data, 2, flat).view([B, C] + list(idx.shape[1:]))
+
+
+def gather_rows(rows, idx):
+    """rows [B,N,C], idx [B,S,k] -> [B,S,k,C]."""
+    B, N, C = rows.shape
+    S, k = idx.shape[1:]
+    flat = idx.reshape(B, S * k, 1).expand(B, S * k, C)
+    return torch.gather(rows, 1, flat).view(B, S, k, C)
+
+
+def f_knn_interpolate(input_xyz, input_feat, query_xyz, k):
+    """models/utils.py:130-146."""
+    idx = k_nearest_neighbor(input_xyz.detach(), query_xyz.detach(), k)
+    d = torch.linalg.norm(gather_cf(input_xyz, idx) - query_xyz[..., None], dim=1).clamp(1e-8)
+    w = 1.0 / d
+    w = w / torch.sum(w, -1, keepdim=True)
+    return torch.sum(gather_cf(input_feat, idx) * w[:, None], -1)
+
+
+def f_bilinear_sample_rows(feat2d, uv):
+    """models/utils.py:262-269 -> rows [B,N,C]."""
+    H, W = feat2d.shape[2:]
+    gx = 2.0 * uv[:, 0] / (W - 1) - 1.0
+    gy = 2.0 * uv[:, 1] / (H - 1) - 1.0
+    g = torch.stack([gx, gy], -1)[:, :, None, :]
+    return F.grid_sample(feat2d, g, "bilinear", align_corners=True)[..., 0].transpose(1, 2)
+
+
+def f_corr2d_pool(vol, num_levels):
+    """models/raft_core.py:65-68: vol [B,HW,H,W] -> the list of pooled levels."""
+    B, P, H, W = vol.shape
+    v = vol.reshape(B * P, 1, H, W)
+    pyr = [vol]
+    for _ in range(num_levels - 1):
+        v = F.avg_pool2d(v, 2, stride=2)
+        pyr.append(v.view(B, P, v.shape[-2], v.shape[-1]))
+    return pyr
+
+
+def f_corr2d_lookup(coords, radius, *pyramid):
+    """models/raft_core.py:71-107."""
+    r = radius
+    coords = coords.permute(0, 2, 3, 1).float()
+    B, H, W, _ = coords.shape
+    d = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
+    delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), -1).view(1, 2 * r + 1, 2 * r + 1, 2)
+    out = []
+    for i, vol in enumerate(pyramid):
+        h, w = vol.shape[-2:]
+        c = coords.reshape(B * H * W, 1, 1, 2) / 2 ** i + delta
+        g = torch.cat([2 * c[..., 0:1] / (w - 1) - 1, 2 * c[..., 1:2] / (h - 1) - 1], -1)
+        s = F.grid_sample(vol.reshape(B * H * W, 1, h, w), g, align_corners=True)
+        out.append(s.view(B, H, W, -1))
+    return torch.cat(out, -1).permute(0, 3, 1, 2)
+
+
+def f_corr3d_pool(vol, idx):
+    """models/camliraft_l_core.py:56-60: vol [B,n1,n_in], idx [B,n_out,k] -> [B,n1,n_out]."""
+    return torch.mean(gather_cf(vol, idx), -1)
+
+
+def f_corr3d_lookup_rows(xyz1, W1, b1, W2, b2, k, n_levels, *rest):
+    """models/camliraft_l_core.py:62-98 -> rows [B,n1,32*L]; rest = xyzs2 levels, then pyramid levels."""
+    xyzs2, pyramid = rest[:n_levels], rest[n_levels:]
+    costs = []
+    for xyz2, vol in zip(xyzs2, pyramid):
+        B, n1, n2 = vol.shape
+        idx = k_nearest_neighbor(xyz2.detach(), xyz1.detach(), k)
+        off = gather_cf(xyz2, idx) - xyz1[:, :, :, None]
+        c = torch.gather(vol, 2, idx).view(B, 1, n1, -1)
+        x = torch.cat([off, c], 1)
+        x = F.relu(F.conv2d(x, W1[:, :, None, None], b1))
+        x = F.relu(F.conv2d(x, W2[:, :, None, None], b2))
+        costs.append(x.sum(-1))
+    return torch.cat(costs, 1).transpose(1, 2)
+
+
+def f_pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, *params):
+    """models/point_conv.py:122-127 -> [B,S,k,O]."""
+    x = gather_cf(xyz, knn_idx[:, :, :k]) - sampled_xyz[:, :, :, None]
+    for w, b in zip(params[0::2], params[1::2]):
+        x = F.relu(F.conv2d(x, w[:, :, None, None], b))
+    return x.permute(0, 2, 3, 1)
+
+
+def f_pointconv_group(rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2, slope):
+    """models/point_conv.py:56-66 -> [B,S,16*(3+C)]."""
+    idx = knn_idx[:, :, :k]
+    B, S = idx.shape[:2]
+    g = gather_rows(rows, idx)                                                        # [B,S,k,3+C]
+    off = (g[..., :3] - sampled_xyz.transpose(1, 2)[:, :, None, :]).permute(0, 3, 1, 2)   # [B,3,S,k]
+    w = F.leaky_relu(F.conv2d(off, w1[:, :, None, None], b1), slope)
+    w = F.leaky_relu(F.conv2d(w, w2[:, :, None, None], b2), slope).transpose(1, 2)      # [B,S,16,k]
+    return torch.matmul(w, g).reshape(B, S, -1)
+
+
+def f_clfm_interp(uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W):
+    """models/clfm.py:57-75 before out_conv -> [B,C,H,W]."""
+    B = uv.shape[0]
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=uv.device),
+                            torch.arange(W, dtype=torch.float32, device=uv.device), indexing="ij")
+    grid = torch.stack([xs, ys], 0).reshape(1, 2, -1).expand(B, 2, -1)
+    off = gather_cf(uv, nn_idx) - grid
+    si = torch.cat([off, torch.linalg.norm(off, dim=1, keepdim=True)], 1)[..., None]
+    s = F.leaky_relu(F.conv2d(si, w1[:, :, None, None], b1), 0.1)
+    s = torch.sigmoid(F.conv2d(s, w2[:, :, None, None], b2))
+    feat = gather_cf(feat3d_rows.transpose(1, 2), nn_idx)
+    return (s[..., 0] * feat).view(B, -1, H, W)
+
+
+# --------------------------------------------------------------------------------------- machinery
+def needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+class _Recompute(torch.autograd.Function):
+    """forward: `kernel(*args)` under no_grad; backward: autograd through `formula(*args)` recomputed on
+    detached copies.  `args` may mix tensors and plain Python values; outputs: a tensor or a list of tensors."""
+
+    @staticmethod
+    def forward(ctx, kernel, formula, *args):
+        ctx.formula, ctx.args = formula, args
+        with torch.no_grad():
+            out = kernel(*args)
+        ctx.multi = isinstance(out, (list, tuple))
+        return tuple(out) if ctx.multi else out
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        needs = ctx.needs_input_grad[2:]
+        args = []
+        for a, n in zip(ctx.args, needs):
+            if isinstance(a, torch.Tensor):
+                a = a.detach()
+                if n:
+                    a.requires_grad_(True)
+            args.append(a)
+        with torch.enable_grad():
+            out = ctx.formula(*args)
+        outs = list(out) if isinstance(out, (list, tuple)) else [out]
+        pairs = [(o, g) for o, g in zip(outs, gouts) if g is not None and o.requires_grad]
+        wrt = [a for a, n in zip(args, needs) if n]
+        grads = iter(torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True)
+                     if pairs and wrt else [None] * len(wrt))
+        return (None, None) + tuple(next(grads) if n else None for n in needs)
+
+
+def recompute(kernel, formula, *args):
+    """Run `kernel(*args)`; when a tensor argument requires grad, make the call differentiable through
+    `formula` (see the module docstring)."""
+    if not needs_grad(*args):
+        return kernel(*args)
+    out = _Recompute.apply(kernel, formula, *args)
+    return list(out) if isinstance(out, tuple) else out

@@ -7,7 +7,8 @@
               neighbour's feature vector is one contiguous, coalesced read.
 
 There is no CPU path and no eager-PyTorch fallback: CUDA tensors and a built library are
-required.  Forward only for now: calling these with tensors that require grad raises.
+required.  Every operator is differentiable (camliflow_b200/grad.py): the forward is always the fused
+kernel, the backward a hand-written kernel or a recompute of the operator's formula.
 """
 import ctypes
 import os
@@ -15,7 +16,7 @@ import os
 import torch
 import torch.nn.functional as F
 
-from . import native
+from . import grad, native
 from .csrc import k_nearest_neighbor
 from .native import i32, i64, ptr, stream
 
@@ -75,7 +76,10 @@ def knn_interpolate(input_xyz, input_feat, query_xyz, k=3):
     """Three-NN inverse-distance interpolation fused with the search (models/utils.py:130-146).
     input_xyz [B,3,m], input_feat [B,F,m], query_xyz [B,3,n] -> [B,F,n]."""
     _need_cuda(input_xyz, input_feat, query_xyz)
-    _no_grad("knn_interpolate", input_xyz, input_feat, query_xyz)
+    return grad.recompute(_knn_interpolate, grad.f_knn_interpolate, input_xyz, input_feat, query_xyz, k)
+
+
+def _knn_interpolate(input_xyz, input_feat, query_xyz, k):
     B, Fc, m = input_feat.shape
     n = query_xyz.shape[-1]
     out = torch.empty((B, Fc, n), dtype=torch.float32, device=input_feat.device)
@@ -93,7 +97,8 @@ def knn_interpolate(input_xyz, input_feat, query_xyz, k=3):
 def backwarp_3d(xyz1, xyz2, flow12, k=3):
     """xyz2 + interp(xyz1 + flow12, -flow12)(xyz2) in one kernel (models/utils.py:149-159)."""
     _need_cuda(xyz1, xyz2, flow12)
-    _no_grad("backwarp_3d", xyz1, xyz2, flow12)
+    if grad.needs_grad(xyz1, xyz2, flow12):       # (the models always warp by a detached flow; kept for completeness)
+        return xyz2 + knn_interpolate(xyz1 + flow12, -flow12, xyz2, k)
     xyz1, xyz2, flow12 = xyz1.contiguous(), xyz2.contiguous(), flow12.contiguous()
     B, _, m = xyz1.shape
     n = xyz2.shape[-1]
@@ -109,7 +114,10 @@ def bilinear_sample_rows(feat2d, uv):
     """feat2d [B,C,H,W] (channels_last preferred), uv [B,2,N] pixel coords -> rows [B,N,C]
     (align_corners, zero padding; models/utils.py:262-269)."""
     _need_cuda(feat2d, uv)
-    _no_grad("bilinear_sample", feat2d, uv)
+    return grad.recompute(_bilinear_sample_rows, grad.f_bilinear_sample_rows, feat2d, uv)
+
+
+def _bilinear_sample_rows(feat2d, uv):
     B, C, H, W = feat2d.shape
     N = uv.shape[-1]
     src = nhwc_rows(feat2d)
@@ -145,7 +153,29 @@ ALLPAIRS_IMPL = os.environ.get("CAMLI_ALLPAIRS", "tcgen05")
 def allpairs(a_rows, b_rows, scale):
     """out[b,m,n] = scale * <a_rows[b,m,:], b_rows[b,n,:]>: a_rows [B,M,K], b_rows [B,N,K] -> [B,M,N]."""
     _need_cuda(a_rows, b_rows)
-    _no_grad("allpairs", a_rows, b_rows)
+    if grad.needs_grad(a_rows, b_rows):
+        return _AllPairs.apply(a_rows, b_rows, scale)
+    return _allpairs(a_rows, b_rows, scale)
+
+
+class _AllPairs(torch.autograd.Function):
+    """d/da = scale * gO @ b, d/db = scale * gO^T @ a (the transposed products of the forward GEMM)."""
+
+    @staticmethod
+    def forward(ctx, a_rows, b_rows, scale):
+        ctx.save_for_backward(a_rows, b_rows)
+        ctx.scale = scale
+        return _allpairs(a_rows, b_rows, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        a_rows, b_rows = ctx.saved_tensors
+        ga = torch.bmm(g, b_rows).mul_(ctx.scale) if ctx.needs_input_grad[0] else None
+        gb = torch.bmm(g.transpose(1, 2), a_rows).mul_(ctx.scale) if ctx.needs_input_grad[1] else None
+        return ga, gb, None
+
+
+def _allpairs(a_rows, b_rows, scale):
     B, M, K = a_rows.shape
     N = b_rows.shape[1]
     if ALLPAIRS_IMPL == "cublas" or K % 32 != 0:
@@ -271,11 +301,15 @@ def corr2d_build(fmap1, fmap2, num_levels):
     (models/raft_core.py:56-68).  Returns [B,H*W,h_l,w_l] per level; the coarser levels come from one
     fused pass over level 0."""
     _need_cuda(fmap1, fmap2)
-    _no_grad("corr2d_build", fmap1, fmap2)
     B, C, H, W = fmap1.shape
     a = nhwc_rows(fmap1).view(B, H * W, C)
     b = nhwc_rows(fmap2).view(B, H * W, C)
     vol = allpairs(a, b, 1.0 / C ** 0.5).view(B, H * W, H, W)
+    return grad.recompute(_corr2d_pool, grad.f_corr2d_pool, vol, num_levels)
+
+
+def _corr2d_pool(vol, num_levels):
+    B, _, H, W = vol.shape
     pyr = [vol]
     h, w = H, W
     for _ in range(num_levels - 1):
@@ -293,7 +327,45 @@ def corr2d_lookup(pyramid, coords, radius, channels_last=True):
     """models/raft_core.py:71-107: coords [B,2,H,W] -> logical [B, L*(2r+1)^2, H, W] (NHWC storage when
     channels_last); window index i moves x, j moves y (the reference's meshgrid quirk)."""
     _need_cuda(coords, *pyramid)
-    _no_grad("corr2d_lookup", coords, *pyramid)
+    if grad.needs_grad(coords, *pyramid):
+        return _Corr2dLookup.apply(coords, radius, channels_last, *pyramid)
+    return _corr2d_lookup(pyramid, coords, radius, channels_last)
+
+
+class _Corr2dLookup(torch.autograd.Function):
+    """Backward by the scatter kernel camli_corr2d_lookup_backward: the gradient of volume slice V_l[p] only
+    comes from pixel p's own window, so every (pixel, level) footprint is written by exactly one CTA -- no
+    atomics, deterministic.  The coordinates get no gradient (the models look up at a detached flow,
+    models/camliraft_core.py:105)."""
+
+    @staticmethod
+    def forward(ctx, coords, radius, channels_last, *pyramid):
+        ctx.save_for_backward(coords)
+        ctx.radius, ctx.shapes = radius, [tuple(v.shape) for v in pyramid]
+        return _corr2d_lookup(list(pyramid), coords, radius, channels_last)
+
+    @staticmethod
+    def backward(ctx, g):
+        (coords,) = ctx.saved_tensors
+        grads = _corr2d_lookup_backward(g, coords, ctx.radius, ctx.shapes)
+        return (None, None, None) + tuple(gv if need else None for gv, need in zip(grads, ctx.needs_input_grad[3:]))
+
+
+def _corr2d_lookup_backward(g, coords, radius, shapes):
+    """g: logical [B, L*81, H, W] -> zero-filled gradient volumes [B,HW,h_l,w_l] with the window footprints."""
+    coords = coords.float().contiguous()
+    B, _, H, W = coords.shape
+    g_rows = nhwc_rows(g.float())
+    grads = [torch.zeros(sh, dtype=torch.float32, device=g.device) for sh in shapes]
+    with torch.cuda.device(g.device):
+        native.call("camli_corr2d_lookup_backward", _ptr_array(grads), _int_array([sh[-2] for sh in shapes]),
+                    _int_array([sh[-1] for sh in shapes]), i32(len(shapes)), ptr(coords), ptr(g_rows), i32(B), i32(H), i32(W),
+                    i32(radius), stream(),
+                    algo_bytes=B * H * W * (len(shapes) * ((2 * radius + 2) ** 2 + (2 * radius + 1) ** 2) * 4 + 8))
+    return grads
+
+
+def _corr2d_lookup(pyramid, coords, radius, channels_last):
     coords = coords.float().contiguous()
     B, _, H, W = coords.shape
     L, n_ch = len(pyramid), len(pyramid) * (2 * radius + 1) ** 2
@@ -314,35 +386,44 @@ def corr2d_lookup(pyramid, coords, radius, channels_last=True):
 def corr3d_build(feat1, feat2, xyzs2, k=3):
     """models/camliraft_l_core.py:51-60: feat [B,C,n] -> volumes [B,n1,n2_l]."""
     _need_cuda(feat1, feat2)
-    _no_grad("corr3d_build", feat1, feat2)
     B, C, n1 = feat1.shape
     vol = allpairs(rows_of(feat1.float()), rows_of(feat2.float()), 1.0 / C)
     pyr = [vol]
     for i in range(1, len(xyzs2)):
-        idx = k_nearest_neighbor(xyzs2[i - 1], xyzs2[i], k)
-        n_in, n_out = pyr[-1].shape[-1], xyzs2[i].shape[-1]
-        nxt = torch.empty((B, n1, n_out), dtype=torch.float32, device=vol.device)
-        with torch.cuda.device(vol.device):
-            native.call("camli_corr3d_pool", i32(B), i32(n1), i32(n_in), i32(n_out), i32(k), ptr(pyr[-1]), ptr(idx),
-                        ptr(nxt), stream(), algo_bytes=B * n1 * (n_in + n_out) * 4)
-        pyr.append(nxt)
+        idx = k_nearest_neighbor(xyzs2[i - 1].detach(), xyzs2[i].detach(), k)
+        pyr.append(grad.recompute(_corr3d_pool, grad.f_corr3d_pool, pyr[-1], idx))
     return pyr
+
+
+def _corr3d_pool(vol, idx):
+    B, n1, n_in = vol.shape
+    n_out, k = idx.shape[1], idx.shape[2]
+    vol = vol.contiguous()
+    nxt = torch.empty((B, n1, n_out), dtype=torch.float32, device=vol.device)
+    with torch.cuda.device(vol.device):
+        native.call("camli_corr3d_pool", i32(B), i32(n1), i32(n_in), i32(n_out), i32(k), ptr(vol), ptr(idx),
+                    ptr(nxt), stream(), algo_bytes=B * n1 * (n_in + n_out) * 4)
+    return nxt
 
 
 def corr3d_lookup_rows(xyz1, xyzs2, pyramid, W1, b1, W2, b2):
     """Correlation3D.forward before `merge` (models/camliraft_l_core.py:62-98), every level in one
     launch: rows [B,n1,32*L]."""
     _need_cuda(xyz1, *xyzs2, *pyramid)
-    _no_grad("corr3d_lookup", xyz1, *xyzs2, *pyramid, W1, W2)
+    L = len(pyramid)
+    return grad.recompute(_corr3d_lookup_rows, grad.f_corr3d_lookup_rows, xyz1, W1, b1, W2, b2, 16, L, *xyzs2, *pyramid)
+
+
+def _corr3d_lookup_rows(xyz1, W1, b1, W2, b2, k, L, *rest):
+    xyzs2, pyramid = list(rest[:L]), [v.contiguous() for v in rest[L:]]
+    W1, b1, W2, b2 = W1.contiguous(), b1.contiguous(), W2.contiguous(), b2.contiguous()
     xyz1 = xyz1.contiguous()
     B, _, n1 = xyz1.shape
-    L = len(pyramid)
     out = torch.empty((B, n1, 32 * L), dtype=torch.float32, device=xyz1.device)
     strides = []
     for x in xyzs2:
         s = x.stride()
         strides += [s[0], s[2], s[1]]
-    k = 16
     with torch.cuda.device(xyz1.device):
         native.call("camli_corr3d_lookup", i32(B), i32(n1), i32(L), ptr(xyz1), _ptr_array(xyzs2),
                     _int_array(strides, ctypes.c_int64), _int_array([x.shape[-1] for x in xyzs2]), _ptr_array(pyramid),
@@ -361,8 +442,12 @@ def pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, weight_net):
     params = []
     for c in convs:
         w, b = c.folded()
-        params += [w.contiguous(), b.contiguous()]
-    _no_grad("pointconv_dw_weights", xyz, sampled_xyz, *params)
+        params += [w, b]
+    return grad.recompute(_pointconv_dw_weights, grad.f_pointconv_dw_weights, xyz, sampled_xyz, knn_idx, k, *params)
+
+
+def _pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, *params):
+    params = [p.contiguous() for p in params]
     B, _, N = xyz.shape
     S, K = knn_idx.shape[1], knn_idx.shape[2]
     O = params[4].shape[0]
@@ -382,8 +467,39 @@ def pointconv_dw_gather_max(feat_rows, weights, knn_idx, k):
     """out[b,s,o] = max_j feat_rows[b, idx[b,s,j], o] * weights[b,s,j,o] (models/point_conv.py:126-128):
     feat_rows [B,N,O], weights [B,S,k,O], knn_idx [B,S,K>=k] -> rows [B,S,O]."""
     _need_cuda(feat_rows, weights, knn_idx)
-    _no_grad("pointconv_dw_gather_max", feat_rows, weights)
-    assert feat_rows.is_contiguous() and weights.is_contiguous()
+    if grad.needs_grad(feat_rows, weights):
+        return _DwGatherMax.apply(feat_rows, weights, knn_idx, k)
+    return _pointconv_dw_gather_max(feat_rows, weights, knn_idx, k)
+
+
+class _DwGatherMax(torch.autograd.Function):
+    """Backward by camli_pointconv_dw_gather_max_backward: the arg-max neighbour j* of every (s, o) is found
+    again from the saved inputs; d feat[idx[s,j*], o] += g * w[s,j*,o] (atomic scatter), d w[s,j*,o] = g * feat[...]."""
+
+    @staticmethod
+    def forward(ctx, feat_rows, weights, knn_idx, k):
+        feat_rows, weights = feat_rows.contiguous(), weights.contiguous()
+        ctx.save_for_backward(feat_rows, weights, knn_idx)
+        ctx.k = k
+        return _pointconv_dw_gather_max(feat_rows, weights, knn_idx, k)
+
+    @staticmethod
+    def backward(ctx, g):
+        feat_rows, weights, knn_idx = ctx.saved_tensors
+        B, N, O = feat_rows.shape
+        S, K = knn_idx.shape[1], knn_idx.shape[2]
+        g = g.contiguous()
+        g_feat = torch.zeros_like(feat_rows)
+        g_w = torch.zeros_like(weights) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(g.device):
+            native.call("camli_pointconv_dw_gather_max_backward", i32(B), i32(N), i32(S), i32(K), i32(ctx.k), i32(O),
+                        ptr(feat_rows), ptr(weights), ptr(knn_idx.contiguous()), ptr(g), ptr(g_feat), ptr(g_w), stream(),
+                        algo_bytes=B * S * (ctx.k * (2 * O * 4 + 8) + 3 * O * 4))
+        return g_feat if ctx.needs_input_grad[0] else None, g_w, None, None
+
+
+def _pointconv_dw_gather_max(feat_rows, weights, knn_idx, k):
+    feat_rows, weights = feat_rows.contiguous(), weights.contiguous()
     knn_idx = knn_idx.contiguous()
     B, N, O = feat_rows.shape
     S, K = knn_idx.shape[1], knn_idx.shape[2]
@@ -401,8 +517,13 @@ def pointconv_group(rows, sampled_xyz, knn_idx, k, weight_net, negative_slope):
     Returns [B,S,16*(3+C)] in the order the reference's Linear expects (weight-major)."""
     _need_cuda(rows, sampled_xyz, knn_idx)
     (w1, b1), (w2, b2) = weight_net.convs[0].folded(), weight_net.convs[1].folded()
-    _no_grad("pointconv_group", rows, w1, w2)
-    assert rows.is_contiguous() and w1.shape == (8, 3) and w2.shape == (16, 8)
+    return grad.recompute(_pointconv_group, grad.f_pointconv_group, rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2,
+                          negative_slope)
+
+
+def _pointconv_group(rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2, negative_slope):
+    rows = rows.contiguous()
+    assert w1.shape == (8, 3) and w2.shape == (16, 8)
     knn_idx = knn_idx.contiguous()
     B, N, C = rows.shape
     S, K = knn_idx.shape[1], knn_idx.shape[2]
@@ -431,8 +552,11 @@ def clfm_interp(uv, nn_idx, feat3d_rows, score_net, H, W):
     """FusionAwareInterp before out_conv (models/clfm.py:57-75): logical [B,C,H,W], NHWC storage."""
     _need_cuda(uv, nn_idx, feat3d_rows)
     (w1, b1), (w2, b2) = score_net[0].folded(), score_net[1].folded()
-    _no_grad("clfm_interp", uv, feat3d_rows, w1, w2)
-    assert feat3d_rows.is_contiguous()
+    return grad.recompute(_clfm_interp, grad.f_clfm_interp, uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W)
+
+
+def _clfm_interp(uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W):
+    feat3d_rows = feat3d_rows.contiguous()
     B, N, C = feat3d_rows.shape
     uv, nn_idx = uv.contiguous(), nn_idx.contiguous()
     store = torch.empty((B, H, W, C), dtype=torch.float32, device=uv.device)

@@ -306,6 +306,25 @@ int camli_conv_small_n(const float* x, int B, int H, int W, int Cin, int64_t ldx
                        int kh, int kw, const float* bias, int act, float slope, float* out, int64_t ldo,
                        void* stream);
 
+/*
+ * Backward of camli_corr2d_lookup with respect to the volume pyramid (the coordinates carry no gradient: the
+ * models look up at a detached flow, models/camliraft_core.py:105).  grad_volumes[l]: [B,H*W,h_l,w_l] f32,
+ * ZERO-INITIALISED by the caller; grad_out_rows: channel-last [B,H*W,n_levels*(2r+1)^2].  Each (pixel, level)
+ * footprint is written by one CTA: no atomics, deterministic.
+ */
+int camli_corr2d_lookup_backward(float* const* grad_volumes, const int* level_h, const int* level_w, int n_levels,
+                                 const float* coords, const float* grad_out_rows, int B, int H, int W,
+                                 int radius, void* stream);
+
+/*
+ * Backward of camli_pointconv_dw_gather_max: the arg-max neighbour j* of every (centroid s, channel o) is found
+ * again from the saved inputs (first maximum, as torch.max); grad_feat_rows[b, idx[b,s,j*], o] += g * w (atomic),
+ * grad_weights[b,s,j*,o] = g * feat.  Both gradients ZERO-INITIALISED by the caller; grad_weights may be NULL.
+ */
+int camli_pointconv_dw_gather_max_backward(int B, int N, int S, int K, int k, int O, const float* feat_rows,
+                                           const float* weights, const int64_t* knn_idx, const float* grad_out_rows,
+                                           float* grad_feat_rows, float* grad_weights, void* stream);
+
 /* Diagnostics for camli_conv_gemm: a device buffer of >= 128 int64 that CTA 0 of every following launch stamps
  * with SM-clock values of its pipeline events (scripts/conv_gemm_timeline.py); NULL detaches (default). */
 int camli_conv_gemm_set_timeline(long long* device_buffer);

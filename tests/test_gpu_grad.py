@@ -1,0 +1,220 @@
+"""GPU parity of the training path: gradients of the fused operators (kernel forward + hand-written or
+recompute backward, camliflow_b200/grad.py) against torch autograd through the plain-PyTorch formulas of
+tests/torch_ref.py, per operator and through a whole CamLiRAFT training step (forward, sequence losses,
+backward).  Tolerances are written at each comparison."""
+import contextlib
+
+import pytest
+import torch
+
+from tests import torch_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from camliflow_b200 import ops
+    return ops
+
+
+def _knn(a, q, k):
+    from camliflow_b200.csrc import k_nearest_neighbor
+    return k_nearest_neighbor(a, q, k)
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def test_dw_gather_max_backward(dev):
+    g = torch.Generator().manual_seed(41)
+    B, N, S, K, k, O = 2, 600, 500, 32, 16, 125
+    xyz = ((torch.rand(B, 3, N, generator=g) - 0.5) * 10).to(dev)
+    idx = _knn(xyz, xyz[:, :, :S].contiguous(), K)
+    feat = torch.randn(B, N, O, generator=g).to(dev).requires_grad_(True)
+    w = torch.rand(B, S, k, O, generator=g).to(dev).requires_grad_(True)
+    gout = torch.randn(B, S, O, generator=g).to(dev)
+    out = _ops().pointconv_dw_gather_max(feat, w, idx, k)
+    gf, gw = torch.autograd.grad(out, [feat, w], gout)
+    ref = R.pointconv_dw_gather_max(feat.transpose(1, 2), w, idx[:, :, :k]).transpose(1, 2)
+    rf, rw = torch.autograd.grad(ref, [feat, w], gout)
+    assert _rel(out, ref) <= 1e-6
+    assert _rel(gf, rf) <= 1e-5 and _rel(gw, rw) <= 1e-6      # g_feat is an atomic sum: order-dependent rounding
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 64, 24, 40), (2, 32, 17, 30)])
+def test_corr2d_build_lookup_backward(dev, B, C, H, W):
+    g = torch.Generator().manual_seed(42)
+    f1 = torch.randn(B, C, H, W, generator=g).to(dev).requires_grad_(True)
+    f2 = torch.randn(B, C, H, W, generator=g).to(dev).requires_grad_(True)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    coords = (torch.stack([xs, ys], 0)[None] + torch.randn(B, 2, H, W, generator=g) * 3).to(dev)
+    coords[:, :, 0, 0] = torch.tensor([W + 20.0, -30.0], device=dev)           # a window entirely outside the map
+    gout = torch.randn(B, 4 * 81, H, W, generator=g).to(dev)
+    out = _ops().corr2d_lookup(_ops().corr2d_build(f1, f2, 4), coords, 4)
+    g1, g2 = torch.autograd.grad(out, [f1, f2], gout)
+    ref = R.corr2d_lookup(R.corr2d_build(f1, f2, 4), coords, 4)
+    r1, r2 = torch.autograd.grad(ref, [f1, f2], gout)
+    assert _rel(out, ref) <= 2e-5
+    assert _rel(g1, r1) <= 2e-4 and _rel(g2, r2) <= 2e-4
+
+
+def test_recompute_backward_operators(dev):
+    """knn_interpolate, corr3d build + lookup, PointConv grouping, PointConvDW WeightNet, CLFM interpolation:
+    kernel forward, formula-recompute backward."""
+    from camliflow_b200.mlp import Conv2dNormRelu, MLP2d
+    ops = _ops()
+    g = torch.Generator().manual_seed(43)
+    B, n, C = 1, 512, 32
+    xyz1 = ((torch.rand(B, 3, n, generator=g) - 0.5) * 10).to(dev)
+    xyz2 = (xyz1.cpu() + torch.randn(B, 3, n, generator=g) * 0.1).to(dev)
+    xyzs2 = [xyz2, xyz2[:, :, :256].contiguous(), xyz2[:, :, :128].contiguous()]
+    f1 = torch.randn(B, C, n, generator=g).to(dev).requires_grad_(True)
+    f2 = torch.randn(B, C, n, generator=g).to(dev).requires_grad_(True)
+    cost = MLP2d(4, [32, 32], act="relu").to(dev)
+    P = [cost.convs[0].conv_fn.weight.flatten(1), cost.convs[0].conv_fn.bias, cost.convs[1].conv_fn.weight.flatten(1),
+         cost.convs[1].conv_fn.bias]
+
+    pyr = ops.corr3d_build(f1, f2, xyzs2)
+    out = ops.corr3d_lookup_rows(xyz1, xyzs2, pyr, *P)
+    gout = torch.randn(out.shape, generator=g).to(dev)
+    got = torch.autograd.grad(out, [f1, f2] + list(cost.parameters()), gout)
+    rp = [torch.bmm(f1.transpose(1, 2), f2) / C]
+    for i in (1, 2):
+        rp.append(R.corr3d_pool(rp[-1], _knn(xyzs2[i - 1], xyzs2[i], 3)))
+    ref = R.corr3d_lookup(xyz1, xyzs2, rp, [_knn(x, xyz1, 16) for x in xyzs2], *P).transpose(1, 2)
+    want = torch.autograd.grad(ref, [f1, f2] + list(cost.parameters()), gout)
+    assert _rel(out, ref) <= 2e-5
+    for a, b in zip(got, want):
+        assert _rel(a, b) <= 5e-4
+
+    flow = torch.randn(B, 3, n, generator=g).to(dev).requires_grad_(True)
+    q = ((torch.rand(B, 3, 900, generator=g) - 0.5) * 10).to(dev)
+    up = ops.knn_interpolate(xyz1, flow, q, 3)
+    gq = torch.randn(up.shape, generator=g).to(dev)
+    assert _rel(torch.autograd.grad(up, flow, gq)[0],
+                torch.autograd.grad(R.knn_interpolate(xyz1, flow, q, _knn(xyz1, q, 3)), flow, gq)[0]) <= 1e-5
+
+    wn = MLP2d(3, [8, 16], act="leaky_relu").to(dev)
+    feat = torch.randn(B, C, n, generator=g).to(dev).requires_grad_(True)
+    S = 256
+    sx = xyz1[:, :, :S].contiguous()
+    idx = _knn(xyz1, sx, 16)
+    rows = ops.rows_of(torch.cat([xyz1, feat], 1))
+    grp = ops.pointconv_group(rows, sx, idx, 16, wn, 0.1)
+    gg = torch.randn(grp.shape, generator=g).to(dev)
+    got = torch.autograd.grad(grp, [feat] + list(wn.parameters()), gg)
+    fp = [wn.convs[0].conv_fn.weight.flatten(1), wn.convs[0].conv_fn.bias, wn.convs[1].conv_fn.weight.flatten(1),
+          wn.convs[1].conv_fn.bias]
+    want = torch.autograd.grad(R.pointconv_group(xyz1, feat, sx, idx, *fp, 0.1), [feat] + list(wn.parameters()), gg)
+    for a, b in zip(got, want):
+        assert _rel(a, b) <= 5e-4
+
+    wn3 = MLP2d(3, [8, 32, 40], act="relu").to(dev)
+    w = ops.pointconv_dw_weights(xyz1, xyz1, _knn(xyz1, xyz1, 16), 16, wn3)
+    gw = torch.randn(w.shape, generator=g).to(dev)
+    got = torch.autograd.grad(w, list(wn3.parameters()), gw)
+    fp = []
+    for c in wn3.convs:
+        fp += [c.conv_fn.weight.flatten(1), c.conv_fn.bias]
+    want = torch.autograd.grad(R.pointconv_dw_weights(xyz1, xyz1, _knn(xyz1, xyz1, 16), fp), list(wn3.parameters()), gw)
+    for a, b in zip(got, want):
+        assert _rel(a, b) <= 5e-4
+
+    sn = torch.nn.Sequential(Conv2dNormRelu(3, 16), Conv2dNormRelu(16, C, act="sigmoid")).to(dev)
+    H, W = 12, 20
+    uv = torch.stack([torch.rand(B, n, generator=g) * (W - 1), torch.rand(B, n, generator=g) * (H - 1)], 1).to(dev)
+    nn_idx = ops.nearest_point_2d(uv, H, W)
+    f3 = torch.randn(B, n, C, generator=g).to(dev)
+    ci = ops.clfm_interp(uv, nn_idx, f3, sn, H, W)
+    gc = torch.randn(ci.shape, generator=g).to(dev)
+    got = torch.autograd.grad(ci, list(sn.parameters()), gc)
+    fp = [sn[0].conv_fn.weight.flatten(1), sn[0].conv_fn.bias, sn[1].conv_fn.weight.flatten(1), sn[1].conv_fn.bias]
+    want = torch.autograd.grad(R.clfm_interp(uv, nn_idx, f3.transpose(1, 2), *fp, H, W), list(sn.parameters()), gc)
+    for a, b in zip(got, want):
+        assert _rel(a, b) <= 5e-4
+
+
+@contextlib.contextmanager
+def formula_ops():
+    """camliflow_b200.ops with every differentiable operator answered by its plain-PyTorch formula (the index
+    searches stay on the CUDA kernels): the pure-autograd checker of the training step."""
+    import camliflow_b200.ops as ops
+
+    def folded(layers):
+        out = []
+        for c in layers:
+            w, b = c.folded()
+            out += [w, b]
+        return out
+
+    def knn_interpolate(input_xyz, input_feat, query_xyz, k=3):
+        return R.knn_interpolate(input_xyz, input_feat, query_xyz, _knn(input_xyz, query_xyz, k))
+
+    def corr3d_build(feat1, feat2, xyzs2, k=3):
+        pyr = [torch.bmm(feat1.transpose(1, 2), feat2) / feat1.shape[1]]
+        for i in range(1, len(xyzs2)):
+            pyr.append(R.corr3d_pool(pyr[-1], _knn(xyzs2[i - 1], xyzs2[i], k)))
+        return pyr
+
+    patches = {
+        "knn_interpolate": knn_interpolate,
+        "backwarp_3d": lambda a, b, f, k=3: b + knn_interpolate(a + f, -f, b, k),
+        "bilinear_sample_rows": lambda f, uv: ops.rows_of(R.bilinear_sample(f, uv)),
+        "corr2d_build": R.corr2d_build,
+        "corr2d_lookup": lambda pyr, c, r, channels_last=True: R.corr2d_lookup(pyr, c, r),
+        "corr3d_build": corr3d_build,
+        "corr3d_lookup_rows": lambda xyz1, xyzs2, pyr, W1, b1, W2, b2: R.corr3d_lookup(
+            xyz1, xyzs2, pyr, [_knn(x, xyz1, 16) for x in xyzs2], W1, b1, W2, b2).transpose(1, 2).contiguous(),
+        "pointconv_dw_weights": lambda xyz, s, idx, k, wn: R.pointconv_dw_weights(xyz, s, idx[:, :, :k], folded(wn.convs)),
+        "pointconv_dw_gather_max": lambda f, w, idx, k: ops.rows_of(R.pointconv_dw_gather_max(ops.cf_of(f), w, idx[:, :, :k])),
+        "pointconv_group": lambda rows, sx, idx, k, wn, slope: R.pointconv_group(
+            ops.cf_of(rows)[:, :3], ops.cf_of(rows)[:, 3:], sx, idx[:, :, :k], *folded(wn.convs), slope),
+        "clfm_interp": lambda uv, nn, f, sn, H, W: R.clfm_interp(uv, nn, ops.cf_of(f), *folded(sn), H, W),
+    }
+    saved = {k: getattr(ops, k) for k in patches}
+    try:
+        for k, fn in patches.items():
+            setattr(ops, k, fn)
+        yield
+    finally:
+        for k, fn in saved.items():
+            setattr(ops, k, fn)
+
+
+def test_camliraft_training_step_gradients(dev):
+    """One training step (train mode, 3 refinement iterations, sequence losses, backward) through the fused
+    operators against the same step with every operator replaced by its torch formula."""
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.init import seed_module_
+    from oracle import camliraft_oracle as co
+    inputs = {k: v.to(dev) for k, v in co.synthetic_inputs(1, 96, 128, 8192, seed=17).items()}
+    g = torch.Generator().manual_seed(18)
+    inputs["flow_2d"] = (torch.randn(1, 2, 96, 128, generator=g) * 3).to(dev)
+    inputs["flow_3d"] = (torch.randn(1, 3, 8192, generator=g) * 0.1).to(dev)
+    model = seed_module_(CamLiRAFT(camliraft_config(n_iters_train=3)), seed=0).to(dev).train()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        model(inputs)
+        model.loss.backward()
+        return model.loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    loss, grads = step()
+    with formula_ops():
+        ref_loss, ref_grads = step()
+    assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss), (loss, ref_loss)
+    assert set(grads) == set(ref_grads)
+    # every trainable tensor of the model receives a gradient
+    assert len(grads) == sum(1 for _ in model.parameters())
+    worst = max((_rel(grads[n], ref_grads[n]), n) for n in grads if ref_grads[n].abs().max() > 1e-9)
+    print("training step: loss %.6f (formula %.6f), worst relative gradient difference %.2e at %s" % ((loss, ref_loss) + worst))
+    assert worst[0] <= 5e-3, worst
