@@ -32,7 +32,11 @@ WORKLOADS = {
     # name: (H, W, N points, GRU iterations, pairs per GPU)
     "c2": (540, 960, 8192, 12, 1),
     "small": (160, 224, 8192, 3, 1),
+    # BASELINE config 5 (secondary; `--workload c5`): training step, n_iters_train = 10, 2 pairs per GPU
+    "c5": (540, 960, 8192, 10, 2),
+    "c5small": (160, 224, 8192, 3, 1),
 }
+TRAIN_WORKLOADS = ("c5", "c5small")
 METRIC = "CamLiRAFT frame-pairs/sec 960x540+8192pts"
 
 
@@ -217,6 +221,82 @@ def run_ours(args, rank, world, local_rank):
     return line
 
 
+def run_train(args, rank, world, local_rank):
+    """Training step (forward with targets, sequence losses, backward through the fused operators' backward
+    kernels, DDP gradient all-reduce over NCCL, AdamW step), timed like the inference workloads."""
+    import torch.distributed as dist
+    from camliflow_b200 import native, trainer
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.init import seed_module_
+
+    H, W, N, iters, B = WORKLOADS[args.workload]
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    strict = args.conv_precision == "fp32"
+    torch.backends.cudnn.allow_tf32 = not strict
+    torch.backends.cuda.matmul.allow_tf32 = not strict
+    model = seed_module_(CamLiRAFT(camliraft_config(n_iters_train=iters)), seed=0).to(dev).train()
+    ddp = trainer.wrap_ddp(model, dev)
+    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, weight_decay=1e-6)
+    inputs = synthetic_inputs(B, H, W, N, seed=shard_seed(rank))
+    g = torch.Generator().manual_seed(1000 + shard_seed(rank))
+    inputs["flow_2d"] = torch.randn(B, 2, H, W, generator=g) * 5.0           # SURVEY 8(d) targets
+    inputs["flow_3d"] = torch.randn(B, 3, N, generator=g) * 0.1
+    pinned = {k: v.pin_memory() for k, v in inputs.items()}
+    dev_in = {k: v.to(dev) for k, v in inputs.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        return max_over_ranks(s.elapsed_time(e), world, dev)
+
+    losses = []
+
+    def step_resident():
+        losses.append(trainer.train_step(ddp, opt, dev_in))
+
+    def step_e2e():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        losses.append(float(trainer.train_step(ddp, opt, batch)))            # D2H read of the loss
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    c0 = native.launch_count()
+    ms_dev = timed(step_resident, args.steps, args.warmup)
+    launches = (native.launch_count() - c0) // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    pairs = B * world
+    return {
+        "metric": "CamLiRAFT training frame-pairs/sec 960x540+8192pts", "value": pairs * args.steps / (ms_dev / 1e3),
+        "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: CamLiRAFT training step (fwd + sequence losses + bwd + AdamW) %dx%d RGB + %d pts, "
+                               "%d iters, batch %d per GPU" % (args.workload, W, H, N, iters, B),
+                   "pairs_per_step": pairs, "parallelism": "dp%d (DDP gradient all-reduce over NCCL)" % world,
+                   "l2": "working set (activations of %d iterations) larger than L2" % iters,
+                   "conv_precision": "fp32" if strict else "tf32", "final_loss": float(losses[-1])},
+        "e2e": {"value": pairs * args.steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": sum(v.numel() * 4 for v in pinned.values()), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches * args.steps, "clocks": clocks,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,7 +335,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    line = run_ours(args, rank, world, local_rank)
+    line = (run_train if args.workload in TRAIN_WORKLOADS else run_ours)(args, rank, world, local_rank)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

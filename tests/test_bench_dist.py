@@ -52,3 +52,50 @@ def test_reference_arm_json_contract():
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+class _TinyFlow(torch.nn.Module):
+    """Stand-in with the contract trainer.train_step needs: forward(inputs) sets `.loss`."""
+
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Linear(4, 2)
+
+    def forward(self, inputs):
+        self.loss = (self.lin(inputs["x"]) - inputs["flow_2d"]).pow(2).mean()
+        return {}
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from camliflow_b200 import trainer
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = trainer.wrap_ddp(_TinyFlow())
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(100 + rank)                       # every rank owns different "pairs"
+    inputs = {"x": torch.randn(8, 4, generator=g), "flow_2d": torch.randn(8, 2, generator=g)}
+    loss = trainer.train_step(model, opt, inputs)
+    torch.save({"w": trainer.unwrap(model).lin.weight.detach(), "g": trainer.unwrap(model).lin.weight.grad, "loss": loss,
+                "x": inputs["x"], "y": inputs["flow_2d"]}, os.path.join(out_dir, "t%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_step_allreduces_gradients(tmp_path):
+    """trainer.train_step under DistributedDataParallel: both ranks end with identical weights, and the applied
+    gradient is the mean of the per-rank gradients (the all-reduce of BASELINE config 5's data-parallel step)."""
+    world, port = 2, 31500 + os.getpid() % 2000
+    mp.spawn(_train_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(tmp_path / ("t%d.pt" % i)) for i in range(world)]
+    assert torch.equal(r[0]["w"], r[1]["w"]) and torch.equal(r[0]["g"], r[1]["g"])
+    torch.manual_seed(0)
+    ref = _TinyFlow()
+    grads = []
+    for i in range(world):
+        ref.zero_grad()
+        ref({"x": r[i]["x"], "flow_2d": r[i]["y"]})
+        ref.loss.backward()
+        grads.append(ref.lin.weight.grad.clone())
+    assert torch.allclose(r[0]["g"], (grads[0] + grads[1]) / 2, atol=1e-6)

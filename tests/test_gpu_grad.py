@@ -196,9 +196,10 @@ def test_camliraft_training_step_gradients(dev):
     from camliflow_b200.config import camliraft_config
     from camliflow_b200.init import seed_module_
     from oracle import camliraft_oracle as co
-    inputs = {k: v.to(dev) for k, v in co.synthetic_inputs(1, 96, 128, 8192, seed=17).items()}
+    inputs = {k: v.to(dev) for k, v in co.synthetic_inputs(1, 128, 160, 8192, seed=17).items()}
+    # (a smaller image makes the REFERENCE's own coarsest lookup divide by h - 1 = 0)
     g = torch.Generator().manual_seed(18)
-    inputs["flow_2d"] = (torch.randn(1, 2, 96, 128, generator=g) * 3).to(dev)
+    inputs["flow_2d"] = (torch.randn(1, 2, 128, 160, generator=g) * 3).to(dev)
     inputs["flow_3d"] = (torch.randn(1, 3, 8192, generator=g) * 0.1).to(dev)
     model = seed_module_(CamLiRAFT(camliraft_config(n_iters_train=3)), seed=0).to(dev).train()
 
