@@ -93,6 +93,7 @@ class CamLiRAFT_Core(nn.Module):
         flow_2d = torch.zeros_like(grid)
         flow_3d = torch.zeros_like(xyz1)
         dw_cache = {}                  # iteration-invariant WeightNet outputs of the PointConvDW layers
+        gru_cache = {}                 # iteration-invariant context contributions to the ConvGRU pre-activations
         preds_2d, preds_3d = [], []
         for it in range(n_iters):
             if it > 0:
@@ -115,7 +116,10 @@ class CamLiRAFT_Core(nn.Module):
             last = every or it == n_iters - 1
 
             def update_2d():
-                h = b2.gru(h=h_2d, x=torch.cat([x_2d, motion_2d], dim=1))
+                if tc.fused(h_2d):
+                    h = b2.gru.forward_split(h_2d, x_2d, motion_2d, gru_cache)
+                else:
+                    h = b2.gru(h=h_2d, x=torch.cat([x_2d, motion_2d], dim=1))
                 flow = flow_2d + b2.flow_head(h)
                 return h, flow, (b2.convex_upsampler(h, flow) if last and not cfgs.fuse_hidden else None)
 
@@ -154,7 +158,8 @@ class _TwoStreams:
         if enabled:
             dev = torch.cuda.current_device()
             if dev not in _TwoStreams._side:
-                _TwoStreams._side[dev] = torch.cuda.Stream(dev)
+                # the point branch is a chain of short kernels: give its CTAs precedence whenever SMs free up
+                _TwoStreams._side[dev] = torch.cuda.Stream(dev, priority=-1)
             self.side = _TwoStreams._side[dev]
 
     def run(self, fn_main, fn_side):

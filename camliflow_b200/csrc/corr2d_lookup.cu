@@ -66,52 +66,77 @@ corr2d_lookup_kernel(const __grid_constant__ LookupLevels lv, const float* __res
     }
     __syncthreads();
 
-    // ---- phase 1: footprints -> shared memory.  All of a thread's loads are issued before the first
-    // shared-memory store, so 13 independent requests per thread are in flight (latency-bound otherwise).
-    constexpr int LK_PER_THREAD = (LK_TP * LK_FP * LK_FP + LK_THREADS - 1) / LK_THREADS;   // 13
-    float v[LK_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < LK_PER_THREAD; ++i) {
-        const int e = t + i * LK_THREADS;
-        const int px = min(e / (LK_FP * LK_FP), LK_TP - 1), a = e - (e / (LK_FP * LK_FP)) * (LK_FP * LK_FP);
-        const int ry = a / LK_FP, rx = a - ry * LK_FP;
-        const int p = p0 + px;
-        const int yy = s_y0[px] + ry, xx = s_x0[px] + rx;
-        v[i] = 0.f;
-        if (e < LK_TP * LK_FP * LK_FP && p < HW && yy >= 0 && yy < h && xx >= 0 && xx < w)
-            v[i] = __ldg(vol + ((size_t)p * h + yy) * w + xx);
-    }
-#pragma unroll
-    for (int i = 0; i < LK_PER_THREAD; ++i) {
-        const int e = t + i * LK_THREADS;
-        if (e < LK_TP * LK_FP * LK_FP) s_fp[(e / (LK_FP * LK_FP)) * LK_STRIDE + e % (LK_FP * LK_FP)] = v[i];
-    }
-    __syncthreads();
-
+    // ---- phase 1: footprints -> shared memory.  A warp owns 4 pixels; lane l handles footprint elements
+    // l, l+32, l+64, l+96 of each, so the (row, column) of an element is a per-thread constant (no index
+    // arithmetic in the loop) and a warp-wide load covers ~3 contiguous 40-byte row segments.  All 16 loads of
+    // a thread are issued before the first shared-memory store (latency-bound otherwise).
     const int lane = t & 31, warp = t >> 5;
+    constexpr int LK_PXW = LK_TP / (LK_THREADS / 32);       // 4 pixels per warp
+    constexpr int LK_EPT = (LK_FP * LK_FP + 31) / 32;       // 4 elements per lane and pixel
+    int off[LK_EPT], ry[LK_EPT], rx[LK_EPT];
+#pragma unroll
+    for (int i = 0; i < LK_EPT; ++i) {
+        const int e = lane + 32 * i;
+        ry[i] = e / LK_FP;
+        rx[i] = e - ry[i] * LK_FP;
+        off[i] = e < LK_FP * LK_FP ? e : -1;
+    }
+    float v[LK_PXW][LK_EPT];
+#pragma unroll
+    for (int q = 0; q < LK_PXW; ++q) {
+        const int px = warp * LK_PXW + q, p = p0 + px;
+        const int y0 = s_y0[px], x0 = s_x0[px];
+        const float* __restrict__ slice = vol + (size_t)min(p, HW - 1) * h * w;
+#pragma unroll
+        for (int i = 0; i < LK_EPT; ++i) {
+            const int yy = y0 + ry[i], xx = x0 + rx[i];
+            v[q][i] = 0.f;
+            if (off[i] >= 0 && p < HW && (unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w)
+                v[q][i] = __ldg(slice + yy * w + xx);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < LK_PXW; ++q)
+#pragma unroll
+        for (int i = 0; i < LK_EPT; ++i)
+            if (off[i] >= 0) s_fp[(warp * LK_PXW + q) * LK_STRIDE + off[i]] = v[q][i];
+
     const int n_ch = n_levels * LK_WIN * LK_WIN;
     if (NHWC) {
-        // ---- phase 2 (NHWC out): warp = pixel (4 per warp), lane = window position; a pixel's 81
+        // ---- phase 2 (NHWC out): the same warp turns its 4 footprints into 4 x 81 outputs; lane = window
+        // position (c, c+32, c+64), whose (i -> x, j -> y) split is again a per-thread constant; a pixel's 81
         // channels of this level are contiguous in the output row
-        for (int px = warp; px < LK_TP; px += LK_THREADS / 32) {
-            const int p = p0 + px;
+        __syncwarp();
+        constexpr int LK_CPT = (LK_WIN * LK_WIN + 31) / 32;  // 3
+        int qoff[LK_CPT];
+#pragma unroll
+        for (int j = 0; j < LK_CPT; ++j) {
+            const int c = lane + 32 * j;
+            const int ci = c / LK_WIN, cj = c - ci * LK_WIN;        // ci -> x offset, cj -> y offset
+            qoff[j] = c < LK_WIN * LK_WIN ? cj * LK_FP + ci : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < LK_PXW; ++q) {
+            const int px = warp * LK_PXW + q, p = p0 + px;
             if (p >= HW) break;
             const float fx = s_fx[px], fy = s_fy[px];
             const float w00 = (1.f - fx) * (1.f - fy), w10 = fx * (1.f - fy), w01 = (1.f - fx) * fy, w11 = fx * fy;
             const float* fp = s_fp + px * LK_STRIDE;
             float* __restrict__ o = out + ((size_t)b * HW + p) * n_ch + level * LK_WIN * LK_WIN;
-            for (int c = lane; c < LK_WIN * LK_WIN; c += 32) {
-                const int i = c / LK_WIN, j = c - i * LK_WIN;
-                const float* q = fp + j * LK_FP + i;
-                float v = q[0] * w00;
-                v = fmaf(q[1], w10, v);
-                v = fmaf(q[LK_FP], w01, v);
-                v = fmaf(q[LK_FP + 1], w11, v);
-                o[c] = v;
+#pragma unroll
+            for (int j = 0; j < LK_CPT; ++j) {
+                if (qoff[j] < 0) continue;
+                const float* qp = fp + qoff[j];
+                float r = qp[0] * w00;
+                r = fmaf(qp[1], w10, r);
+                r = fmaf(qp[LK_FP], w01, r);
+                r = fmaf(qp[LK_FP + 1], w11, r);
+                o[lane + 32 * j] = r;
             }
         }
         return;
     }
+    __syncthreads();
     // ---- phase 2 (NCHW out): lane = pixel, warp strides over the 81 window positions
     const int p = p0 + lane;
     if (p >= HW) return;

@@ -85,8 +85,11 @@ dw_weights_kernel(int N, int S, int K, int k, int O,
 }
 
 // ---------------------------------------------------------------- (2) gather * weight, max over k
-// One warp per (centroid, 32-channel chunk): 2k independent coalesced 128-byte loads in flight.
-template <int WARPS>
+// One warp per (centroid, 32-channel chunk).  The kernel is a pure stream (no reuse), so its speed is the
+// number of bytes in flight: ALL 2k 128-byte loads of a warp (k feature rows, k weight rows) are issued
+// before the first one is consumed (KT = k known at compile time, registers hold the k x 2 values); an
+// in-order warp that consumed them batch by batch would expose one full memory latency per batch.
+template <int WARPS, int KT>
 __global__ void __launch_bounds__(WARPS * 32)
 dw_gather_max_kernel(int N, int S, int K, int k, int O, int chunks,
                      const float* __restrict__ feat, long long ldf,      // rows [B,N,ldf]
@@ -103,8 +106,21 @@ dw_gather_max_kernel(int N, int S, int K, int k, int O, int chunks,
     const float* fb = feat + (size_t)b * N * ldf;
     const float* wp = wc + ((size_t)b * S + s) * k * O;
     float best = -INFINITY;
-    // k is a multiple of 4 in every layer of the model; batches of 4 neighbours keep 8 independent
-    // 128-byte requests in flight per warp
+    if (KT > 0) {
+        float f[KT > 0 ? KT : 1], w[KT > 0 ? KT : 1];
+        const bool live = o < O;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            const int ij = __shfl_sync(CAMLI_FULL_MASK, my, j);
+            f[j] = live ? __ldg(fb + (size_t)ij * ldf + o) : 0.f;
+            w[j] = live ? __ldcs(wp + (size_t)j * O + o) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < KT; ++j) best = fmaxf(best, f[j] * w[j]);
+        if (live) out[((size_t)b * S + s) * ldo + o] = best;
+        return;
+    }
+    // generic k: batches of 4 neighbours
     int j = 0;
     for (; j + 4 <= k; j += 4) {
         int ij[4];
@@ -160,7 +176,17 @@ extern "C" int camli_pointconv_dw_gather_max(int B, int N, int S, int K, int k, 
     constexpr int WARPS = 8;
     const int chunks = camli_div_up(O, 32);
     dim3 grid((unsigned)camli_div_up_ll((long long)S * chunks, WARPS), B);
-    dw_gather_max_kernel<WARPS><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
-        N, S, K, k, O, chunks, feat_rows, ld_feat, weights, knn_idx, out_rows, ld_out);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CAMLI_DW_LAUNCH(KT)                                                                                    \
+    dw_gather_max_kernel<WARPS, KT><<<grid, WARPS * 32, 0, st>>>(N, S, K, k, O, chunks, feat_rows, ld_feat, weights, \
+                                                                 knn_idx, out_rows, ld_out)
+    switch (k) {          // the neighbourhood sizes of the models get fully unrolled instances
+        case 4: CAMLI_DW_LAUNCH(4); break;
+        case 8: CAMLI_DW_LAUNCH(8); break;
+        case 16: CAMLI_DW_LAUNCH(16); break;
+        case 32: CAMLI_DW_LAUNCH(32); break;
+        default: CAMLI_DW_LAUNCH(0); break;
+    }
+#undef CAMLI_DW_LAUNCH
     CAMLI_RETURN_LAUNCH_STATUS();
 }

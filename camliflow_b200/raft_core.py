@@ -173,6 +173,39 @@ class GRU2D(nn.Module):
         z, rhx = ops.gru_gate(zr, h, x)
         return ops.gru_update(z, h, tc.conv2d(rhx, convq), fix_nonfinite=last)
 
+    def _split_weights(self, convz, convr, convq, n_h, n_static):
+        """The z|r and q convolutions split by input-channel group [h | x_static | x_dynamic]: the x_static part
+        (the context features, identical in every refinement iteration) is convolved once per forward."""
+        key = tuple((p.data_ptr(), p._version) for p in (convz.weight, convz.bias, convr.weight, convr.bias,
+                                                        convq.weight, convq.bias)) + (n_h, n_static)
+        cache = self.__dict__.setdefault("_split_cache", {})
+        hit = cache.get(id(convz))
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                wzr, bzr = self._merged_zr(convz, convr)
+                lo, hi = n_h, n_h + n_static
+                dyn = lambda w: torch.cat([w[:, :lo], w[:, hi:]], 1).contiguous()      # noqa: E731
+                hit = (key, dyn(wzr), bzr, wzr[:, lo:hi].contiguous(), dyn(convq.weight), convq.bias,
+                       convq.weight[:, lo:hi].contiguous())
+            cache[id(convz)] = hit
+        return hit[1:]
+
+    def forward_split(self, h, x_static, x_dynamic, cache):
+        """forward(h, cat([x_static, x_dynamic])) with the x_static contributions to the z, r and q
+        pre-activations taken from `cache` (a dict owned by the caller for one forward pass) and added in the
+        convolution epilogues: the per-iteration convolutions shrink from 384 to 256 input channels."""
+        n_h, n_static = h.shape[1], x_static.shape[1]
+        for half, (cz, cr, cq) in enumerate(((self.convz1, self.convr1, self.convq1), (self.convz2, self.convr2, self.convq2))):
+            w_zr, b_zr, w_zr_s, w_q, b_q, w_q_s = self._split_weights(cz, cr, cq, n_h, n_static)
+            ctx = cache.get(("gru2d", half))
+            if ctx is None:
+                ctx = (tc.conv2d_weights(x_static, w_zr_s, None, cz.padding), tc.conv2d_weights(x_static, w_q_s, None, cq.padding))
+                cache[("gru2d", half)] = ctx
+            zr = tc.conv2d_weights(torch.cat([h, x_dynamic], dim=1), w_zr, b_zr, cz.padding, residual=ctx[0])
+            z, rhx = ops.gru_gate(zr, h, x_dynamic)
+            h = ops.gru_update(z, h, tc.conv2d_weights(rhx, w_q, b_q, cq.padding, residual=ctx[1]), fix_nonfinite=half == 1)
+        return h
+
     def forward(self, h, x):
         if h.is_cuda and not (torch.is_grad_enabled() and (h.requires_grad or x.requires_grad or self.convz1.weight.requires_grad)):
             h = self._half_fused(h, x, self.convz1, self.convr1, self.convq1, False)

@@ -106,7 +106,7 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
     return y
 
 
-def conv2d_weights(x, weight, bias, padding, act=None, slope=0.1, out=None):
+def conv2d_weights(x, weight, bias, padding, act=None, slope=0.1, out=None, residual=None):
     """Same for an explicit stride-1 (weight [O,I,kh,kw], bias) pair -- e.g. two convolutions merged into one;
     `weight` / `bias` must be long-lived tensors (they key the split cache)."""
     O, I, kh, kw = weight.shape
@@ -116,8 +116,16 @@ def conv2d_weights(x, weight, bias, padding, act=None, slope=0.1, out=None):
             rows = rows.contiguous()
         if ops.conv_gemm_ok(rows, kh, kw):
             w_hi, w_lo, b = ops.tc_weight([weight, bias], lambda: (weight.permute(0, 2, 3, 1).reshape(O, -1), bias))
-            return ops.conv_gemm(rows, w_hi, w_lo, kh, kw, b, act, slope, None, out).permute(0, 3, 1, 2)
-    y = _TORCH_ACTS[act](F.conv2d(x, weight, bias, padding=padding), slope)
+            res = None
+            if residual is not None:
+                res = residual.permute(0, 2, 3, 1)
+                if not ops._pixel_layout(res)[1]:
+                    res = res.contiguous()
+            return ops.conv_gemm(rows, w_hi, w_lo, kh, kw, b, act, slope, res, out).permute(0, 3, 1, 2)
+    y = F.conv2d(x, weight, bias, padding=padding)
+    if residual is not None:
+        y = y + residual
+    y = _TORCH_ACTS[act](y, slope)
     if out is not None:
         out.copy_(y.permute(0, 2, 3, 1))
         return out.permute(0, 3, 1, 2)

@@ -355,3 +355,23 @@ def test_gru3d_fused_matches_layerwise(dev):
         finally:
             tc.ENABLED = True
     _close(fused, plain, 2e-5, rtol=1e-4, what="GRU3D fused")
+
+
+def test_gru2d_split_matches_plain(dev):
+    """ConvGRU with the context contribution precomputed (forward_split) against the plain module."""
+    from camliflow_b200.raft_core import GRU2D
+    g = torch.Generator().manual_seed(36)
+    gru = GRU2D(hidden_dim=128, input_dim=256)
+    for p in gru.parameters():
+        p.data.copy_(torch.randn(p.shape, generator=g) * 0.03)
+    gru = gru.to(dev).eval().to(memory_format=torch.channels_last)
+    mk = lambda c: torch.randn(1, c, 20, 28, generator=g).to(dev).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    h, xs, xd = torch.tanh(mk(128)), torch.relu(mk(128)), mk(128)
+    with torch.no_grad():
+        cache = {}
+        a = gru.forward_split(h, xs, xd, cache)
+        a2 = gru.forward_split(h, xs, xd, cache)           # second call reuses the cached context terms
+    with torch.enable_grad():
+        b = gru(h, torch.cat([xs, xd], 1)).detach()        # module-by-module torch path
+    assert torch.equal(a, a2)
+    _close(a, b, 2e-5, rtol=1e-4, what="GRU2D split")
