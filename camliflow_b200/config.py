@@ -21,6 +21,14 @@ def camliraft_config(n_iters_eval=20, n_iters_train=10, **overrides):
     return AttrDict(cfg)
 
 
+def camliraft_l_config(n_iters_eval=20, n_iters_train=10, **overrides):
+    """conf/model/camliraft_l.yaml."""
+    cfg = dict(name="camliraft_l", batch_size=8, n_iters_train=n_iters_train, n_iters_eval=n_iters_eval,
+               ids=dict(enabled=True), loss=dict(gamma=0.8, order="l2-norm"))
+    cfg.update(overrides)
+    return AttrDict(cfg)
+
+
 def camlipwc_config(**overrides):
     """conf/model/camlipwc.yaml."""
     cfg = dict(name="camlipwc", batch_size=32, freeze_bn=False,

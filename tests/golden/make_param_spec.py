@@ -1,4 +1,4 @@
-"""Writes oracle/param_spec_{camliraft,camlipwc}.json: parameter/buffer names -> shapes of the
+"""Writes oracle/param_spec_{camliraft,camlipwc,camliraft_l}.json: parameter/buffer names -> shapes of the
 REFERENCE models (built from /root/reference through tests/golden/ref_harness.py; build
 container only).  The oracle and the product both key their seeded weights on these names,
 so a test that the product's state_dict matches the spec is a test of checkpoint
@@ -21,6 +21,7 @@ def main():
     nets = {
         "camliraft": models.camliraft.CamLiRAFT(rh.camliraft_cfg()),
         "camlipwc": models.camlipwc.CamLiPWC(rh.camlipwc_cfg()),
+        "camliraft_l": models.camliraft_l.CamLiRAFT_L(rh.camliraft_l_cfg()),
     }
     for name, net in nets.items():
         spec = {k: list(v.shape) for k, v in net.state_dict().items()}

@@ -77,6 +77,11 @@ def camliraft_cfg(n_iters=12):
                           loss2d=dict(gamma=0.8, order="l2-norm"), loss3d=dict(gamma=0.8, order="l2-norm")))
 
 
+def camliraft_l_cfg(n_iters=4):
+    return _AttrDict(dict(name="camliraft_l", batch_size=8, n_iters_train=10, n_iters_eval=n_iters,
+                          ids=dict(enabled=True), loss=dict(gamma=0.8, order="l2-norm")))
+
+
 def camlipwc_cfg():
     return _AttrDict(dict(name="camlipwc", batch_size=32, freeze_bn=False,
                           pwc2d=dict(norm=dict(feature_pyramid="batch_norm", flow_estimator=None, context_network=None),

@@ -131,3 +131,35 @@ def test_camlipwc_batch4():
     one = {k: v[2:3] for k, v in inputs.items()}
     g2, g3 = _run(model, one)
     assert epe(f2[2].numpy(), g2[0].numpy()) <= 1e-4 and epe(f3[2].numpy(), g3[0].numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("case,B,N,iters,seed", [("c1", 1, 8192, 4, 21), ("c1_batch2", 2, 4500, 2, 22)])
+def test_camliraft_l_vs_reference_golden(case, B, N, iters, seed):
+    """CamLiRAFT-L (BASELINE config 1 geometry, and a batch of two) on the GPU kernels against the reference
+    model's golden output."""
+    from camliflow_b200.camliraft_l import CamLiRAFT_L
+    from camliflow_b200.config import camliraft_l_config
+    from camliflow_b200.init import seed_module_
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    G = np.load(os.path.join(GOLDEN, "model_camliraft_l.npz"))
+    inputs = co.synthetic_inputs(B, 540, 960, N, seed)
+    net = seed_module_(CamLiRAFT_L(camliraft_l_config(n_iters_eval=iters)), seed=0).cuda().eval()
+    with torch.no_grad():
+        out = net({"pcs": inputs["pcs"].cuda(), "intrinsics": inputs["intrinsics"].cuda()})["flow_3d"].cpu()
+    for b in range(B):
+        e3 = epe(out[b, :, ::4].numpy(), G[case + "_kernel_flow3d"][b])
+        print("camliraft_l %s[%d] vs reference golden: EPE3D %.3e" % (case, b, e3))
+        assert e3 <= TOL_EPE3D, e3
+
+
+def test_camliraft_batch2_equals_single_samples():
+    """BASELINE config 4 runs several pairs per GPU: every sample of a batch equals its single-sample result."""
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    model = _model(2)
+    inputs = co.synthetic_inputs(2, 160, 224, 8192, seed=44)
+    f2, f3 = _run(model, inputs)
+    for b in range(2):
+        g2, g3 = _run(model, {k: v[b:b + 1] for k, v in inputs.items()})
+        assert epe(f2[b].numpy(), g2[0].numpy()) <= 1e-4 and epe(f3[b].numpy(), g3[0].numpy()) <= 1e-5

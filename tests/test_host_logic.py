@@ -92,3 +92,25 @@ def test_camlipwc_state_dict_and_graph_match_reference_golden():
     e2 = epe(out["flow_2d"][0, :, ::4, ::4].numpy(), G["small_kernel_flow2d"])
     e3 = epe(out["flow_3d"][0, :, ::4].numpy(), G["small_kernel_flow3d"])
     assert e2 <= 1e-3 and e3 <= 1e-4, (e2, e3)
+
+
+def test_camliraft_l_c1_on_cpu_matches_reference_golden():
+    """BASELINE config 1 (the reference's own CPU-runnable case): CamLiRAFT-L, 8192-point pair -> 2048 working
+    points, 4 GRU iterations, batch 1, on CPU (kernels answered by formulas): reference state_dict
+    names/shapes and the reference model's golden output; plus a ragged batch of two 4500-point pairs."""
+    from camliflow_b200.camliraft_l import CamLiRAFT_L
+    from camliflow_b200.config import camliraft_l_config
+    from camliflow_b200.init import seed_module_
+    spec = co.param_spec("camliraft_l")
+    G = np.load(os.path.join(GOLDEN, "model_camliraft_l.npz"))
+    for case, B, N, iters, seed in (("c1", 1, 8192, 4, 21), ("c1_batch2", 2, 4500, 2, 22)):
+        net = seed_module_(CamLiRAFT_L(camliraft_l_config(n_iters_eval=iters)), seed=0).eval()
+        sd = net.state_dict()
+        assert set(sd) == set(spec) and all(tuple(sd[k].shape) == spec[k] for k in spec)
+        inputs = co.synthetic_inputs(B, 540, 960, N, seed)
+        with cpu_kernels(), torch.no_grad():
+            out = net({"pcs": inputs["pcs"], "intrinsics": inputs["intrinsics"]})
+        want = G[case + "_kernel_flow3d"]
+        for b in range(B):
+            e3 = epe(out["flow_3d"][b, :, ::4].numpy(), want[b])
+            assert e3 <= 1e-4, (case, b, e3)
