@@ -32,6 +32,8 @@ WORKLOADS = {
     # name: (H, W, N points, GRU iterations, pairs per GPU)
     "c2": (540, 960, 8192, 12, 1),
     "small": (160, 224, 8192, 3, 1),
+    # BASELINE config 4 (`--workload c4`): 32 iterations, 32 pairs over 8 GPUs = 4 pairs per GPU
+    "c4": (540, 960, 8192, 32, 4),
     # BASELINE config 5 (secondary; `--workload c5`): training step, n_iters_train = 10, 2 pairs per GPU
     "c5": (540, 960, 8192, 10, 2),
     "c5small": (160, 224, 8192, 3, 1),
