@@ -103,12 +103,17 @@ class CamLiRAFT_Core(nn.Module):
                 warped = warp_pyramid(xyz1, xyzs2, flow_3d) if it > 0 else xyzs2
                 return b3.correlation.forward_rows(xyz1, warped)
 
-            corr_2d, corr_3d = par.run(lambda: b2.correlation(grid + flow_2d), corr_3d_fn)
+            def corr_2d_fn():
+                # + the flow half of the motion encoder, which only needs flow_2d: fills the image stream while
+                # the point stream is still in its (longer) correlation lookup
+                return b2.correlation(grid + flow_2d), (b2.motion_encoder.flow_features(flow_2d) if tc.fused(flow_2d) else None)
+
+            (corr_2d, cf_2d), corr_3d = par.run(corr_2d_fn, corr_3d_fn)
             if cfgs.fuse_corr:
                 corr_2d, corr_3d = self.clfm_corr.forward_rows(uv1, corr_2d, corr_3d, nn1, par)
 
             motion_2d, motion_3d = par.run(
-                lambda: b2.motion_encoder(flow_2d, corr_2d),
+                lambda: b2.motion_encoder(flow_2d, corr_2d, cf_2d),
                 lambda: b3.motion_encoder.forward_rows(xyz1, ops.rows_of(flow_3d), corr_3d, nbr, dw_cache))
             if cfgs.fuse_motion:
                 motion_2d, motion_3d = self.clfm_motion.forward_rows(uv1, motion_2d, motion_3d, nn1, par)

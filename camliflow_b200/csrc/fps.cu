@@ -267,6 +267,10 @@ static_assert(FPSA_RECORDS == 64, "winner pick reads two records per lane");
 
 __device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Diagnostics: SM-clock stamps of rounds 100..103 as seen by thread 0 of CTA 0 (5 per round), when a buffer is attached.
+__device__ long long* g_fps_timeline = nullptr;
+#define FPS_STAMP(i) do { if (tl && s >= 100 && s < 104) tl[(s - 100) * 5 + (i)] = clock64(); } while (0)
+
 template <int PPT>
 __global__ void __cluster_dims__(FPSA_CTAS, 1, 1) __launch_bounds__(FPSA_THREADS, 1)
 fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_t* __restrict__ out_all) {
@@ -321,6 +325,7 @@ fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_
         }
     }
     const uint32_t l_bar[2] = {fps_smem_u32(&s_bar[0]), fps_smem_u32(&s_bar[1])};
+    long long* tl = (blockIdx.x == 0 && t == 0) ? g_fps_timeline : nullptr;
     cluster.sync();                                               // every CTA's barriers exist before any remote store
 
     int cur = 0;
@@ -328,6 +333,7 @@ fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_
         if (rank == 0 && t == 0) out[s] = (int64_t)cur;
         if (s == S - 1) break;
         const int par = s & 1;
+        FPS_STAMP(0);
         if (t == 0)                                               // arm this round's barrier (remote stores may already have landed)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                          ::"r"(l_bar[par]), "r"((uint32_t)(FPSA_RECORDS * sizeof(uint2))) : "memory");
@@ -342,6 +348,7 @@ fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_
             pd[j] = nd;
             if (nd > best_d || (nd == best_d && plo[j] > best_lo)) { best_d = nd; best_lo = plo[j]; }
         }
+        FPS_STAMP(1);
         // ---- warp key, pushed to all 8 CTAs
         const int hi = __float_as_int(best_d);
         const int hmax = __reduce_max_sync(CAMLI_FULL_MASK, hi);
@@ -349,6 +356,7 @@ fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_
         if (lane < FPSA_CTAS)
             asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
                          ::"r"(r_rec[par]), "r"(hmax), "r"(lmax), "r"(r_bar[par]) : "memory");
+        FPS_STAMP(2);
         // ---- wait for the 64 records of this round (bounded: a protocol bug traps instead of hanging)
         const uint32_t phase = (uint32_t)(s >> 1) & 1u;
         for (uint32_t spin = 0;; ++spin) {
@@ -359,6 +367,7 @@ fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_
             if (done) break;
             if (spin > (1u << 24)) __trap();
         }
+        FPS_STAMP(3);
         // ---- global winner: max over the 64 (hi, lo) keys
         const uint2 r0 = s_rec[par][lane], r1 = s_rec[par][lane + 32];
         const bool second = (int)r1.x > (int)r0.x || (r1.x == r0.x && r1.y > r0.y);
@@ -367,6 +376,7 @@ fps_cluster_async_kernel(const float* __restrict__ xyz_all, int N, int S, int64_
         const int gh = __reduce_max_sync(CAMLI_FULL_MASK, mh);
         const unsigned gl = __reduce_max_sync(CAMLI_FULL_MASK, mh == gh ? ml : 0u);
         cur = (int)(0x3FFFFFu - (gl & 0x3FFFFFu));
+        FPS_STAMP(4);
     }
     cluster.sync();                                               // no CTA exits while peers may still store to it
 }
@@ -405,6 +415,10 @@ extern "C" int camli_fps_set_cluster_path(int mode) {
     const int old = camli_fps_use_cluster;
     camli_fps_use_cluster = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
     return old;
+}
+
+extern "C" int camli_fps_set_timeline(long long* device_buffer) {
+    return (int)cudaMemcpyToSymbol(g_fps_timeline, &device_buffer, sizeof(device_buffer));
 }
 
 extern "C" int camli_furthest_point_sampling(const float* xyz, float* dists_tmp, int B, int N, int S,

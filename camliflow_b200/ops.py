@@ -286,6 +286,25 @@ def conv_small_n(x_bhwc, w2d, kh, kw, bias=None, act=None, slope=0.1, out=None):
     return out
 
 
+def conv_small_cin(x_bhwc, w2d, kh, kw, bias=None, act=None, slope=0.1, out=None):
+    """Stride-1 "same" convolution with Cin <= 4 (windows up to 7x7) on the CUDA cores (camli_conv_small_cin):
+    x_bhwc [B,H,W,Cin] channel-last view (any pixel stride), w2d [Cout, kh*kw*Cin] (OHWI, fp32)."""
+    _need_cuda(x_bhwc, w2d)
+    _no_grad("conv_small_cin", x_bhwc, w2d)
+    B, H, W, Cin = x_bhwc.shape
+    Cout = w2d.shape[0]
+    assert w2d.shape[1] == kh * kw * Cin and w2d.is_contiguous()
+    ldx = _pixel_layout(x_bhwc)[0]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x_bhwc.device)
+    ldo = _pixel_layout(out)[0]
+    with torch.cuda.device(x_bhwc.device):
+        native.call("camli_conv_small_cin", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w2d), i32(Cout),
+                    i32(kh), i32(kw), ptr(bias), i32(ACT_CODES[act]), ctypes.c_float(slope), ptr(out), i64(ldo), stream(),
+                    algo_bytes=B * H * W * (Cin + Cout) * 4, flops=2 * B * H * W * Cout * kh * kw * Cin)
+    return out
+
+
 def linear_rows(x, w_hi, w_lo, bias=None, act=None, slope=0.1, residual=None):
     """x [..., K] contiguous rows -> [..., N] through conv_gemm (1x1)."""
     K = x.shape[-1]

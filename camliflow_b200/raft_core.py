@@ -227,14 +227,22 @@ class MotionEncoder2D(nn.Module):
         self.conv_f2 = nn.Conv2d(128, 64, kernel_size=3, padding=1)
         self.conv = nn.Conv2d(64 + 192, 128 - 2, kernel_size=3, padding=1)
 
-    def forward(self, flow, corr):
+    def flow_features(self, flow):
+        """The flow half of the encoder (conv_f1, conv_f2), written into its slice of the [corr | flow] feature
+        buffer.  It depends on the flow alone, so the fused core issues it while the point branch is still busy
+        with its correlation lookup; pass the result to forward(..., cf=)."""
+        B, _, H, W = flow.shape
+        cf = torch.empty((B, H, W, 192 + 64), dtype=torch.float32, device=flow.device)
+        tc.conv2d(tc.conv2d(flow, self.conv_f1, "relu"), self.conv_f2, "relu", out=cf[..., 192:])
+        return cf
+
+    def forward(self, flow, corr, cf=None):
         if tc.fused(corr):
             # every convolution with its ReLU in one kernel; the two branches write straight into the halves
             # of one channel-last buffer (no torch.cat)
-            B, _, H, W = corr.shape
-            cf = torch.empty((B, H, W, 192 + 64), dtype=torch.float32, device=corr.device)
+            if cf is None:
+                cf = self.flow_features(flow)
             tc.conv2d(tc.conv2d(corr, self.conv_c1, "relu"), self.conv_c2, "relu", out=cf[..., :192])
-            tc.conv2d(tc.conv2d(flow, self.conv_f1, "relu"), self.conv_f2, "relu", out=cf[..., 192:])
             out = torch.nan_to_num(tc.conv2d(cf.permute(0, 3, 1, 2), self.conv, "relu"))
             return torch.cat([out, flow], dim=1)
         c = F.relu(self.conv_c2(F.relu(self.conv_c1(corr))))

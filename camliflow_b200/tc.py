@@ -70,6 +70,20 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
     storage in, channel-last storage out (`out`: optional [B,H,W,Cout] channel-last destination view, e.g. a
     channel slice of a concatenation buffer).  Returns the logical [B,Cout,H,W] result."""
     kh, kw = conv.kernel_size
+    if (fused(x) and _bn_foldable(bn) and residual is None and conv.in_channels <= 4 and max(kh, kw) <= 7
+            and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and conv.padding == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1):
+        rows = x.permute(0, 2, 3, 1)                   # few input channels, many outputs: CUDA-core kernel
+        if not ops._pixel_layout(rows)[1] and rows.stride(-1) != 1:
+            rows = rows.contiguous()
+        O = conv.out_channels
+
+        def build_small():
+            w, b = _fold(conv.weight, conv.bias, bn)
+            return w.permute(0, 2, 3, 1).reshape(O, -1), b
+
+        w2d, bias = _plain_weight(_key_params(conv.weight, conv.bias, bn), build_small)
+        return ops.conv_small_cin(rows, w2d, kh, kw, bias, act, slope, out).permute(0, 3, 1, 2)
     if (fused(x) and _bn_foldable(bn) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
             and conv.padding == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1 and conv.in_channels % 4 == 0):
         rows = x.permute(0, 2, 3, 1)

@@ -55,6 +55,10 @@ int camli_furthest_point_sampling(const float* xyz, float* dists_tmp,
  * 0 = single-CTA register kernel.  Returns the previous setting.  Results are identical. */
 int camli_fps_set_cluster_path(int mode);
 
+/* Diagnostics: a device buffer of >= 20 int64 that thread 0 of CTA 0 of the async-cluster FPS kernel stamps with
+ * SM-clock values of rounds 100..103 (5 events per round); NULL detaches (default). */
+int camli_fps_set_timeline(long long* device_buffer);
+
 /*
  * Brute-force exact k nearest neighbours, ascending distance.
  * Replaces k_nearest_neighbor_{2d,3d}_kernel_wrapper(int b,int n,int m,int k,
@@ -324,6 +328,15 @@ int camli_corr2d_lookup_backward(float* const* grad_volumes, const int* level_h,
 int camli_pointconv_dw_gather_max_backward(int B, int N, int S, int K, int k, int O, const float* feat_rows,
                                            const float* weights, const int64_t* knn_idx, const float* grad_out_rows,
                                            float* grad_feat_rows, float* grad_weights, void* stream);
+
+/*
+ * The same operation for a handful of INPUT channels (Cin <= 4, windows up to 7x7: the first layer of the motion
+ * encoder's flow path, models/raft_core.py:154) on the CUDA cores, plain fp32 FMA.  x may have any pixel stride
+ * ldx >= Cin (no alignment requirement); w [Cout, kh*kw*Cin] f32 in OHWI order.
+ */
+int camli_conv_small_cin(const float* x, int B, int H, int W, int Cin, int64_t ldx, const float* w, int Cout,
+                         int kh, int kw, const float* bias, int act, float slope, float* out, int64_t ldo,
+                         void* stream);
 
 /* Diagnostics for camli_conv_gemm: a device buffer of >= 128 int64 that CTA 0 of every following launch stamps
  * with SM-clock values of its pipeline events (scripts/conv_gemm_timeline.py); NULL detaches (default). */

@@ -375,3 +375,16 @@ def test_gru2d_split_matches_plain(dev):
         b = gru(h, torch.cat([xs, xd], 1)).detach()        # module-by-module torch path
     assert torch.equal(a, a2)
     _close(a, b, 2e-5, rtol=1e-4, what="GRU2D split")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw,act", [(1, 68, 120, 2, 128, 7, 7, "relu"), (2, 13, 37, 3, 40, 3, 5, None),
+                                                      (1, 9, 33, 4, 32, 1, 1, "sigmoid")])
+def test_conv_small_cin(dev, B, H, W, Cin, Cout, kh, kw, act):
+    g = torch.Generator().manual_seed(37)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    out = _ops().conv_small_cin(x, w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), kh, kw, b, act)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=(kh // 2, kw // 2))
+    ref = {None: lambda v: v, "relu": torch.relu, "sigmoid": torch.sigmoid}[act](ref).permute(0, 2, 3, 1)
+    assert (out.double() - ref).abs().max().item() <= 5e-6
