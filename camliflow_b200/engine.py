@@ -93,6 +93,78 @@ class FlowEngine:
         self.step()
         return self.fetch()
 
+    # ------------------------------------------------------------------ pipelined execution
+    def pipelined(self, batches):
+        """Throughput mode of the end-to-end call: yields the host outputs of every batch of `batches` (an iterable
+        of input dicts of host tensors), with the H2D copy of batch i+1 and the D2H copy of batch i-1 running on a
+        copy stream while batch i computes.  Every batch still pays its own pinned H2D / D2H transfers; they are
+        overlapped, not skipped.  Double-buffered staging on both sides; the compute stream only ever waits on
+        events.  The yielded dict is reused two batches later: consume (or clone) it before advancing twice."""
+        dev = self.device
+        if not hasattr(self, "_pipe"):
+            with torch.cuda.device(dev):
+                self._pipe = {
+                    "copy": torch.cuda.Stream(dev),
+                    "in_host": [{k: torch.empty_like(v).pin_memory() for k, v in self.host_in.items()} for _ in range(2)],
+                    "in_dev": [{k: torch.empty_like(v) for k, v in self.dev_in.items()} for _ in range(2)],
+                    "out_dev": [{k: torch.empty_like(v) for k, v in self.dev_out.items()} for _ in range(2)],
+                    "out_host": [{k: torch.empty_like(v).pin_memory() for k, v in self.host_out.items()} for _ in range(2)],
+                }
+        P, copy = self._pipe, self._pipe["copy"]
+        loaded = [torch.cuda.Event(), torch.cuda.Event()]       # H2D of slot done
+        computed = [torch.cuda.Event(), torch.cuda.Event()]     # outputs of slot ready in out_dev
+        fetched = [torch.cuda.Event(), torch.cuda.Event()]      # D2H of slot done
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]     # compute stream finished reading in_dev[slot]
+
+        def upload(slot, inputs):
+            for k, dst in P["in_host"][slot].items():
+                dst.copy_(inputs[k])
+            with torch.cuda.stream(copy):
+                copy.wait_event(consumed[slot])
+                for k, dst in P["in_dev"][slot].items():
+                    dst.copy_(P["in_host"][slot][k], non_blocking=True)
+                loaded[slot].record(copy)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        for ev in consumed + fetched:
+            ev.record(self.stream)
+        upload(0, nxt)
+        i = 0
+        pending = None                                          # slot whose D2H is in flight
+        while nxt is not None:
+            slot = i & 1
+            nxt = next(it, None)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(loaded[slot])
+                for k, dst in self.dev_in.items():
+                    dst.copy_(P["in_dev"][slot][k], non_blocking=True)   # device-to-device: microseconds
+                consumed[slot].record(self.stream)
+                if self.graph is not None:
+                    self.graph.replay()
+                else:
+                    self._forward_static()
+                self.stream.wait_event(fetched[slot])           # out_dev[slot] no longer being read by the copy stream
+                for k, dst in P["out_dev"][slot].items():
+                    dst.copy_(self.dev_out[k], non_blocking=True)
+                computed[slot].record(self.stream)
+            if nxt is not None:
+                upload(slot ^ 1, nxt)                           # overlaps with the compute just enqueued
+            with torch.cuda.stream(copy):
+                copy.wait_event(computed[slot])
+                for k, dst in P["out_host"][slot].items():
+                    dst.copy_(P["out_dev"][slot][k], non_blocking=True)
+                fetched[slot].record(copy)
+            if pending is not None:
+                fetched[pending].synchronize()
+                yield P["out_host"][pending]
+            pending = slot
+            i += 1
+        fetched[pending].synchronize()
+        yield P["out_host"][pending]
+
     def io_bytes(self):
         h2d = sum(v.numel() * v.element_size() for v in self.host_in.values())
         d2h = sum(v.numel() * v.element_size() for v in self.host_out.values())

@@ -163,3 +163,17 @@ def test_camliraft_batch2_equals_single_samples():
     for b in range(2):
         g2, g3 = _run(model, {k: v[b:b + 1] for k, v in inputs.items()})
         assert epe(f2[b].numpy(), g2[0].numpy()) <= 1e-4 and epe(f3[b].numpy(), g3[0].numpy()) <= 1e-5
+
+
+def test_engine_pipelined_matches_call():
+    """FlowEngine.pipelined (overlapped transfers) returns, batch by batch, what the synchronous call returns."""
+    from camliflow_b200.engine import FlowEngine
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    eng = FlowEngine(_model(2), 1, 160, 224, 8192, use_graph=True)
+    batches = [co.synthetic_inputs(1, 160, 224, 8192, seed=60 + i) for i in range(5)]
+    want = [{k: v.clone() for k, v in eng(b).items()} for b in batches]
+    got = [{k: v.clone() for k, v in out.items()} for out in eng.pipelined(batches)]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a["flow_2d"], b["flow_2d"]) and torch.equal(a["flow_3d"], b["flow_3d"])
