@@ -311,7 +311,9 @@ def run_train(args, rank, world, local_rank):
                                "%d iters, batch %d per GPU" % (args.workload, W, H, N, iters, B),
                    "pairs_per_step": pairs, "parallelism": "dp%d (DDP gradient all-reduce over NCCL)" % world,
                    "l2": "working set (activations of %d iterations) larger than L2" % iters,
-                   "conv_precision": "fp32" if strict else "tf32", "final_loss": float(losses[-1])},
+                   "conv_precision": ("fp32 (strict)" if strict else "tf32 for the cuDNN / cuBLAS layers of the autograd path (torch's "
+                                      "default, what the reference trains with); the fused operators stay fp32"),
+                   "final_loss": float(losses[-1])},
         "e2e": {"value": pairs * args.steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": sum(v.numel() * 4 for v in pinned.values()), "d2h_bytes_per_step": 4},
         "gpu_launches": launches * args.steps, "clocks": clocks,
@@ -325,12 +327,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--conv-precision", default="fp32", choices=["fp32", "tf32"],
-                    help="fp32: cuDNN convolutions in strict fp32, the mode the EPE parity tests run in (default); "
-                         "tf32: torch's default (cudnn.allow_tf32=True), what the reference gets out of the box")
+    ap.add_argument("--conv-precision", default=None, choices=["fp32", "tf32"],
+                    help="library (cuDNN / cuBLAS) convolution precision.  fp32: strict fp32, the mode the EPE parity tests "
+                         "run in (default for the inference workloads); tf32: torch's default (allow_tf32=True), what the "
+                         "reference trains with out of the box (default for the training workloads c5*)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.conv_precision is None:
+        args.conv_precision = "tf32" if args.workload in TRAIN_WORKLOADS else "fp32"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

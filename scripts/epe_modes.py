@@ -33,9 +33,11 @@ def main():
         m.channels_last = cl
         with torch.no_grad():
             out = m(inputs)
-        e2 = epe(out["flow_2d"][0, :, ::8, ::8].cpu().numpy(), G["c2_kernel_flow2d"])
-        e3 = epe(out["flow_3d"][0, :, ::4].cpu().numpy(), G["c2_kernel_flow3d"])
-        print(json.dumps({"allpairs": allpairs, "cudnn_tf32": tf32, "channels_last": cl, "epe2d": e2, "epe3d": e3}))
+        d2 = np.sqrt(((out["flow_2d"][0, :, ::8, ::8].cpu().numpy() - G["c2_kernel_flow2d"]) ** 2).sum(0)).ravel()
+        d3 = np.sqrt(((out["flow_3d"][0, :, ::4].cpu().numpy() - G["c2_kernel_flow3d"]) ** 2).sum(0)).ravel()
+        dist = lambda d: {"mean": float(d.mean()), "median": float(np.median(d)), "p99": float(np.percentile(d, 99)),   # noqa: E731
+                          "max": float(d.max()), "share_of_sum_in_top_1pct": float(np.sort(d)[-max(1, d.size // 100):].sum() / d.sum())}
+        print(json.dumps({"allpairs": allpairs, "cudnn_tf32": tf32, "channels_last": cl, "epe2d": dist(d2), "epe3d": dist(d3)}))
 
 
 if __name__ == "__main__":
