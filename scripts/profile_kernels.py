@@ -44,6 +44,7 @@ def main():
             "corr2d_build(allpairs+pool)": lambda: ops.corr2d_build(f1, f2, 4),
             "corr2d_lookup": lambda: ops.corr2d_lookup(pyr, coords, 4),
             "dw_gather_max_k32_O128": lambda: ops.pointconv_dw_gather_max(feat, wc, nbr, 32),
+            "dw_gather_max_k16_O128": lambda: ops.pointconv_dw_gather_max(feat, wc[:, :, :16].contiguous(), nbr, 16),
             "dw_weights_k32_O128": lambda: ops.pointconv_dw_weights(xyz, xyz, nbr, 32, wn),
             "knn_2048x2048_k32": lambda: k_nearest_neighbor(xyz, xyz, 32),
             "knn_2048x2048_k16": lambda: k_nearest_neighbor(xyz, xyz, 16),
