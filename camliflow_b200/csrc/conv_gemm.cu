@@ -219,7 +219,8 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     const uint32_t tmem_main = tmem_base + acc * 2 * BN, tmem_corr = tmem_main + BN;
                     const int kb1 = min(kb0 + CG_CHUNK, kblocks);
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(bar_full + 8 * stage, phase);
+                        // conv[s] completes only after the converter warps observed full[s] (acquire) and arrived
+                        // (release), so it also orders the TMA-written weight tiles before this thread: one wait, not two
                         mbar_wait(bar_conv + 8 * stage, phase);
                         tc_fence_after();
                         const uint32_t src = tiles_base + stage * Cfg::kStageBytes;
