@@ -103,10 +103,35 @@ __device__ __forceinline__ void knn_insert_block(KnnList& L, float d, bool valid
     }
 }
 
-// One warp: scan a staged tile for the query (ux,uy,uz).
+// One warp: per-lane minimum distance over a staged tile (lane l sees candidates l, l+32, ...).
+template <int D>
+__device__ __forceinline__ float knn_tile_lane_min(const KnnTile& t, int cnt, float ux, float uy, float uz) {
+    const int lane = threadIdx.x & 31;
+    float m = INFINITY;
+    for (int i = lane; i < cnt; i += 32) {
+        const float d = (D == 3) ? camli_sqdist3(ux - t.x[i], uy - t.y[i], uz - t.z[i]) : camli_sqdist2(ux - t.x[i], uy - t.y[i]);
+        m = fminf(m, d);
+    }
+    return m;
+}
+
+// The k-th smallest (1-based, k <= 32) of the 32 lane values, returned to every lane.
+__device__ __forceinline__ float knn_kth_smallest_of_lanes(float v, int k) {
+    const int lane = threadIdx.x & 31;
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float o = __shfl_sync(CAMLI_FULL_MASK, v, j);
+        rank += (o < v || (o == v && j < lane)) ? 1 : 0;
+    }
+    const unsigned hit = __ballot_sync(CAMLI_FULL_MASK, rank == k - 1);    // ranks are a permutation: exactly one lane
+    return __shfl_sync(CAMLI_FULL_MASK, v, __ffs(hit) - 1);
+}
+
+// One warp: scan a staged tile for the query (ux,uy,uz); candidates farther than `tau` are not offered to the list.
 template <int D, int SLOTS>
 __device__ __forceinline__ void knn_scan_tile(KnnList& L, const KnnTile& t, int tile0, int cnt, int k,
-                                              float ux, float uy, float uz) {
+                                              float ux, float uy, float uz, float tau = INFINITY) {
     const int lane = threadIdx.x & 31;
     for (int base = 0; base < cnt; base += 128) {
         float d[4];
@@ -119,22 +144,54 @@ __device__ __forceinline__ void knn_scan_tile(KnnList& L, const KnnTile& t, int 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int b = base + j * 32;
-            if (b < cnt) knn_insert_block<SLOTS>(L, d[j], b + lane < cnt, tile0 + b, k);
+            if (b < cnt) knn_insert_block<SLOTS>(L, d[j], b + lane < cnt && !(d[j] > tau), tile0 + b, k);
         }
     }
 }
 
 // Whole search for a CTA of KNN_WARPS query-warps over a cloud of m candidates.  Every thread of
 // the CTA must call (it contains __syncthreads); `active` = this warp has a real query.
+//
+// Threshold pre-pass.  The insertion sort costs ~k(1 + ln(m/k)) serial warp-collective insertions per query,
+// almost all of them for candidates that are evicted again.  A first pass over the candidates gives every lane
+// the minimum distance among ITS candidates; these 32 minima belong to 32 distinct candidates, so the k-th
+// smallest of them, tau, bounds the final k-th distance from above.  The second pass offers only candidates
+// with d <= tau to the (unchanged, reference-order) insertion routine.  Candidates with d > d_k never influence
+// the final list (the result equals the replay of the points with d <= d_k alone, which holds for
+// any candidate set containing them), so the output is bit-identical -- including ties at d_k, all of which
+// pass d <= tau -- while the number of insertions drops ~4x (k = 16, m = 2048) to ~20x (k <= 3).
 template <int D, int SLOTS, typename Points>
 __device__ __forceinline__ void knn_cta_search(KnnList& L, KnnTile& tile, const Points& pts, int m, int k,
                                                bool active, float ux, float uy, float uz) {
     L.init();
+    const bool prefilter = k <= 32 && m >= 128;          // CTA-uniform
+    if (m <= KNN_TILE) {                                   // one tile: staged once, both passes read it
+        knn_stage_tile(tile, pts, 0, m);
+        __syncthreads();
+        if (active) {
+            const float tau = prefilter ? knn_kth_smallest_of_lanes(knn_tile_lane_min<D>(tile, m, ux, uy, uz), k) : INFINITY;
+            knn_scan_tile<D, SLOTS>(L, tile, 0, m, k, ux, uy, uz, tau);
+        }
+        return;
+    }
+    float tau = INFINITY;
+    if (prefilter) {
+        float lane_min = INFINITY;
+        for (int tile0 = 0; tile0 < m; tile0 += KNN_TILE) {
+            const int cnt = min(KNN_TILE, m - tile0);
+            if (tile0) __syncthreads();
+            knn_stage_tile(tile, pts, tile0, cnt);
+            __syncthreads();
+            if (active) lane_min = fminf(lane_min, knn_tile_lane_min<D>(tile, cnt, ux, uy, uz));
+        }
+        if (active) tau = knn_kth_smallest_of_lanes(lane_min, k);
+        __syncthreads();
+    }
     for (int tile0 = 0; tile0 < m; tile0 += KNN_TILE) {
         const int cnt = min(KNN_TILE, m - tile0);
         if (tile0) __syncthreads();
         knn_stage_tile(tile, pts, tile0, cnt);
         __syncthreads();
-        if (active) knn_scan_tile<D, SLOTS>(L, tile, tile0, cnt, k, ux, uy, uz);
+        if (active) knn_scan_tile<D, SLOTS>(L, tile, tile0, cnt, k, ux, uy, uz, tau);
     }
 }
