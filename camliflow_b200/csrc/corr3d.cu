@@ -89,18 +89,32 @@ corr3d_lookup_kernel(const __grid_constant__ Corr3dLevels lv, int n1, const floa
     out[((size_t)b * n1 + q) * ld_out + level * C3_H + lane] = total;
 }
 
-// vol_out[b,p,q] = mean_j vol_in[b,p,idx[b,q,j]]   (camliraft_l_core.py:56-60)
+// vol_out[b,p,q] = mean_j vol_in[b,p,idx[b,q,j]]   (camliraft_l_core.py:56-60).  A thread owns one output column q:
+// its k neighbour columns are read once (the int64 table is the largest stream of the naive form, re-read for
+// every row) and kept in registers while the CTA walks C3P_ROWS rows of the volume.
+constexpr int C3P_ROWS = 16;
+constexpr int C3P_MAX_K = 8;
+
 __global__ void __launch_bounds__(256)
 corr3d_pool_kernel(int n1, int n_in, int n_out, int k, const float* __restrict__ vol_in,
                    const int64_t* __restrict__ idx, float* __restrict__ vol_out) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const int p = blockIdx.y, b = blockIdx.z;
+    const int p0 = blockIdx.y * C3P_ROWS, b = blockIdx.z;
     if (q >= n_out) return;
-    const float* row = vol_in + ((size_t)b * n1 + p) * n_in;
+    int col[C3P_MAX_K];
     const int64_t* ip = idx + ((size_t)b * n_out + q) * k;
-    float acc = 0.f;
-    for (int j = 0; j < k; ++j) acc += __ldg(row + __ldg(ip + j));
-    vol_out[((size_t)b * n1 + p) * n_out + q] = acc / (float)k;
+#pragma unroll
+    for (int j = 0; j < C3P_MAX_K; ++j) col[j] = j < k ? (int)__ldg(ip + j) : 0;
+    const float kf = (float)k;                          // torch.mean divides: keep the division
+    const int p1 = min(p0 + C3P_ROWS, n1);
+    for (int p = p0; p < p1; ++p) {
+        const float* row = vol_in + ((size_t)b * n1 + p) * n_in;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < C3P_MAX_K; ++j)
+            if (j < k) acc += __ldg(row + col[j]);
+        vol_out[((size_t)b * n1 + p) * n_out + q] = acc / kf;
+    }
 }
 
 }  // namespace
@@ -131,10 +145,10 @@ extern "C" int camli_corr3d_lookup(int B, int n1, int n_levels, const float* xyz
 extern "C" int camli_corr3d_pool(int B, int n1, int n_in, int n_out, int k, const float* vol_in,
                                  const int64_t* knn_idx, float* vol_out, void* stream) {
     if (B < 0 || n1 < 0 || n_in < 1 || n_out < 0 || k < 1) return CAMLI_EINVAL;
-    if (B > 65535 || n1 > 65535) return CAMLI_EUNSUPPORTED;
+    if (B > 65535 || camli_div_up(n1, C3P_ROWS) > 65535 || k > C3P_MAX_K) return CAMLI_EUNSUPPORTED;
     if (B == 0 || n1 == 0 || n_out == 0) return CAMLI_OK;
     if (!vol_in || !knn_idx || !vol_out) return CAMLI_EINVAL;
-    dim3 grid(camli_div_up(n_out, 256), n1, B);
+    dim3 grid(camli_div_up(n_out, 256), camli_div_up(n1, C3P_ROWS), B);
     corr3d_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n1, n_in, n_out, k, vol_in, knn_idx, vol_out);
     CAMLI_RETURN_LAUNCH_STATUS();
 }

@@ -84,6 +84,49 @@ dw_weights_kernel(int N, int S, int K, int k, int O,
     }
 }
 
+// ---------------------------------------------------------------- (1b) WeightNet hidden layer only
+// Layers 1-2 of the WeightNet (3 -> 8 -> 32, ReLU) per neighbour, written as rows [B,S,k,32]: the 32 -> O
+// output layer is then ONE tensor-core GEMM over all B*S*k neighbours (camli_conv_gemm with its ReLU epilogue,
+// K = 32 = a single k-block), which writes the [B,S,k,O] cache directly.  Lane = hidden unit.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+dw_hidden_kernel(int N, int S, int K, int k,
+                 const float* __restrict__ xyz, long long x_sb, long long x_sp, long long x_sd,
+                 const float* __restrict__ centre, long long c_sb, long long c_sp, long long c_sd,
+                 const int64_t* __restrict__ idx,
+                 const float* __restrict__ W1, const float* __restrict__ b1,    // [8,3],[8]
+                 const float* __restrict__ W2, const float* __restrict__ b2,    // [32,8],[32]
+                 float* __restrict__ out) {                                     // [B,S,k,32]
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (s >= S) return;
+    const int b = blockIdx.y;
+    float w1[DW_H1][3], bb1[DW_H1], w2[DW_H1];
+#pragma unroll
+    for (int a = 0; a < DW_H1; ++a) {
+        w1[a][0] = __ldg(W1 + a * 3); w1[a][1] = __ldg(W1 + a * 3 + 1); w1[a][2] = __ldg(W1 + a * 3 + 2);
+        bb1[a] = __ldg(b1 + a);
+        w2[a] = __ldg(W2 + lane * DW_H1 + a);
+    }
+    const float bb2 = __ldg(b2 + lane);
+    const float* cp = centre + b * c_sb + s * c_sp;
+    const float cx = __ldg(cp), cy = __ldg(cp + c_sd), cz = __ldg(cp + 2 * c_sd);
+    const int64_t* ip = idx + ((size_t)b * S + s) * K;
+    const float* xb = xyz + b * x_sb;
+    float* ob = out + ((size_t)b * S + s) * k * DW_H2;
+    for (int j = 0; j < k; ++j) {
+        const float* p = xb + __ldg(ip + j) * x_sp;
+        const float dx = __ldg(p) - cx, dy = __ldg(p + x_sd) - cy, dz = __ldg(p + 2 * x_sd) - cz;
+        float h2 = bb2;
+#pragma unroll
+        for (int a = 0; a < DW_H1; ++a) {
+            const float h1 = fmaxf(fmaf(w1[a][2], dz, fmaf(w1[a][1], dy, fmaf(w1[a][0], dx, bb1[a]))), 0.f);
+            h2 = fmaf(w2[a], h1, h2);
+        }
+        ob[j * DW_H2 + lane] = fmaxf(h2, 0.f);
+    }
+}
+
 // ---------------------------------------------------------------- (2) gather * weight, max over k
 // One warp per (centroid, 32-channel chunk).  The kernel is a pure stream (no reuse), so its speed is the
 // number of bytes in flight: ALL 2k 128-byte loads of a warp (k feature rows, k weight rows) are issued
@@ -196,6 +239,22 @@ extern "C" int camli_pointconv_dw_weights(int B, int N, int S, int K, int k, int
     dim3 grid(camli_div_up(S, WARPS), B);
     dw_weights_kernel<WARPS><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(
         N, S, K, k, O, xyz, x_sb, x_sp, x_sd, centre_xyz, c_sb, c_sp, c_sd, knn_idx, W1, b1, W2, b2, W3, b3, weights_out);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int camli_pointconv_dw_hidden(int B, int N, int S, int K, int k,
+                                         const float* xyz, int64_t x_sb, int64_t x_sp, int64_t x_sd,
+                                         const float* centre_xyz, int64_t c_sb, int64_t c_sp, int64_t c_sd,
+                                         const int64_t* knn_idx, const float* W1, const float* b1, const float* W2,
+                                         const float* b2, float* hidden_out, void* stream) {
+    if (B < 0 || N < 1 || S < 0 || k < 1 || K < k) return CAMLI_EINVAL;
+    if (k > 64 || B > 65535) return CAMLI_EUNSUPPORTED;
+    if (B == 0 || S == 0) return CAMLI_OK;
+    if (!xyz || !centre_xyz || !knn_idx || !W1 || !b1 || !W2 || !b2 || !hidden_out) return CAMLI_EINVAL;
+    constexpr int WARPS = 8;
+    dim3 grid(camli_div_up(S, WARPS), B);
+    dw_hidden_kernel<WARPS><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+        N, S, K, k, xyz, x_sb, x_sp, x_sd, centre_xyz, c_sb, c_sp, c_sd, knn_idx, W1, b1, W2, b2, hidden_out);
     CAMLI_RETURN_LAUNCH_STATUS();
 }
 

@@ -462,7 +462,28 @@ def pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, weight_net):
     for c in convs:
         w, b = c.folded()
         params += [w, b]
+    if not grad.needs_grad(xyz, sampled_xyz, *params) and params[4].shape[0] >= 32:
+        return _pointconv_dw_weights_tc(xyz, sampled_xyz, knn_idx, k, params, convs[2].conv_fn)
     return grad.recompute(_pointconv_dw_weights, grad.f_pointconv_dw_weights, xyz, sampled_xyz, knn_idx, k, *params)
+
+
+def _pointconv_dw_weights_tc(xyz, sampled_xyz, knn_idx, k, params, out_layer):
+    """Inference route: hidden layer [B,S,k,32] by a small kernel, the 32 -> O output layer (where the flops are)
+    as one tensor-core GEMM with its bias + ReLU epilogue over all B*S*k neighbours."""
+    params = [p.contiguous() for p in params]
+    B, _, N = xyz.shape
+    S, K = knn_idx.shape[1], knn_idx.shape[2]
+    knn_idx = knn_idx.contiguous()
+    hidden = torch.empty((B, S, k, 32), dtype=torch.float32, device=xyz.device)
+    xs, cs = xyz.stride(), sampled_xyz.stride()
+    with torch.cuda.device(xyz.device):
+        native.call("camli_pointconv_dw_hidden", i32(B), i32(N), i32(S), i32(K), i32(k),
+                    ptr(xyz), i64(xs[0]), i64(xs[2]), i64(xs[1]), ptr(sampled_xyz), i64(cs[0]), i64(cs[2]), i64(cs[1]),
+                    ptr(knn_idx), *[ptr(p) for p in params[:4]], ptr(hidden), stream(),
+                    algo_bytes=B * S * k * (32 * 4 + 8 + 12), flops=2 * B * S * k * (24 + 256))
+    w_hi, w_lo, bias = tc_weight([out_layer.weight, out_layer.bias], lambda: (params[4], params[5]))
+    O = params[4].shape[0]
+    return linear_rows(hidden.view(B, S * k, 32), w_hi, w_lo, bias, "relu").view(B, S, k, O)
 
 
 def _pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, *params):

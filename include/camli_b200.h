@@ -174,6 +174,15 @@ int camli_pointconv_dw_weights(int B, int N, int S, int K, int k, int O,
  * PointConvDW aggregation (models/point_conv.py:126-128):
  * out_rows[b,s,o] = max_{j<k} feat_rows[b, idx[b,s,j], o] * weights[b,s,j,o].  k <= 32.
  */
+/* Layers 1-2 only of the same WeightNet (3 -> 8 -> 32, ReLU) as rows hidden_out [B,S,k,32]; the 32 -> O output
+ * layer is then one camli_conv_gemm (K = 32, ReLU epilogue) over the B*S*k rows, which yields the [B,S,k,O]
+ * weights of camli_pointconv_dw_weights on the tensor cores. */
+int camli_pointconv_dw_hidden(int B, int N, int S, int K, int k,
+                              const float* xyz, int64_t x_sb, int64_t x_sp, int64_t x_sd,
+                              const float* centre_xyz, int64_t c_sb, int64_t c_sp, int64_t c_sd,
+                              const int64_t* knn_idx, const float* W1, const float* b1, const float* W2,
+                              const float* b2, float* hidden_out, void* stream);
+
 int camli_pointconv_dw_gather_max(int B, int N, int S, int K, int k, int O,
                                   const float* feat_rows, int64_t ld_feat, const float* weights,
                                   const int64_t* knn_idx, float* out_rows, int64_t ld_out, void* stream);

@@ -388,3 +388,23 @@ def test_conv_small_cin(dev, B, H, W, Cin, Cout, kh, kw, act):
     ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=(kh // 2, kw // 2))
     ref = {None: lambda v: v, "relu": torch.relu, "sigmoid": torch.sigmoid}[act](ref).permute(0, 2, 3, 1)
     assert (out.double() - ref).abs().max().item() <= 5e-6
+
+
+def test_pointconv_dw_weights_tensor_core_route(dev):
+    """Inference route of the PointConvDW WeightNet (hidden-layer kernel + tensor-core output layer) against the
+    formula; the autograd route (single fused kernel) against the same."""
+    from camliflow_b200.mlp import MLP2d
+    g = torch.Generator().manual_seed(38)
+    xyz = _cloud(2, 700, dev, 39)
+    nbr = _knn(xyz, xyz, 32)
+    wn = MLP2d(3, [8, 32, 128], act="relu").to(dev)
+    fp = []
+    for c in wn.convs:
+        fp += [c.conv_fn.weight.flatten(1), c.conv_fn.bias]
+    for k in (32, 16, 4):
+        with torch.no_grad():
+            fast = _ops().pointconv_dw_weights(xyz, xyz, nbr, k, wn)
+            ref = R.pointconv_dw_weights(xyz, xyz, nbr[:, :, :k], fp)
+        slow = _ops().pointconv_dw_weights(xyz, xyz, nbr, k, wn).detach()       # parameters require grad: fused kernel
+        _close(fast, ref, 2e-5, rtol=1e-4, what="dw_weights tensor-core route k=%d" % k)
+        _close(slow, ref, 2e-5, rtol=1e-4, what="dw_weights fused kernel k=%d" % k)
