@@ -68,6 +68,11 @@ struct CgParams {
     long long ldo;
     int act;                       // CAMLI_ACT_*
     float slope;
+    // fused ConvGRU epilogues (CAMLI_ACT_GRU_*): per-pixel side inputs and an optional second destination
+    const float* aux1; long long ld1;
+    const float* aux2; long long ld2;
+    int split;                     // columns >= split: GATE multiplies by aux1[:, n - split]; with out2 they go to out2
+    float* out2; long long ldo2;
     long long* timeline;           // diagnostics: SM-clock stamps of CTA 0's pipeline events (null in production)
 };
 
@@ -81,6 +86,55 @@ __device__ __forceinline__ float cg_activate(float v, float slope) {
     if (ACT == CAMLI_ACT_TANH) return tanhf(v);
     if (ACT == CAMLI_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     return v;
+}
+
+// ConvGRU epilogues (reference models/raft_core.py:125-138), same arithmetic as gru_gate_kernel / gru_update_kernel:
+//   GATE   : sigmoid(v), times a1 (the hidden state) for the reset-gate columns (a1 != null)
+//   UPDATE : (1 - z) * h + z * tanh(v) with z = a1, h = a2; the _FIX variant adds torch.nan_to_num
+template <int ACT>
+__device__ __forceinline__ float cg_gru(float v, float a1, float a2, bool has_a1) {
+    if (ACT == CAMLI_ACT_GRU_GATE) {
+        const float g = 1.f / (1.f + expf(-v));
+        return has_a1 ? g * a1 : g;
+    }
+    float r = (1.f - a1) * a2 + a1 * tanhf(v);
+    if (ACT == CAMLI_ACT_GRU_UPDATE_FIX) {
+        if (isnan(r)) r = 0.f;
+        else if (isinf(r)) r = r > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+    }
+    return r;
+}
+
+template <int ACT>
+__device__ __forceinline__ void cg_store32_gru(float (&v)[32], float* __restrict__ orow, const float* __restrict__ rrow,
+                                               const float* __restrict__ bias, const float* __restrict__ a1,
+                                               const float* __restrict__ a2, int col0, int n_cols) {
+    const bool vec = col0 + 32 <= n_cols &&
+                     (((reinterpret_cast<uintptr_t>(orow) | reinterpret_cast<uintptr_t>(rrow) | reinterpret_cast<uintptr_t>(a1) |
+                        reinterpret_cast<uintptr_t>(a2)) & 15) == 0);
+    if (vec) {                                           // 128-bit side loads and stores (null pointers count as aligned)
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + col0 + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 r = rrow ? __ldg(reinterpret_cast<const float4*>(rrow + j)) : z4;
+            const float4 p = a1 ? __ldg(reinterpret_cast<const float4*>(a1 + j)) : z4;
+            const float4 q = a2 ? __ldg(reinterpret_cast<const float4*>(a2 + j)) : z4;
+            *reinterpret_cast<float4*>(orow + j) =
+                make_float4(cg_gru<ACT>(v[j] + r.x, p.x, q.x, a1 != nullptr), cg_gru<ACT>(v[j + 1] + r.y, p.y, q.y, a1 != nullptr),
+                            cg_gru<ACT>(v[j + 2] + r.z, p.z, q.z, a1 != nullptr), cg_gru<ACT>(v[j + 3] + r.w, p.w, q.w, a1 != nullptr));
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (col0 + j >= n_cols) break;
+        const float x = v[j] + (bias ? __ldg(bias + col0 + j) : 0.f) + (rrow ? __ldg(rrow + j) : 0.f);
+        orow[j] = cg_gru<ACT>(x, a1 ? __ldg(a1 + j) : 0.f, a2 ? __ldg(a2 + j) : 0.f, a1 != nullptr);
+    }
 }
 
 // One thread's 32 consecutive output columns: + bias, + residual, activation, store (masked at the ragged edge).
@@ -317,6 +371,20 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     if (col0 >= P.Cout) break;
                     float (&v)[32] = *reinterpret_cast<float (*)[32]>(&sum[c * 32]);
                     const float* rr = rrow ? rrow + c * 32 : nullptr;
+                    if (P.act >= CAMLI_ACT_GRU_GATE) {
+                        const bool hi_part = col0 >= P.split;
+                        float* dst = (P.out2 && hi_part) ? P.out2 + pix * P.ldo2 + (col0 - P.split) : orow + c * 32;
+                        if (P.act == CAMLI_ACT_GRU_GATE) {
+                            const float* a1 = hi_part ? P.aux1 + pix * P.ld1 + (col0 - P.split) : nullptr;
+                            cg_store32_gru<CAMLI_ACT_GRU_GATE>(v, dst, rr, P.bias, a1, nullptr, col0, P.Cout);
+                        } else {
+                            const float* a1 = P.aux1 + pix * P.ld1 + col0;
+                            const float* a2 = P.aux2 + pix * P.ld2 + col0;
+                            if (P.act == CAMLI_ACT_GRU_UPDATE) cg_store32_gru<CAMLI_ACT_GRU_UPDATE>(v, dst, rr, P.bias, a1, a2, col0, P.Cout);
+                            else cg_store32_gru<CAMLI_ACT_GRU_UPDATE_FIX>(v, dst, rr, P.bias, a1, a2, col0, P.Cout);
+                        }
+                        continue;
+                    }
                     switch (P.act) {
                         case CAMLI_ACT_RELU: cg_store32<CAMLI_ACT_RELU>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
                         case CAMLI_ACT_LEAKY: cg_store32<CAMLI_ACT_LEAKY>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
@@ -394,9 +462,25 @@ extern "C" int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int
                                const float* w_hi, const float* w_lo, int Cout, int kh, int kw,
                                const float* bias, const float* residual, int64_t ldr,
                                int act, float slope, float* out, int64_t ldo, int tile_n, void* stream) {
-    if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin || ldo < Cout) return CAMLI_EINVAL;
-    if (residual && ldr < Cout) return CAMLI_EINVAL;
     if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
+    return camli_conv_gemm_fused(x, B, H, W, Cin, ldx, w_hi, w_lo, Cout, kh, kw, bias, residual, ldr, act, slope, out, ldo,
+                                 nullptr, 0, nullptr, 0, 0, nullptr, 0, tile_n, stream);
+}
+
+extern "C" int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Cin, int64_t ldx,
+                                     const float* w_hi, const float* w_lo, int Cout, int kh, int kw,
+                                     const float* bias, const float* residual, int64_t ldr,
+                                     int act, float slope, float* out, int64_t ldo,
+                                     const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,
+                                     float* out2, int64_t ldo2, int tile_n, void* stream) {
+    if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin) return CAMLI_EINVAL;
+    if (residual && ldr < Cout) return CAMLI_EINVAL;
+    if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_GRU_UPDATE_FIX) return CAMLI_EINVAL;
+    if (act == CAMLI_ACT_GRU_GATE && (!aux1 || split < 0 || split > Cout || (split & 31) || ld1 < Cout - split)) return CAMLI_EINVAL;
+    if (act > CAMLI_ACT_GRU_GATE && (!aux1 || !aux2 || ld1 < Cout || ld2 < Cout)) return CAMLI_EINVAL;
+    if (act < CAMLI_ACT_GRU_GATE) { split = Cout; out2 = nullptr; }
+    if (act > CAMLI_ACT_GRU_GATE) { split = Cout; out2 = nullptr; }
+    if (out2 ? (ldo < split || ldo2 < Cout - split) : ldo < Cout) return CAMLI_EINVAL;
     // TMA: 16-byte aligned bases and strides; odd windows only ("same" padding)
     if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (Cin & 3) || (ldx & 3)) return CAMLI_EUNSUPPORTED;
     if (B == 0) return CAMLI_OK;
@@ -427,6 +511,7 @@ extern "C" int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int
     if (bn != 32 && bn != 64 && bn != 128) return CAMLI_EINVAL;
     P.tiles_n = camli_div_up(Cout, bn);
     P.bias = bias; P.residual = residual; P.ldr = ldr; P.out = out; P.ldo = ldo; P.act = act; P.slope = slope; P.timeline = camli_cg_timeline;
+    P.aux1 = aux1; P.ld1 = ld1; P.aux2 = aux2; P.ld2 = ld2; P.split = split; P.out2 = out2; P.ldo2 = ldo2;
     const long long total = (long long)B * P.tiles_y * P.tiles_x * P.tiles_n;
     if (total > 2147483647LL) return CAMLI_EUNSUPPORTED;
 

@@ -193,7 +193,8 @@ def _allpairs(a_rows, b_rows, scale):
 
 
 # ---------------------------------------------------------------- tensor-core linear / convolution
-ACT_CODES = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "tanh": 3, "sigmoid": 4}
+ACT_CODES = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "tanh": 3, "sigmoid": 4,
+             "gru_gate": 5, "gru_update": 6, "gru_update_fix": 7}
 _TC_WEIGHTS = {}
 
 
@@ -235,11 +236,14 @@ def conv_gemm_ok(x_bhwc, kh=1, kw=1):
     return ok and x_bhwc.shape[-1] % 4 == 0 and kh % 2 == 1 and kw % 2 == 1
 
 
-def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residual=None, out=None, tile_n=0):
+def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residual=None, out=None, tile_n=0,
+              aux1=None, aux2=None, split=0, out2=None):
     """Linear layer / stride-1 "same" convolution + bias + residual + activation in one tcgen05 kernel
     (include/camli_b200.h: camli_conv_gemm).  x_bhwc [B,H,W,Cin] channel-last view (a linear layer over rows
     is [1,1,R,K]); w_hi/w_lo [Cout, kh*kw*Cin] from tc_weight(); residual / out [B,H,W,Cout] channel-last views
-    (out may be a channel slice of a wider buffer).  Returns out."""
+    (out may be a channel slice of a wider buffer).  act "gru_gate" / "gru_update[_fix]" fuse the ConvGRU
+    arithmetic (camli_conv_gemm_fused): aux1 / aux2 [B,H,W,*] channel-last side inputs, columns >= split of a gate
+    convolution go to out2.  Returns out."""
     _need_cuda(x_bhwc, w_hi, w_lo)
     _no_grad("conv_gemm", x_bhwc, w_hi)
     B, H, W, Cin = x_bhwc.shape
@@ -248,18 +252,22 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
     ldx, ok = _pixel_layout(x_bhwc)
     if not ok or Cin % 4:
         raise RuntimeError("conv_gemm: input must be a 16-byte aligned channel-last view with Cin % 4 == 0")
+    n_out = split if out2 is not None else Cout
     if out is None:
-        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x_bhwc.device)
-    ldo = _pixel_layout(out)[0] if out.shape[-1] == Cout else None
-    assert tuple(out.shape) == (B, H, W, Cout) and ldo is not None
+        out = torch.empty((B, H, W, n_out), dtype=torch.float32, device=x_bhwc.device)
+    assert tuple(out.shape) == (B, H, W, n_out)
+    ldo = _pixel_layout(out)[0]
     ldr = 0
     if residual is not None:
         assert tuple(residual.shape) == (B, H, W, Cout)
         ldr = _pixel_layout(residual)[0]
     with torch.cuda.device(x_bhwc.device):
-        native.call("camli_conv_gemm", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w_hi), ptr(w_lo),
+        native.call("camli_conv_gemm_fused", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w_hi), ptr(w_lo),
                     i32(Cout), i32(kh), i32(kw), ptr(bias), ptr(residual), i64(ldr), i32(ACT_CODES[act]),
-                    ctypes.c_float(slope), ptr(out), i64(ldo), i32(tile_n), stream(),
+                    ctypes.c_float(slope), ptr(out), i64(ldo),
+                    ptr(aux1), i64(_pixel_layout(aux1)[0] if aux1 is not None else 0),
+                    ptr(aux2), i64(_pixel_layout(aux2)[0] if aux2 is not None else 0), i32(split),
+                    ptr(out2), i64(_pixel_layout(out2)[0] if out2 is not None else 0), i32(tile_n), stream(),
                     algo_bytes=B * H * W * (Cin + Cout) * 4 + Cout * kh * kw * Cin * 4,
                     flops=2 * B * H * W * Cout * kh * kw * Cin)
     return out

@@ -174,8 +174,10 @@ class GRU2D(nn.Module):
         return ops.gru_update(z, h, tc.conv2d(rhx, convq), fix_nonfinite=last)
 
     def _split_weights(self, convz, convr, convq, n_h, n_static):
-        """The z|r and q convolutions split by input-channel group [h | x_static | x_dynamic]: the x_static part
-        (the context features, identical in every refinement iteration) is convolved once per forward."""
+        """The z|r and q convolutions split by input-channel group [h | x_static | x_dynamic], as tf32 hi/lo
+        OHWI matrices: the x_static part (the context features, identical in every refinement iteration) is
+        convolved once per forward; the per-iteration parts read the recurrent buffer [h | x_dynamic | r*h]
+        (z|r from its first two groups, q from its last two, hence the [x_dynamic | r*h] column order of w_q)."""
         key = tuple((p.data_ptr(), p._version) for p in (convz.weight, convz.bias, convr.weight, convr.bias,
                                                         convq.weight, convq.bias)) + (n_h, n_static)
         cache = self.__dict__.setdefault("_split_cache", {})
@@ -184,27 +186,49 @@ class GRU2D(nn.Module):
             with torch.no_grad():
                 wzr, bzr = self._merged_zr(convz, convr)
                 lo, hi = n_h, n_h + n_static
-                dyn = lambda w: torch.cat([w[:, :lo], w[:, hi:]], 1).contiguous()      # noqa: E731
-                hit = (key, dyn(wzr), bzr, wzr[:, lo:hi].contiguous(), dyn(convq.weight), convq.bias,
-                       convq.weight[:, lo:hi].contiguous())
+                ohwi = lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()     # noqa: E731
+                keep = [torch.cat([wzr[:, :lo], wzr[:, hi:]], 1), wzr[:, lo:hi],
+                        torch.cat([convq.weight[:, hi:], convq.weight[:, :lo]], 1), convq.weight[:, lo:hi]]
+                mats = [ops.tc_weight([t], lambda t=t: (ohwi(t), None))[:2] for t in keep]
+                hit = (key, keep, mats, bzr.contiguous(), convq.bias.detach().contiguous())
             cache[id(convz)] = hit
-        return hit[1:]
+        return hit[2], hit[3], hit[4]
 
     def forward_split(self, h, x_static, x_dynamic, cache):
-        """forward(h, cat([x_static, x_dynamic])) with the x_static contributions to the z, r and q
-        pre-activations taken from `cache` (a dict owned by the caller for one forward pass) and added in the
-        convolution epilogues: the per-iteration convolutions shrink from 384 to 256 input channels."""
-        n_h, n_static = h.shape[1], x_static.shape[1]
+        """forward(h, cat([x_static, x_dynamic])) as four tensor-core launches per call and nothing else:
+        * the x_static contributions to the z, r and q pre-activations come from `cache` (a dict owned by the
+          caller for one forward pass) and are added in the convolution epilogues (384 -> 256 input channels);
+        * the gate and update arithmetic runs in the epilogues too (camli_conv_gemm_fused): the z|r convolution
+          writes z and r*h, the q convolution writes h' over h -- no gate, update or concatenation kernels;
+        * h, x_dynamic and r*h live in one channel-last buffer [h | x_dynamic | r*h]; the returned state is a
+          view of its first group and is recognised (no copy) when it comes back in the next iteration."""
+        B, C, H, W = h.shape
+        S, X = x_static.shape[1], x_dynamic.shape[1]
+        bufs = cache.get("gru2d_buffers")
+        if bufs is None:
+            bufs = (torch.empty((B, H, W, C + X + C), dtype=torch.float32, device=h.device),
+                    torch.empty((B, H, W, C), dtype=torch.float32, device=h.device))
+            cache["gru2d_buffers"] = bufs
+        Q, Z = bufs
+        h_rows = Q[..., :C]
+        if h.data_ptr() != h_rows.data_ptr():
+            h_rows.copy_(h.permute(0, 2, 3, 1))
+        Q[..., C:C + X].copy_(x_dynamic.permute(0, 2, 3, 1))
+        xs_rows = x_static.permute(0, 2, 3, 1)
+        if not ops.conv_gemm_ok(xs_rows):
+            xs_rows = xs_rows.contiguous()
         for half, (cz, cr, cq) in enumerate(((self.convz1, self.convr1, self.convq1), (self.convz2, self.convr2, self.convq2))):
-            w_zr, b_zr, w_zr_s, w_q, b_q, w_q_s = self._split_weights(cz, cr, cq, n_h, n_static)
+            (w_zr, w_zr_s, w_q, w_q_s), b_zr, b_q = self._split_weights(cz, cr, cq, C, S)
+            kh, kw = cz.kernel_size
             ctx = cache.get(("gru2d", half))
             if ctx is None:
-                ctx = (tc.conv2d_weights(x_static, w_zr_s, None, cz.padding), tc.conv2d_weights(x_static, w_q_s, None, cq.padding))
+                ctx = (ops.conv_gemm(xs_rows, *w_zr_s, kh, kw), ops.conv_gemm(xs_rows, *w_q_s, kh, kw))
                 cache[("gru2d", half)] = ctx
-            zr = tc.conv2d_weights(torch.cat([h, x_dynamic], dim=1), w_zr, b_zr, cz.padding, residual=ctx[0])
-            z, rhx = ops.gru_gate(zr, h, x_dynamic)
-            h = ops.gru_update(z, h, tc.conv2d_weights(rhx, w_q, b_q, cq.padding, residual=ctx[1]), fix_nonfinite=half == 1)
-        return h
+            ops.conv_gemm(Q[..., :C + X], *w_zr, kh, kw, b_zr, "gru_gate", residual=ctx[0], out=Z, out2=Q[..., C + X:],
+                          aux1=h_rows, split=C)
+            ops.conv_gemm(Q[..., C:], *w_q, kh, kw, b_q, "gru_update_fix" if half == 1 else "gru_update", residual=ctx[1],
+                          out=h_rows, aux1=Z, aux2=h_rows)
+        return h_rows.permute(0, 3, 1, 2)
 
     def forward(self, h, x):
         if h.is_cuda and not (torch.is_grad_enabled() and (h.requires_grad or x.requires_grad or self.convz1.weight.requires_grad)):

@@ -287,6 +287,10 @@ int camli_gru_update(int64_t n, const float* z, const float* h, const float* q, 
 #define CAMLI_ACT_LEAKY   2   /* v > 0 ? v : v * slope */
 #define CAMLI_ACT_TANH    3
 #define CAMLI_ACT_SIGMOID 4
+/* fused ConvGRU epilogues of camli_conv_gemm_fused (models/raft_core.py:125-138) */
+#define CAMLI_ACT_GRU_GATE       5   /* sigmoid(v); columns >= split are multiplied by aux1[p, n - split] (r * h)      */
+#define CAMLI_ACT_GRU_UPDATE     6   /* (1 - z) * h + z * tanh(v) with z = aux1[p, n], h = aux2[p, n]                */
+#define CAMLI_ACT_GRU_UPDATE_FIX 7   /* ... followed by torch.nan_to_num                                              */
 
 /* x -> (hi, lo) with hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand split of the 3xTF32
  * tensor-core kernels; used once per weight tensor. */
@@ -309,6 +313,21 @@ int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int64_t ldx,
                     const float* w_hi, const float* w_lo, int Cout, int kh, int kw,
                     const float* bias, const float* residual, int64_t ldr,
                     int act, float slope, float* out, int64_t ldo, int tile_n, void* stream);
+
+/*
+ * camli_conv_gemm with the ConvGRU gate / update arithmetic in its epilogue, so a ConvGRU half is two launches
+ * (z|r convolution -> z and r*h; q convolution -> h') with no gate / update / concatenation kernels:
+ * aux1 [B*H*W, ld1], aux2 [B*H*W, ld2] per-pixel side inputs (see CAMLI_ACT_GRU_*); with act = GRU_GATE and out2 != NULL
+ * the columns n >= split are written to out2[p, n - split] (row stride ldo2) instead of out.  The bias and the residual
+ * are added before the gate arithmetic.  `out` may alias aux2 (h' over h): each element is read and written by the
+ * same thread.  Other arguments as camli_conv_gemm.
+ */
+int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Cin, int64_t ldx,
+                          const float* w_hi, const float* w_lo, int Cout, int kh, int kw,
+                          const float* bias, const float* residual, int64_t ldr,
+                          int act, float slope, float* out, int64_t ldo,
+                          const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,
+                          float* out2, int64_t ldo2, int tile_n, void* stream);
 
 /*
  * The same operation for a handful of output channels (Cout <= 4: the last layer of the flow heads,
