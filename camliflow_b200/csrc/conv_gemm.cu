@@ -501,13 +501,12 @@ extern "C" int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Ci
     }
     P.th = best_th; P.tw = CG_BM / best_th;
     P.tiles_y = camli_div_up(H, P.th); P.tiles_x = camli_div_up(W, P.tw);
-    // N tile: wide tiles amortise the activation split; small problems take narrow tiles to fill the SMs
+    // N tile: the widest tile that Cout fills.  A tf32 MMA instruction costs the same ~140 cycles whatever its N
+    // (measured, M = 128), so a narrow tile does not shorten a CTA's k-loop -- it only multiplies the CTAs (and the
+    // activation splits).  Few, wide CTAs also leave SMs free for the kernels of the other branch's stream: the
+    // C_out <= 128 convolutions of the update block occupy 68 SMs instead of 136, a point-branch linear 16 instead of 64.
     int bn = tile_n;
-    if (bn == 0) {
-        const long long mt = (long long)B * P.tiles_y * P.tiles_x;
-        bn = 128;
-        while (bn > 32 && (Cout <= bn / 2 || mt * camli_div_up(Cout, bn) * 10 < (long long)sm_count() * 6)) bn /= 2;
-    }
+    if (bn == 0) bn = Cout > 64 ? 128 : (Cout > 32 ? 64 : 32);
     if (bn != 32 && bn != 64 && bn != 128) return CAMLI_EINVAL;
     P.tiles_n = camli_div_up(Cout, bn);
     P.bias = bias; P.residual = residual; P.ldr = ldr; P.out = out; P.ldo = ldo; P.act = act; P.slope = slope; P.timeline = camli_cg_timeline;

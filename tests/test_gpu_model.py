@@ -177,3 +177,20 @@ def test_engine_pipelined_matches_call():
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert torch.equal(a["flow_2d"], b["flow_2d"]) and torch.equal(a["flow_3d"], b["flow_3d"])
+
+
+def test_engine_pool_matches_call():
+    """EnginePool.pipelined (several CUDA graphs in flight over one model) returns, in submission order, what the
+    synchronous single-engine call returns."""
+    from camliflow_b200.engine import EnginePool, FlowEngine
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    model = _model(2)
+    eng = FlowEngine(model, 1, 160, 224, 8192, use_graph=True)
+    batches = [co.synthetic_inputs(1, 160, 224, 8192, seed=70 + i) for i in range(7)]
+    want = [{k: v.clone() for k, v in eng(b).items()} for b in batches]
+    pool = EnginePool(model, 3, 1, 160, 224, 8192, use_graph=True)
+    got = [{k: v.clone() for k, v in out.items()} for out in pool.pipelined(batches)]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a["flow_2d"], b["flow_2d"]) and torch.equal(a["flow_3d"], b["flow_3d"])
