@@ -192,7 +192,6 @@ def run_ours(args, rank, world, local_rank):
     ms_dev = timed(engine.step, args.steps, args.warmup)
     if os.environ.get("CAMLI_PROFILER_RANGE"):
         torch.cuda.profiler.stop()
-    clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(lambda: engine(pinned), args.steps, args.warmup)
 
     # the same end-to-end call in throughput mode: H2D of pair i+1 and D2H of pair i-1 overlap the compute of pair i
@@ -250,6 +249,8 @@ def run_ours(args, rank, world, local_rank):
                 "engines": args.concurrent,
                 "mode": "EnginePool.pipelined: %d CUDA graphs of batch %d in flight, round-robin; each pair pays its own pinned "
                         "H2D + D2H (host wall clock)" % (args.concurrent, B)}
+
+    clocks = sampler.stop() if rank == 0 else None      # sampled over every timed region above
 
     # per-launch timing of the dominant hand-written kernel (eager pass, events on the launch stream)
     roofline = None
