@@ -1,15 +1,23 @@
 #!/bin/bash
-# One GPU-box round: parity tests, bench, launch list, ncu captures. Outputs under gpurun_out/.
+# GPU box round: parity tests, EPE per precision mode, kernel microbench, bench, kernel timeline.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt
-timeout 1200 python -m pytest tests -m gpu -q -s 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/pytest_gpu.log
-timeout 300 python scripts/profile_kernels.py > gpurun_out/kernels.json 2> gpurun_out/kernels.err; tail -3 gpurun_out/kernels.err
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -c 1500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-if [ "$1" != "quick" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 14000 -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-wc -l gpurun_out/launches.csv
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'corr2d_lookup_kernel|dw_gather_max_kernel|knn_warp_kernel|allpairs_tf32x3_kernel|corr3d_lookup_kernel' -c 12 -f -o gpurun_out/prof_kernels python scripts/profile_kernels.py --iters 1 > gpurun_out/ncu_kernels.log 2>&1
-ls -la gpurun_out/*.ncu-rep
-fi
+timeout 1200 python -m pytest tests -m gpu -q -s -x 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+grep -E "passed|failed|FAILED|EPE|Error" gpurun_out/pytest_gpu.log
+timeout 600 python scripts/epe_modes.py > gpurun_out/epe_modes.jsonl 2> gpurun_out/epe_modes.err; cat gpurun_out/epe_modes.jsonl; tail -3 gpurun_out/epe_modes.err
+timeout 300 python scripts/profile_kernels.py --iters 3 > gpurun_out/kernels.json 2> gpurun_out/kernels.err; tail -3 gpurun_out/kernels.err
+python - <<'PY'
+import json
+k=json.load(open("gpurun_out/kernels.json"))
+for n,v in k.items():
+    if n.endswith("/min"): print("%-48s %s"%(n[:-4], v))
+PY
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_fp32.json 2> gpurun_out/bench.err
+tail -5 gpurun_out/bench.err
+python - <<'PY'
+import json
+for f in ("fp32",):
+    try:
+        b=json.load(open("gpurun_out/bench_%s.json"%f)); print(f, b["value"], b["ms_per_step"], b["e2e"]["value"], b["gpu_launches"], b.get("cpu_baseline",{}).get("value"))
+    except Exception as e: print(f, "ERR", e)
+PY
+timeout 600 python scripts/trace_forward.py > gpurun_out/trace.log 2>&1; tail -45 gpurun_out/trace.log | cut -c1-150
