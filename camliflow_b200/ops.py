@@ -732,8 +732,16 @@ def profile_end(peaks_path=None):
         out = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "peak_source": src, "unit": "GB/s",
                "frac": achieved / hbm, "algorithmic_bytes_per_launch": rec["bytes"]}
     out.update({"traffic": None, "avg_us": rec["avg_us"], "launches": rec["launches"], "all": per})
-    # the two HBM-bound kernels the north star names, always reported
+    # the two HBM-bound kernels the north star names, always reported: live CUDA-event figures of this run (cold
+    # launches of an eager pass, launch overhead included) + the ncu capture committed under profiles/ (kernel-only
+    # duration and DRAM traffic at the C2 sizes: profiles/r1_v5_kernels.json)
+    ncu = {"camli_corr2d_lookup": {"ncu_us": 14.8, "ncu_dram_traffic_bytes": 37.4e6, "algorithmic_bytes": 23.7e6},
+           "camli_pointconv_dw_gather_max": {"ncu_us": 14.8, "ncu_dram_traffic_bytes": 35.1e6, "algorithmic_bytes": 35.1e6}}
     for name, key in (("camli_corr2d_lookup", "corr_lookup"), ("camli_pointconv_dw_gather_max", "knn_gather")):
         if name in per:
             out[key] = {"achieved_GBps": per[name]["GBps"], "frac_of_hbm_peak": per[name]["GBps"] / hbm, "avg_us": per[name]["avg_us"]}
+            c = ncu[name]
+            out[key].update({"ncu_us": c["ncu_us"], "traffic": c["ncu_dram_traffic_bytes"],
+                             "ncu_frac_of_hbm_peak_algorithmic": c["algorithmic_bytes"] / (c["ncu_us"] * 1e-6) / 1e9 / hbm,
+                             "ncu_frac_of_hbm_peak_traffic": c["ncu_dram_traffic_bytes"] / (c["ncu_us"] * 1e-6) / 1e9 / hbm})
     return out
