@@ -408,3 +408,25 @@ def test_pointconv_dw_weights_tensor_core_route(dev):
         slow = _ops().pointconv_dw_weights(xyz, xyz, nbr, k, wn).detach()       # parameters require grad: fused kernel
         _close(fast, ref, 2e-5, rtol=1e-4, what="dw_weights tensor-core route k=%d" % k)
         _close(slow, ref, 2e-5, rtol=1e-4, what="dw_weights fused kernel k=%d" % k)
+
+
+def test_dense_three_nn_kitti_size(dev):
+    """the KITTI-submission densification, 375 x 1242 = 465 750 queries against 8192 points
+    (kitti_submission.py:89-93), against the formula with the kernel's own neighbour indices."""
+    import time
+    from camliflow_b200.utils import densify_flow_3d
+    g = torch.Generator().manual_seed(40)
+    H, W, f, cx, cy = 375, 1242, 721.5, 609.5, 172.8
+    disp = (torch.rand(H, W, generator=g) * 70 + 5).to(dev)
+    u, v, z = torch.rand(8192, generator=g) * (W - 1), torch.rand(8192, generator=g) * (H - 1), torch.rand(8192, generator=g) * 60 + 5
+    pc1 = torch.stack([(u - cx) * z / f, (v - cy) * z / f, z], 0).to(dev)
+    flow = (torch.randn(3, 8192, generator=g) * 0.3).to(dev)
+    dense, got = densify_flow_3d(pc1, flow, disp, 0.54, f, cx, cy)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dense, got = densify_flow_3d(pc1, flow, disp, 0.54, f, cx, cy)
+    torch.cuda.synchronize()
+    print("dense three-NN, %d queries x 8192 points: %.2f ms" % (H * W, (time.perf_counter() - t0) * 1e3))
+    idx = _knn(pc1[None], dense[None], 3)
+    ref = R.knn_interpolate(pc1[None], flow[None], dense[None], idx)[0]
+    _close(got, ref, 1e-5, what="dense three-NN")

@@ -114,3 +114,21 @@ def test_camliraft_l_c1_on_cpu_matches_reference_golden():
         for b in range(B):
             e3 = epe(out["flow_3d"][b, :, ::4].numpy(), want[b])
             assert e3 <= 1e-4, (case, b, e3)
+
+
+def test_disp2pc_matches_reference_formula():
+    """utils.disp2pc against the reference's numpy arithmetic (utils.py:319-339), with and without flow."""
+    from camliflow_b200.utils import disp2pc
+    rng = np.random.default_rng(0)
+    disp = rng.uniform(1.0, 80.0, (37, 53)).astype(np.float32)
+    flow = rng.normal(0, 3, (37, 53, 2)).astype(np.float32)
+    f, cx, cy, baseline = 721.5, 609.5, 172.8, 0.54
+    for fl in (None, flow):
+        depth = baseline * f / (disp + 1e-5)
+        xx = np.tile(np.arange(53, dtype=np.float32)[None, :], (37, 1))
+        yy = np.tile(np.arange(37, dtype=np.float32)[:, None], (1, 53))
+        if fl is not None:
+            xx, yy = xx + fl[..., 0], yy + fl[..., 1]
+        want = np.stack([(xx - cx) * depth / f, (yy - cy) * depth / f, depth], -1)
+        got = disp2pc(torch.from_numpy(disp), baseline, f, cx, cy, None if fl is None else torch.from_numpy(fl)).numpy()
+        assert np.allclose(got, want, rtol=1e-6, atol=1e-6)
