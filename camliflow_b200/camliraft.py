@@ -1,17 +1,18 @@
 """CamLiRAFT model wrapper (reference models/camliraft.py:32-73): pad to a multiple of 8,
 ImageNet normalisation, inverse-depth scaling of the clouds, the fused core, and the way back.
-The sequence losses of models/losses.py are evaluated when targets are supplied (training step); the metric
-bookkeeping of models/base.py is outside this path."""
+The sequence losses of models/losses.py and the metric bookkeeping of models/base.py (device-side accumulation,
+one all-reduce at read-out: camliflow_b200/base.py) are evaluated when targets are supplied."""
 import torch
 import torch.nn as nn
 
+from .base import FlowModel
 from .camliraft_core import CamLiRAFT_Core
 from .ids import paral2persp, persp2paral
 from .losses import calc_sequence_loss_2d, calc_sequence_loss_3d
 from .utils import InputPadder
 
 
-class CamLiRAFT(nn.Module):
+class CamLiRAFT(FlowModel):
     def __init__(self, cfgs):
         super().__init__()
         self.cfgs = cfgs
@@ -62,4 +63,15 @@ class CamLiRAFT(nn.Module):
             self.loss2d = calc_sequence_loss_2d(preds_2d, inputs["flow_2d"].float(), self.cfgs.loss2d)
             self.loss3d = calc_sequence_loss_3d(preds_3d, inputs["flow_3d"].float(), self.cfgs.loss3d)
             self.loss = self.loss2d + self.loss3d
+            self.update_metrics("loss", self.loss)
+            self.update_metrics("loss2d", self.loss2d)
+            self.update_metrics("loss3d", self.loss3d)
+            self.update_2d_metrics(preds_2d[-1], inputs["flow_2d"].float())
+            self.update_3d_metrics(preds_3d[-1], inputs["flow_3d"].float())
+            if "occ_mask_3d" in inputs:
+                self.update_3d_metrics(preds_3d[-1], inputs["flow_3d"].float(), inputs["occ_mask_3d"])
         return {"flow_2d": preds_2d[-1], "flow_3d": preds_3d[-1]}
+
+    @staticmethod
+    def is_better(curr_metrics, best_metrics):
+        return best_metrics is None or curr_metrics["epe2d"] < best_metrics["epe2d"]

@@ -16,7 +16,10 @@ def main():
     g = torch.Generator().manual_seed(0)
     lib = native.lib()
     for (B, H, W, Ci, Co, kh, kw, tile_n) in [(1, 1, 2048, 384, 128, 1, 1, 0), (1, 1, 2048, 128, 128, 1, 1, 0),
-                                              (1, 1, 2048, 384, 128, 1, 1, 128), (1, 68, 120, 256, 192, 3, 3, 0)]:
+                                              (1, 1, 2048, 384, 128, 1, 1, 128), (1, 68, 120, 256, 192, 3, 3, 0),
+                                              (1, 68, 120, 256, 128, 1, 5, 0), (1, 68, 120, 256, 128, 1, 5, 64),
+                                              (1, 68, 120, 256, 126, 3, 3, 64), (1, 68, 120, 128, 128, 1, 1, 0),
+                                              (1, 1, 2048, 4, 32, 1, 1, 0)]:
         x = torch.randn(B, H, W, Ci, generator=g).to(dev)
         wt = (torch.randn(Co, kh * kw * Ci, generator=g) / (kh * kw * Ci) ** 0.5).to(dev)
         w_hi, w_lo, _ = ops.tc_weight([wt], lambda: (wt, None))

@@ -12,11 +12,11 @@ from tests import torch_ref as R
 def _knn(input_xyz, query_xyz, k, cpp_impl=True):
     if input_xyz.shape[1] > 3:
         input_xyz, query_xyz = input_xyz.transpose(1, 2), query_xyz.transpose(1, 2)
-    return co.knn(input_xyz, query_xyz, k, "kernel")
+    return co.knn(input_xyz.detach(), query_xyz.detach(), k, "kernel")       # (indices carry no gradient)
 
 
 def _fps(xyz, n_samples, cpp_impl=True):
-    return co.fps(xyz.contiguous(), n_samples, "kernel")
+    return co.fps(xyz.detach().contiguous(), n_samples, "kernel")
 
 
 def _folded(layers):

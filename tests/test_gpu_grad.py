@@ -219,3 +219,47 @@ def test_camliraft_training_step_gradients(dev):
     worst = max((_rel(grads[n], ref_grads[n]), n) for n in grads if ref_grads[n].abs().max() > 1e-9)
     print("training step: loss %.6f (formula %.6f), worst relative gradient difference %.2e at %s" % ((loss, ref_loss) + worst))
     assert worst[0] <= 5e-3, worst
+
+
+# ------------------------------------------------------------------ training parity against the REFERENCE's gradients
+def _golden_train_step(model_ctor, npz, shape, dev):
+    """One train-mode step of the product on the GPU (fused forward kernels, hand-written / recompute backwards)
+    against loss and per-parameter gradients of the reference model (tests/golden/make_golden_r2.py)."""
+    import os
+    import numpy as np
+    from oracle import camliraft_oracle as co
+    from tests._util import GOLDEN
+    from tests.test_train_golden import compare_with_golden, train_targets
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    G = np.load(os.path.join(GOLDEN, npz))
+    H, W, N, B, seed, tseed = shape
+    inputs = dict(co.synthetic_inputs(B, H, W, N, seed), **train_targets(B, H, W, N, tseed))
+    inputs = {k: v.to(dev) for k, v in inputs.items()}
+    model = model_ctor().to(dev).train()
+    model(inputs)
+    model.loss.backward()
+    # loss: fp32 reassociation only.  Gradients: a neighbour that flips in one of the searches on a predicted
+    # (flow-warped) cloud changes a handful of rows, so the norms carry a little more than rounding
+    worst = compare_with_golden(model, G, "small", loss_rtol=2e-4, norm_rtol=2e-2, sample_tol=5e-2)
+    print("%s train step on GPU vs reference golden: loss %.6f (ref %.6f), worst grad-norm diff %.2e at %s"
+          % ((npz, float(model.loss.detach()), float(G["small_loss"])) + worst))
+    return model
+
+
+def test_camliraft_training_step_vs_reference_golden(dev):
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.init import seed_module_
+    model = _golden_train_step(lambda: seed_module_(CamLiRAFT(camliraft_config(n_iters_train=3)), seed=0),
+                               "train_camliraft.npz", (160, 224, 8192, 2, 17, 18), dev)
+    m = model.get_metrics()
+    assert {"loss", "loss2d", "loss3d", "epe2d", "acc2d_1px", "outlier2d", "epe3d", "acc3d_5cm"} <= set(m)
+
+
+def test_camlipwc_training_step_vs_reference_golden(dev):
+    from camliflow_b200.camlipwc import CamLiPWC
+    from camliflow_b200.config import camlipwc_config
+    from camliflow_b200.init import seed_module_
+    _golden_train_step(lambda: seed_module_(CamLiPWC(camlipwc_config()), seed=0),
+                       "train_camlipwc.npz", (128, 192, 8192, 2, 21, 22), dev)

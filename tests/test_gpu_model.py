@@ -75,6 +75,25 @@ def test_c2_vs_reference_golden():
     assert e2 <= TOL_EPE2D and e3 <= TOL_EPE3D, (e2, e3)
 
 
+def test_c4_32_iterations_batch4_vs_reference_golden():
+    """BASELINE config[3], one GPU's shard: 4 frame pairs, 32 GRU iterations, 960x540 + 8192 points, against the
+    reference model run on the same batch (tests/golden/make_golden_r2.py c4).  The error of a neighbour / pixel
+    decision that flips deep in the recurrence compounds per iteration, so this is the
+    case with the least margin."""
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    G = np.load(os.path.join(GOLDEN, "model_camliraft_c4.npz"))
+    inputs = co.synthetic_inputs(4, 540, 960, 8192, seed=4)
+    f2, f3 = _run(_model(32), inputs)
+    e2s = [epe(f2[b, :, ::8, ::8].numpy(), G["flow2d"][b]) for b in range(4)]
+    e3s = [epe(f3[b, :, ::4].numpy(), G["flow3d"][b]) for b in range(4)]
+    mag2 = float(np.sqrt((G["flow2d"] ** 2).sum(1)).mean())
+    mag3 = float(np.sqrt((G["flow3d"] ** 2).sum(1)).mean())
+    print("c4 (32 iters, batch 4) vs reference golden: EPE2D %s EPE3D %s (mean |flow| %.2f px / %.3f m)"
+          % (["%.2e" % e for e in e2s], ["%.2e" % e for e in e3s], mag2, mag3))
+    assert max(e2s) <= TOL_EPE2D and max(e3s) <= TOL_EPE3D, (e2s, e3s)
+
+
 def test_engine_graph_matches_eager():
     """The CUDA-graph engine (public end-to-end call, host tensors in/out) returns what the
     eager module returns."""
