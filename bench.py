@@ -7,11 +7,18 @@
 One process per GPU (torchrun for N>1); the batch of frame pairs is sharded over the ranks
 with no data-path collective ("scaling": "weak").  Prints ONE JSON line on rank 0.
 
-* value        : pairs/s with the inputs resident in HBM (device-timed, CUDA events, max over ranks)
-* e2e          : the same end to end from HOST tensors (pinned H2D + forward + D2H for every pair) through the public
-                 throughput API: EnginePool.pipelined (3 batch-1 CUDA graphs in flight over shared weights); the
-                 single-engine pipelined and the blocking call-per-pair figures are reported beside it
-* roofline     : the dominant hand-written kernel, timed per launch with CUDA events on its stream
+A "step" streams `--pairs-per-step` (default 8) independent frame pairs through the engine(s); every forward is a
+batch-1 CUDA graph (BASELINE config 2), so a default run times >= 160 pairs (>= 1.5 s) instead of a fraction of a second.
+
+* value        : pairs/s with the inputs resident in HBM (device-timed, CUDA events, max over ranks), throughput mode:
+                 3 batch-1 graphs in flight over shared weights (EnginePool)
+* latency      : one graph at a time: ms per frame pair (L2 flushed before every pair) -- the batch-1 latency
+* e2e          : throughput end to end from HOST tensors (pinned H2D + forward + D2H for every pair) through the public
+                 API EnginePool.pipelined; the single-engine pipelined and the blocking call-per-pair figures beside it
+* roofline     : the hand-written kernel with the largest share of the step, timed per launch with CUDA events on its
+                 stream (live); `traffic` from the committed ncu capture under profiles/ when it matches the workload
+* training     : BASELINE config 5 in the same run (a few steps): fwd + losses + bwd + DDP gradient all-reduce over
+                 NCCL + AdamW, so the one collective of this project is on the driver's clock at every N
 * cpu_baseline : the reference algorithm's CPU path (oracle port, fallback index semantics)
                  timed on this host's cores on a bounded sample (rank 0, N=1 only)
 * --impl reference : only the CPU path (the reference cannot travel to the GPU box; its
@@ -31,9 +38,11 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (H, W, N points, GRU iterations, pairs per GPU)
+    # name: (H, W, N points, GRU iterations, pairs per forward on one GPU)
     "c2": (540, 960, 8192, 12, 1),
     "small": (160, 224, 8192, 3, 1),
+    # BASELINE config 3 (`--workload c3`): CamLiPWC (5-level PWC cost volume), batch 4
+    "c3": (540, 960, 8192, 0, 4),
     # BASELINE config 4 (`--workload c4`): 32 iterations, 32 pairs over 8 GPUs = 4 pairs per GPU
     "c4": (540, 960, 8192, 32, 4),
     # BASELINE config 5 (secondary; `--workload c5`): training step, n_iters_train = 10, 2 pairs per GPU
@@ -42,6 +51,29 @@ WORKLOADS = {
 }
 TRAIN_WORKLOADS = ("c5", "c5small")
 METRIC = "CamLiRAFT frame-pairs/sec 960x540+8192pts"
+
+
+def workload_name(workload):
+    """The `config.workload` string -- identical in both arms (ours / --impl reference)."""
+    H, W, N, iters, B = WORKLOADS[workload]
+    if workload == "c3":
+        return "c3: CamLiPWC fusion %dx%d RGB + %d pts, batch %d per forward" % (W, H, N, B)
+    if workload in TRAIN_WORKLOADS:
+        return "%s: CamLiRAFT training step (fwd + sequence losses + bwd + AdamW) %dx%d RGB + %d pts, %d iters, batch %d per GPU" \
+            % (workload, W, H, N, iters, B)
+    return "%s: CamLiRAFT fusion %dx%d RGB + %d pts, %d iters, batch %d per forward" % (workload, W, H, N, iters, B)
+
+
+def build_model(workload):
+    from camliflow_b200.init import seed_module_
+    iters = WORKLOADS[workload][3]
+    if workload == "c3":
+        from camliflow_b200.camlipwc import CamLiPWC
+        from camliflow_b200.config import camlipwc_config
+        return seed_module_(CamLiPWC(camlipwc_config()), seed=0)
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    return seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=iters, n_iters_train=iters)), seed=0)
 
 
 def synthetic_inputs(B, H, W, N, seed):
@@ -94,11 +126,14 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------- CPU path
 def run_cpu_reference(workload, steps, warmup, seed=0):
-    """Times the reference algorithm's CPU path: oracle port, torch fallbacks for FPS / k-NN
-    (what models/csrc/wrapper.py does for CPU tensors), all host threads, eval mode, every
-    iteration's prediction materialised like the reference."""
+    """Times the reference algorithm's CPU path: oracle port, torch fallbacks for FPS / k-NN (what
+    models/csrc/wrapper.py does for CPU tensors), all host threads, eval mode.  Like our arm it materialises the
+    final prediction only (the reference also up-samples the 11 intermediate ones, which nothing reads at
+    inference: leaving that out favours the baseline, so the ratio is like for like)."""
     from oracle import camliraft_oracle as co
     H, W, N, iters, B = WORKLOADS[workload]
+    if workload == "c3":
+        return None            # no CPU restatement of CamLiPWC is kept (the C2 metric is the headline)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     P = co.make_params(co.param_spec("camliraft"), seed=0)
@@ -107,12 +142,12 @@ def run_cpu_reference(workload, steps, warmup, seed=0):
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         co.camliraft_forward(P, inp["images"], inp["pcs"], inp["intrinsics"], n_iters=iters, index_impl="fallback",
-                             all_iters=True)
+                             all_iters=False)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return {"value": B / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": "%d full forward(s) of %d pair(s), %dx%d + %d pts, %d iters, after %d warm-up"
+            "sample": "%d full forward(s) of %d pair(s), %dx%d + %d pts, %d iters, final prediction only, after %d warm-up"
                       % (steps, B, W, H, N, iters, warmup), "sec_per_step": sec}
 
 
@@ -137,26 +172,90 @@ def max_over_ranks(ms, world, device=None):
     return float(t.item())
 
 
-def pairs_per_step(B, world):
-    return B * world
+def pairs_per_step(B, world, forwards=1):
+    return B * world * forwards
+
+
+TENSOR_KERNELS = ("camli_conv_gemm_fused", "camli_conv_gemm", "camli_allpairs_correlation")
+NAMED_HBM_KERNELS = (("camli_corr2d_lookup", "corr_lookup"), ("camli_pointconv_dw_gather_max", "knn_gather"))
+
+
+def committed_ncu(workload):
+    """Per-kernel ncu figures (duration, DRAM bytes) from the newest committed profiles/r*_kernels.json whose
+    `workload` field matches, or {} -- never constants in code."""
+    import glob
+    best = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json"))):
+        try:
+            doc = json.load(open(path))
+        except (OSError, ValueError):
+            continue
+        if doc.get("workload") == workload:
+            best = dict(doc.get("kernels", {}), source=os.path.relpath(path, ROOT), commit=doc.get("commit"))
+    return best
+
+
+def roofline_block(prof, workload):
+    """Roofline record of the hand-written kernel with the largest share of the profiled (eager) step, from live
+    CUDA-event timings.  Tensor-core kernels (3xTF32 implicit GEMM): achieved = ISSUED tf32 flops (3 products per
+    fp32 product) per launch / duration against the tf32 dense peak (half the measured bf16 peak: same tensor
+    pipe, K = 8 instead of 16 per instruction); the fp32-equivalent rate is beside it.  HBM-bound kernels:
+    algorithmic bytes per launch / duration against the measured copy bandwidth."""
+    if not prof:
+        return None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm, bf16, src = 6650.0, 1590.0, "fallback"
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        hbm, bf16, src = float(peaks["hbm_gbs"]), float(peaks.get("bf16_tflops", 1590.0)), "measured"
+    ncu = committed_ncu(workload)
+    per = {n: {"avg_us": r["avg_us"], "launches": r["launches"], "total_us": r["total_us"],
+               "GBps": r["bytes"] / (r["avg_us"] * 1e-6) / 1e9, "GFLOPs": r["flops"] / (r["avg_us"] * 1e-6) / 1e9}
+           for n, r in prof.items()}
+    total = sum(r["total_us"] for r in prof.values())
+    top = max(prof, key=lambda n: prof[n]["total_us"])
+    rec = prof[top]
+    if top in TENSOR_KERNELS:
+        fp32_eq = rec["flops"] / (rec["avg_us"] * 1e-6) / 1e12
+        out = {"kernel": top, "bound": "tensor", "achieved": 3.0 * fp32_eq, "peak": bf16 / 2.0,
+               "peak_source": src + " dense bf16 / 2 (tf32 runs at half the bf16 rate)", "unit": "TFLOP/s",
+               "frac": 3.0 * fp32_eq / (bf16 / 2.0), "fp32_equivalent_TFLOPs": fp32_eq,
+               "note": "achieved = issued tf32 flops: 3 tf32 products per fp32 product (3xTF32); averaged over every launch "
+                       "of the step, from 16-CTA linear layers to 3x3 convolutions",
+               "algorithmic_flops_per_launch": rec["flops"]}
+    else:
+        achieved = rec["bytes"] / (rec["avg_us"] * 1e-6) / 1e9
+        out = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "peak_source": src, "unit": "GB/s",
+               "frac": achieved / hbm, "algorithmic_bytes_per_launch": rec["bytes"]}
+    k = ncu.get(top)
+    out.update({"traffic": k.get("dram_bytes") if k else None, "traffic_source": ncu.get("source") if k else None,
+                "avg_us": rec["avg_us"], "launches": rec["launches"], "share_of_step": rec["total_us"] / total, "all": per})
+    # the two HBM-bound kernels the north star names: live CUDA-event figures of this run (cold launches of an eager
+    # pass, launch overhead included) and, when a committed ncu capture of this workload exists, its figures
+    for name, key in NAMED_HBM_KERNELS:
+        if name in per:
+            out[key] = {"achieved_GBps": per[name]["GBps"], "frac_of_hbm_peak": per[name]["GBps"] / hbm,
+                        "avg_us": per[name]["avg_us"], "launches": per[name]["launches"]}
+            k = ncu.get(name)
+            if k:
+                out[key]["ncu"] = dict(k, source=ncu.get("source"), commit=ncu.get("commit"))
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from camliflow_b200 import native, ops
-    from camliflow_b200.camliraft import CamLiRAFT
-    from camliflow_b200.config import camliraft_config
-    from camliflow_b200.engine import FlowEngine
-    from camliflow_b200.init import seed_module_
+    from camliflow_b200 import ops
+    from camliflow_b200.engine import EnginePool, FlowEngine
 
     H, W, N, iters, B = WORKLOADS[args.workload]
+    R = args.pairs_per_step                        # forwards per step
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
     strict = args.conv_precision == "fp32"
     torch.backends.cudnn.allow_tf32 = not strict
     torch.backends.cuda.matmul.allow_tf32 = False      # GEMMs (1x1 layers, Linear) are always fp32
-    model = seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=iters)), seed=0)
+    model = build_model(args.workload)
     engine = FlowEngine(model, B, H, W, N, device=dev, use_graph=not args.no_graph)
     inputs = synthetic_inputs(B, H, W, N, seed=shard_seed(rank))   # per-rank shard of the batch of pairs
     pinned = {k: v.pin_memory() for k, v in inputs.items()}
@@ -167,13 +266,14 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
+    def timed(fn, n, warm):
+        """n forwards, one CUDA-event pair around each (L2 flushed before, outside the pair); returns total ms."""
+        for _ in range(warm):
             fn()
         barrier()
         evs = []
         with torch.cuda.stream(engine.stream):
-            for _ in range(steps):
+            for _ in range(n):
                 l2_flush(flush)
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record(engine.stream)
@@ -189,37 +289,37 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     if os.environ.get("CAMLI_PROFILER_RANGE"):       # ncu --profile-from-start off: capture the timed steps only
         torch.cuda.profiler.start()
-    ms_dev = timed(engine.step, args.steps, args.warmup)
+    n_lat = max(args.steps, 10)
+    ms_lat = timed(engine.step, n_lat, args.warmup)                      # one graph at a time: latency of a pair
     if os.environ.get("CAMLI_PROFILER_RANGE"):
         torch.cuda.profiler.stop()
-    ms_e2e = timed(lambda: engine(pinned), args.steps, args.warmup)
+    ms_sync = timed(lambda: engine(pinned), n_lat, args.warmup)          # blocking public call per pair
 
-    # the same end-to-end call in throughput mode: H2D of pair i+1 and D2H of pair i-1 overlap the compute of pair i
-    # (every pair still pays both transfers; wall clock on the host around K pairs, barrier + synchronize both sides)
+    n_fwd, n_warm = args.steps * R, args.warmup * R
+
+    # single-engine throughput mode: H2D of pair i+1 and D2H of pair i-1 overlap the compute of pair i
     def piped(n):
         for out in engine.pipelined(pinned for _ in range(n)):
             pass
-    piped(args.warmup)
+    piped(n_warm)
     barrier()
     t0 = time.perf_counter()
-    piped(args.steps)
+    piped(n_fwd)
     barrier()
     ms_pipe = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
 
-    # serving-style concurrency: two engines (two CUDA graphs over the same weights) fed round-robin, so the
+    # serving-style concurrency: several engines (CUDA graphs over the same weights) fed round-robin, so the
     # latency-bound phases of one pair overlap another pair's work; every forward is still batch B
-    conc = None
-    if args.concurrent > 1:
-        from camliflow_b200.engine import EnginePool
-        pool = EnginePool(model, args.concurrent, B, H, W, N, device=dev, use_graph=not args.no_graph)
-
+    n_eng = max(1, args.concurrent)
+    pool = EnginePool(model, n_eng, B, H, W, N, device=dev, use_graph=not args.no_graph) if n_eng > 1 else None
+    if pool is not None:
         def pooled(n):
             for out in pool.pipelined(pinned for _ in range(n)):
                 pass
-        pooled(args.warmup + args.concurrent)
+        pooled(n_warm + n_eng)
         barrier()
         t0 = time.perf_counter()
-        pooled(args.steps)
+        pooled(n_fwd)
         barrier()
         ms_pool = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
         # the same pool with the inputs resident in HBM (no host traffic), device-timed: one start event every engine
@@ -234,25 +334,26 @@ def run_ours(args, rank, world, local_rank):
                 for eng in pool.engines:
                     eng.stream.wait_event(timed_pair[0])
             for i in range(n):
-                pool.engines[i % args.concurrent].step()
+                pool.engines[i % n_eng].step()
             for eng in pool.engines:
                 ctl.wait_stream(eng.stream)
             if timed_pair is not None:
                 timed_pair[1].record(ctl)
-        resident(args.warmup)
+        resident(n_warm)
         barrier()
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        resident(args.steps, ev)
+        resident(n_fwd, ev)
         barrier()
-        ms_pool_dev = max_over_ranks(ev[0].elapsed_time(ev[1]), world, dev)
-        conc = {"value": pairs_per_step(B, world) * args.steps / (ms_pool / 1e3), "unit": "pairs/s", "ms_per_step": ms_pool / args.steps,
-                "engines": args.concurrent,
-                "mode": "EnginePool.pipelined: %d CUDA graphs of batch %d in flight, round-robin; each pair pays its own pinned "
-                        "H2D + D2H (host wall clock)" % (args.concurrent, B)}
+        ms_dev = max_over_ranks(ev[0].elapsed_time(ev[1]), world, dev)
+        ms_e2e, e2e_mode = ms_pool, ("EnginePool.pipelined: %d CUDA graphs of batch %d in flight, round-robin; each pair pays its "
+                                     "own pinned H2D + D2H (host wall clock)" % (n_eng, B))
+    else:
+        ms_dev = ms_lat / n_lat * n_fwd
+        ms_e2e, e2e_mode = ms_pipe, "FlowEngine.pipelined: pinned H2D of pair i+1 and D2H of pair i-1 overlap the forward of pair i"
 
     clocks = sampler.stop() if rank == 0 else None      # sampled over every timed region above
 
-    # per-launch timing of the dominant hand-written kernel (eager pass, events on the launch stream)
+    # per-launch timing of every hand-written kernel (eager pass, events on the launch stream)
     roofline = None
     if rank == 0:
         ops.profile_begin()
@@ -261,71 +362,56 @@ def run_ours(args, rank, world, local_rank):
                 l2_flush(flush)
                 engine._forward_static()
         engine.stream.synchronize()
-        roofline = ops.profile_end(peaks_path=os.path.join(ROOT, "MEASURED_PEAKS.json"))
+        roofline = roofline_block(ops.profile_end(), args.workload)
 
     h2d, d2h = engine.io_bytes()
-    pairs = B * world
+    pairs = pairs_per_step(B, world, R)              # frame pairs per step over all ranks
+    all_pairs = pairs * args.steps
     line = {
-        "metric": METRIC, "value": pairs * args.steps / (ms_dev / 1e3), "unit": "pairs/s", "n_gpus": world,
+        "metric": METRIC if args.workload != "c3" else "CamLiPWC frame-pairs/sec 960x540+8192pts",
+        "value": all_pairs / (ms_dev / 1e3), "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: CamLiRAFT fusion %dx%d RGB + %d pts, %d iters, batch %d per GPU"
-                               % (args.workload, W, H, N, iters, B),
-                   "pairs_per_step": pairs, "cuda_graph": engine.graph is not None,
-                   "l2": "192 MiB flush write before every timed step of `value` (outside the event pair); e2e: inputs re-copied "
-                         "every step and a per-step working set (355 MB volume pyramid + activations) larger than L2",
+        "config": {"workload": workload_name(args.workload), "pairs_per_step": pairs, "forwards_per_step_per_gpu": R,
+                   "engines_in_flight": n_eng, "cuda_graph": engine.graph is not None,
+                   "l2": "value / e2e: %d CUDA graphs in flight, per-engine working set (355 MB volume pyramid + activations) "
+                         "larger than L2, e2e inputs re-copied for every pair; latency: 192 MiB flush write before every "
+                         "timed pair (outside the event pair)" % n_eng,
                    "conv_precision": ("fp32 (cudnn.allow_tf32=False: the mode the parity tests run in)" if strict else
                                       "cuDNN default (TF32 allowed, as torch default in the reference)"),
                    "intermediate_predictions": False},
-        # headline: the public end-to-end call in throughput mode (FlowEngine.pipelined): every pair pays its pinned
-        # H2D and its D2H inside the timed region, overlapped with the compute of the neighbouring pairs; host wall
-        # clock.  `synchronous` = one blocking FlowEngine.__call__ per pair (latency mode), CUDA-event timed.
-        "e2e": {"value": pairs * args.steps / (ms_pipe / 1e3), "unit": "pairs/s", "ms_per_step": ms_pipe / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "mode": "FlowEngine.pipelined: pinned H2D of pair i+1 and D2H of pair i-1 overlap the forward of pair i",
-                "synchronous": {"value": pairs * args.steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+        # batch-1 latency (BASELINE config 2 is batch 1): one CUDA graph at a time
+        "latency": {"ms_per_pair": ms_lat / n_lat / B, "pairs_per_s": B * world * n_lat / (ms_lat / 1e3), "pairs_timed": n_lat * B,
+                    "note": "one CUDA graph at a time, device-timed per pair, L2 flushed before each"},
+        "e2e": {"value": all_pairs / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d * R, "d2h_bytes_per_step": d2h * R, "mode": e2e_mode, "engines_in_flight": n_eng,
+                "single_engine_pipelined": {"value": all_pairs / (ms_pipe / 1e3), "unit": "pairs/s",
+                                            "mode": "FlowEngine.pipelined: pinned H2D of pair i+1 and D2H of pair i-1 overlap "
+                                                    "the forward of pair i"},
+                "synchronous": {"value": B * world * n_lat / (ms_sync / 1e3), "unit": "pairs/s", "ms_per_pair": ms_sync / n_lat / B,
                                 "mode": "FlowEngine.__call__ per pair: pinned H2D -> forward -> D2H -> host sync"}},
-        "gpu_launches": engine.launches_per_step * args.steps,
+        "gpu_launches": engine.launches_per_step * R * args.steps,
         "clocks": clocks, "roofline": roofline,
     }
-    if conc is not None:
-        # `value`: the same pool with resident inputs, CUDA-event timed; the single-engine (one pair at a time) figure,
-        # whose ms_per_step is the latency of a pair, stays beside it
-        line["single_engine"] = {"value": line["value"], "unit": "pairs/s", "ms_per_step": line["ms_per_step"],
-                                 "note": "one CUDA graph at a time: ms_per_step is the latency of a frame pair"}
-        line["value"] = pairs * args.steps / (ms_pool_dev / 1e3)
-        line["ms_per_step"] = ms_pool_dev / args.steps
-        line["config"]["engines_in_flight"] = args.concurrent
-        line["config"]["l2"] = ("value / e2e: %d CUDA graphs in flight, per-engine working set 355 MB volume pyramid + activations "
-                                "(larger than L2), inputs re-copied every step for e2e; single_engine: 192 MiB flush write "
-                                "before every timed step (outside the event pair)" % args.concurrent)
-        # headline end-to-end throughput: the serving-style pool (every forward still a batch-B graph, every pair pays its
-        # own transfers); the single-engine pipelined and synchronous figures stay beside it
-        single = {k: line["e2e"][k] for k in ("value", "unit", "ms_per_step", "mode")}
-        line["e2e"].update({"value": conc["value"], "ms_per_step": conc["ms_per_step"], "mode": conc["mode"],
-                            "engines_in_flight": conc["engines"], "single_engine_pipelined": single})
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = run_cpu_reference(args.workload, steps=1, warmup=1)
     return line
 
 
-def run_train(args, rank, world, local_rank):
+def run_train(args, rank, world, local_rank, steps=None, warmup=None, workload=None):
     """Training step (forward with targets, sequence losses, backward through the fused operators' backward
     kernels, DDP gradient all-reduce over NCCL, AdamW step), timed like the inference workloads."""
     import torch.distributed as dist
     from camliflow_b200 import native, trainer
-    from camliflow_b200.camliraft import CamLiRAFT
-    from camliflow_b200.config import camliraft_config
-    from camliflow_b200.init import seed_module_
 
-    H, W, N, iters, B = WORKLOADS[args.workload]
+    workload = workload or args.workload
+    steps, warmup = steps or args.steps, warmup or args.warmup
+    H, W, N, iters, B = WORKLOADS[workload]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
-    strict = args.conv_precision == "fp32"
-    torch.backends.cudnn.allow_tf32 = not strict
-    torch.backends.cuda.matmul.allow_tf32 = not strict
-    model = seed_module_(CamLiRAFT(camliraft_config(n_iters_train=iters)), seed=0).to(dev).train()
+    precision = args.train_precision
+    torch.backends.cudnn.allow_tf32 = precision != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = precision != "fp32"
+    model = build_model(workload).to(dev).train()
     ddp = trainer.wrap_ddp(model, dev)
     opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, weight_decay=1e-6)
     inputs = synthetic_inputs(B, H, W, N, seed=shard_seed(rank))
@@ -334,19 +420,20 @@ def run_train(args, rank, world, local_rank):
     inputs["flow_3d"] = torch.randn(B, 3, N, generator=g) * 0.1
     pinned = {k: v.pin_memory() for k, v in inputs.items()}
     dev_in = {k: v.to(dev) for k, v in inputs.items()}
+    amp = torch.bfloat16 if precision == "bf16" else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
+    def timed(fn, n, warm):
+        for _ in range(warm):
             fn()
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         e.record()
         barrier()
@@ -355,35 +442,36 @@ def run_train(args, rank, world, local_rank):
     losses = []
 
     def step_resident():
-        losses.append(trainer.train_step(ddp, opt, dev_in))
+        losses.append(trainer.train_step(ddp, opt, dev_in, max_grad_norm=1.0, autocast_dtype=amp))
 
     def step_e2e():
         batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        losses.append(float(trainer.train_step(ddp, opt, batch)))            # D2H read of the loss
+        losses.append(float(trainer.train_step(ddp, opt, batch, max_grad_norm=1.0, autocast_dtype=amp)))   # D2H read of the loss
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     c0 = native.launch_count()
-    ms_dev = timed(step_resident, args.steps, args.warmup)
-    launches = (native.launch_count() - c0) // (args.steps + args.warmup)
+    ms_dev = timed(step_resident, steps, warmup)
+    launches = (native.launch_count() - c0) // (steps + warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, steps, warmup)
     pairs = B * world
+    grad_bytes = sum(p.numel() for p in model.parameters() if p.requires_grad) * 4
     return {
-        "metric": "CamLiRAFT training frame-pairs/sec 960x540+8192pts", "value": pairs * args.steps / (ms_dev / 1e3),
-        "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: CamLiRAFT training step (fwd + sequence losses + bwd + AdamW) %dx%d RGB + %d pts, "
-                               "%d iters, batch %d per GPU" % (args.workload, W, H, N, iters, B),
-                   "pairs_per_step": pairs, "parallelism": "dp%d (DDP gradient all-reduce over NCCL)" % world,
+        "metric": "CamLiRAFT training frame-pairs/sec 960x540+8192pts", "value": pairs * steps / (ms_dev / 1e3),
+        "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16": "bf16 autocast (fp32 islands as in the reference: fused point / correlation operators, losses)",
+                  "tf32": "f32 (tf32 library layers)", "fp32": "f32"}[precision], "data": "synthetic",
+        "config": {"workload": workload_name(workload), "pairs_per_step": pairs,
+                   "parallelism": "dp%d (DDP gradient all-reduce over NCCL, %.1f MB fp32 per step, bucketed, overlapped with the "
+                                  "backward)" % (world, grad_bytes / 1e6),
                    "l2": "working set (activations of %d iterations) larger than L2" % iters,
-                   "conv_precision": ("fp32 (strict)" if strict else "tf32 for the cuDNN / cuBLAS layers of the autograd path (torch's "
-                                      "default, what the reference trains with); the fused operators stay fp32"),
-                   "final_loss": float(losses[-1])},
-        "e2e": {"value": pairs * args.steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                   "precision": precision, "grad_clip": 1.0, "final_loss": float(losses[-1])},
+        "e2e": {"value": pairs * steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": sum(v.numel() * 4 for v in pinned.values()), "d2h_bytes_per_step": 4},
-        "gpu_launches": launches * args.steps, "clocks": clocks,
+        "gpu_launches": launches * steps, "clocks": clocks,
     }
 
 
@@ -394,18 +482,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--conv-precision", default=None, choices=["fp32", "tf32"],
-                    help="library (cuDNN / cuBLAS) convolution precision.  fp32: strict fp32, the mode the EPE parity tests "
-                         "run in (default for the inference workloads); tf32: torch's default (allow_tf32=True), what the "
-                         "reference trains with out of the box (default for the training workloads c5*)")
+    ap.add_argument("--pairs-per-step", type=int, default=8,
+                    help="forwards (of the workload's batch) streamed through the engines per step")
+    ap.add_argument("--conv-precision", default="fp32", choices=["fp32", "tf32"],
+                    help="library (cuDNN) convolution precision of the inference workloads.  fp32: strict fp32, the mode the "
+                         "EPE parity tests run in; tf32: torch's default (fails the EPE bar, kept for A/B only)")
+    ap.add_argument("--train-precision", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="training workloads: bf16 autocast (BASELINE config 5), tf32 library layers (torch default, what the "
+                         "reference trains with when amp is off) or strict fp32")
     ap.add_argument("--concurrent", type=int, default=3,
-                    help="engines (CUDA graphs of batch B) in flight for the end-to-end throughput figure e2e.value "
-                         "(EnginePool.pipelined); 1 = single engine (FlowEngine.pipelined)")
+                    help="engines (CUDA graphs of batch B) in flight for the throughput figures (EnginePool); 1 = single engine")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-training-block", action="store_true",
+                    help="skip the short BASELINE-config-5 training measurement appended to the default (c2) line")
     args = ap.parse_args()
-    if args.conv_precision is None:
-        args.conv_precision = "tf32" if args.workload in TRAIN_WORKLOADS else "fp32"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -414,15 +505,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        H, W, N, iters, B = WORKLOADS[args.workload]
         steps = max(1, min(args.steps, 8))
         base = run_cpu_reference(args.workload, steps=steps, warmup=min(args.warmup, 1))
+        if base is None:
+            print(json.dumps({"impl": "reference", "unavailable": "no CPU restatement of CamLiPWC (workload c3) is kept"}))
+            return
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: CamLiRAFT fusion %dx%d RGB + %d pts, %d iters, batch %d (CPU path)"
-                                   % (args.workload, W, H, N, iters, B)},
+            "config": {"workload": workload_name(args.workload), "pairs_per_step": WORKLOADS[args.workload][4],
+                       "note": "CPU path of the reference algorithm (oracle port), a step = one forward"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
@@ -431,7 +524,18 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    line = (run_train if args.workload in TRAIN_WORKLOADS else run_ours)(args, rank, world, local_rank)
+    if args.workload in TRAIN_WORKLOADS:
+        line = run_train(args, rank, world, local_rank)
+    else:
+        line = run_ours(args, rank, world, local_rank)
+        if args.workload == "c2" and not args.no_training_block:
+            # BASELINE config 5 in the same run: the gradient all-reduce is the only collective of this project
+            torch.cuda.empty_cache()
+            tr = run_train(args, rank, world, local_rank, steps=4, warmup=3, workload="c5")
+            line["training"] = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "dtype", "config",
+                                                   "e2e", "gpu_launches")}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = run_cpu_reference(args.workload, steps=1, warmup=1)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

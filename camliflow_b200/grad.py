@@ -139,13 +139,26 @@ def needs_grad(*tensors):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 
+def f32(*tensors):
+    """The fused operators are fp32 islands (the reference marks the same sites with explicit `.float()`
+    casts): under bf16 / fp16 autocast their floating-point inputs are brought back to fp32."""
+    out = tuple(t.float() if isinstance(t, torch.Tensor) and t.is_floating_point() and t.dtype != torch.float32 else t
+                for t in tensors)
+    return out[0] if len(out) == 1 else out
+
+
 class _Recompute(torch.autograd.Function):
     """forward: `kernel(*args)` under no_grad; backward: autograd through `formula(*args)` recomputed on
-    detached copies.  `args` may mix tensors and plain Python values; outputs: a tensor or a list of tensors."""
+    detached copies.  `args` may mix tensors and plain Python values; outputs: a tensor or a list of tensors.
+    Tensor arguments are kept through save_for_backward (so autograd's version check catches an in-place write
+    between forward and backward); everything else on the context."""
 
     @staticmethod
     def forward(ctx, kernel, formula, *args):
-        ctx.formula, ctx.args = formula, args
+        ctx.formula = formula
+        ctx.is_tensor = [isinstance(a, torch.Tensor) for a in args]
+        ctx.plain = [None if t else a for a, t in zip(args, ctx.is_tensor)]
+        ctx.save_for_backward(*[a for a, t in zip(args, ctx.is_tensor) if t])
         with torch.no_grad():
             out = kernel(*args)
         ctx.multi = isinstance(out, (list, tuple))
@@ -154,14 +167,16 @@ class _Recompute(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         needs = ctx.needs_input_grad[2:]
+        saved = iter(ctx.saved_tensors)
         args = []
-        for a, n in zip(ctx.args, needs):
-            if isinstance(a, torch.Tensor):
-                a = a.detach()
+        for plain, is_t, n in zip(ctx.plain, ctx.is_tensor, needs):
+            a = plain
+            if is_t:
+                a = next(saved).detach()
                 if n:
                     a.requires_grad_(True)
             args.append(a)
-        with torch.enable_grad():
+        with torch.enable_grad(), torch.autocast("cuda", enabled=False):
             out = ctx.formula(*args)
         outs = list(out) if isinstance(out, (list, tuple)) else [out]
         pairs = [(o, g) for o, g in zip(outs, gouts) if g is not None and o.requires_grad]
@@ -173,8 +188,10 @@ class _Recompute(torch.autograd.Function):
 
 def recompute(kernel, formula, *args):
     """Run `kernel(*args)`; when a tensor argument requires grad, make the call differentiable through
-    `formula` (see the module docstring)."""
+    `formula` (see the module docstring).  fp32 island: autocast is off inside, low-precision inputs are cast up."""
+    args = tuple(f32(a) if isinstance(a, torch.Tensor) else a for a in args)
     if not needs_grad(*args):
         return kernel(*args)
-    out = _Recompute.apply(kernel, formula, *args)
+    with torch.autocast("cuda", enabled=False):
+        out = _Recompute.apply(kernel, formula, *args)
     return list(out) if isinstance(out, tuple) else out

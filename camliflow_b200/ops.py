@@ -75,6 +75,7 @@ def gather_points(data, idx):
 def knn_interpolate(input_xyz, input_feat, query_xyz, k=3):
     """Three-NN inverse-distance interpolation fused with the search (models/utils.py:130-146).
     input_xyz [B,3,m], input_feat [B,F,m], query_xyz [B,3,n] -> [B,F,n]."""
+    input_xyz, input_feat, query_xyz = grad.f32(input_xyz, input_feat, query_xyz)
     _need_cuda(input_xyz, input_feat, query_xyz)
     return grad.recompute(_knn_interpolate, grad.f_knn_interpolate, input_xyz, input_feat, query_xyz, k)
 
@@ -113,6 +114,7 @@ def backwarp_3d(xyz1, xyz2, flow12, k=3):
 def bilinear_sample_rows(feat2d, uv):
     """feat2d [B,C,H,W] (channels_last preferred), uv [B,2,N] pixel coords -> rows [B,N,C]
     (align_corners, zero padding; models/utils.py:262-269)."""
+    feat2d, uv = grad.f32(feat2d, uv)
     _need_cuda(feat2d, uv)
     return grad.recompute(_bilinear_sample_rows, grad.f_bilinear_sample_rows, feat2d, uv)
 
@@ -152,9 +154,11 @@ ALLPAIRS_IMPL = os.environ.get("CAMLI_ALLPAIRS", "tcgen05")
 
 def allpairs(a_rows, b_rows, scale):
     """out[b,m,n] = scale * <a_rows[b,m,:], b_rows[b,n,:]>: a_rows [B,M,K], b_rows [B,N,K] -> [B,M,N]."""
+    a_rows, b_rows = grad.f32(a_rows, b_rows)
     _need_cuda(a_rows, b_rows)
     if grad.needs_grad(a_rows, b_rows):
-        return _AllPairs.apply(a_rows, b_rows, scale)
+        with torch.autocast("cuda", enabled=False):
+            return _AllPairs.apply(a_rows, b_rows, scale)
     return _allpairs(a_rows, b_rows, scale)
 
 
@@ -327,6 +331,7 @@ def corr2d_build(fmap1, fmap2, num_levels):
     """All-pairs volume of two [B,C,H,W] maps scaled by 1/sqrt(C) and its 2x2 average-pooled pyramid
     (models/raft_core.py:56-68).  Returns [B,H*W,h_l,w_l] per level; the coarser levels come from one
     fused pass over level 0."""
+    fmap1, fmap2 = grad.f32(fmap1, fmap2)
     _need_cuda(fmap1, fmap2)
     B, C, H, W = fmap1.shape
     a = nhwc_rows(fmap1).view(B, H * W, C)
@@ -353,9 +358,11 @@ def _corr2d_pool(vol, num_levels):
 def corr2d_lookup(pyramid, coords, radius, channels_last=True):
     """models/raft_core.py:71-107: coords [B,2,H,W] -> logical [B, L*(2r+1)^2, H, W] (NHWC storage when
     channels_last); window index i moves x, j moves y (the reference's meshgrid quirk)."""
+    coords, pyramid = grad.f32(coords), [grad.f32(v) for v in pyramid]
     _need_cuda(coords, *pyramid)
     if grad.needs_grad(coords, *pyramid):
-        return _Corr2dLookup.apply(coords, radius, channels_last, *pyramid)
+        with torch.autocast("cuda", enabled=False):
+            return _Corr2dLookup.apply(coords, radius, channels_last, *pyramid)
     return _corr2d_lookup(pyramid, coords, radius, channels_last)
 
 
@@ -436,6 +443,7 @@ def _corr3d_pool(vol, idx):
 def corr3d_lookup_rows(xyz1, xyzs2, pyramid, W1, b1, W2, b2):
     """Correlation3D.forward before `merge` (models/camliraft_l_core.py:62-98), every level in one
     launch: rows [B,n1,32*L]."""
+    xyz1, xyzs2, pyramid = grad.f32(xyz1), [grad.f32(x) for x in xyzs2], [grad.f32(v) for v in pyramid]
     _need_cuda(xyz1, *xyzs2, *pyramid)
     L = len(pyramid)
     return grad.recompute(_corr3d_lookup_rows, grad.f_corr3d_lookup_rows, xyz1, W1, b1, W2, b2, 16, L, *xyzs2, *pyramid)
@@ -514,9 +522,11 @@ def _pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, *params):
 def pointconv_dw_gather_max(feat_rows, weights, knn_idx, k):
     """out[b,s,o] = max_j feat_rows[b, idx[b,s,j], o] * weights[b,s,j,o] (models/point_conv.py:126-128):
     feat_rows [B,N,O], weights [B,S,k,O], knn_idx [B,S,K>=k] -> rows [B,S,O]."""
+    feat_rows, weights = grad.f32(feat_rows, weights)
     _need_cuda(feat_rows, weights, knn_idx)
     if grad.needs_grad(feat_rows, weights):
-        return _DwGatherMax.apply(feat_rows, weights, knn_idx, k)
+        with torch.autocast("cuda", enabled=False):
+            return _DwGatherMax.apply(feat_rows, weights, knn_idx, k)
     return _pointconv_dw_gather_max(feat_rows, weights, knn_idx, k)
 
 
@@ -563,6 +573,7 @@ def pointconv_group(rows, sampled_xyz, knn_idx, k, weight_net, negative_slope):
     """PointConv grouping (models/point_conv.py:56-66): rows [B,N,3+C] = [xyz | features] channel-last,
     sampled_xyz [B,3,S], knn_idx [B,S,K>=k]; WeightNet(3->8->16) evaluated in-kernel.
     Returns [B,S,16*(3+C)] in the order the reference's Linear expects (weight-major)."""
+    rows, sampled_xyz = grad.f32(rows, sampled_xyz)
     _need_cuda(rows, sampled_xyz, knn_idx)
     (w1, b1), (w2, b2) = weight_net.convs[0].folded(), weight_net.convs[1].folded()
     return grad.recompute(_pointconv_group, grad.f_pointconv_group, rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2,
@@ -598,6 +609,7 @@ def nearest_point_2d(uv, H, W):
 
 def clfm_interp(uv, nn_idx, feat3d_rows, score_net, H, W):
     """FusionAwareInterp before out_conv (models/clfm.py:57-75): logical [B,C,H,W], NHWC storage."""
+    uv, feat3d_rows = grad.f32(uv, feat3d_rows)
     _need_cuda(uv, nn_idx, feat3d_rows)
     (w1, b1), (w2, b2) = score_net[0].folded(), score_net[1].folded()
     return grad.recompute(_clfm_interp, grad.f_clfm_interp, uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W)
@@ -694,54 +706,11 @@ def gru_update_rows(z, h, q):
 
 # ---------------------------------------------------------------- per-launch profiling (bench.py)
 def profile_begin():
+    """Start bracketing every C-ABI launch with CUDA events on its stream (native.call)."""
     native.profile_begin()
 
 
-TENSOR_BOUND = ("camli_conv_gemm", "camli_allpairs_correlation")
-
-
-def profile_end(peaks_path=None):
-    """Roofline record of the hand-written kernel with the largest share of the profiled region.
-    HBM-bound kernels: achieved = algorithmic bytes per launch / average launch duration against the measured
-    copy bandwidth.  The tensor-core kernels (3xTF32 GEMM / implicit GEMM): achieved = algorithmic (fp32-
-    equivalent) flops per launch / duration against the measured dense bf16 peak -- tf32 runs at half the bf16
-    rate and 3xTF32 spends three tf32 products per fp32 product, so 1/6 of that peak is the scheme's ceiling."""
-    import json
-    import os
-    prof = native.profile_end()
-    if not prof:
-        return None
-    hbm, tflops, src = 6650.0, 1590.0, "fallback"
-    if peaks_path and os.path.exists(peaks_path):
-        peaks = json.load(open(peaks_path))
-        hbm, tflops, src = float(peaks["hbm_gbs"]), float(peaks.get("bf16_tflops", 1590.0)), "measured"
-    top = max(prof, key=lambda n: prof[n]["total_us"])
-    rec = prof[top]
-    per = {n: {"avg_us": r["avg_us"], "launches": r["launches"], "total_us": r["total_us"],
-               "GBps": r["bytes"] / (r["avg_us"] * 1e-6) / 1e9, "GFLOPs": r["flops"] / (r["avg_us"] * 1e-6) / 1e9}
-           for n, r in prof.items()}
-    if top in TENSOR_BOUND:
-        achieved = rec["flops"] / (rec["avg_us"] * 1e-6) / 1e12
-        out = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": tflops, "peak_source": src + " (dense bf16)",
-               "unit": "TFLOP/s", "frac": achieved / tflops,
-               "note": "fp32-equivalent flops of a 3xTF32 product; tf32 = 1/2 of the bf16 rate and 3 products per "
-                       "fp32 product, so frac 1/6 = 0.167 is the scheme's ceiling",
-               "algorithmic_flops_per_launch": rec["flops"]}
-    else:
-        achieved = rec["bytes"] / (rec["avg_us"] * 1e-6) / 1e9
-        out = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "peak_source": src, "unit": "GB/s",
-               "frac": achieved / hbm, "algorithmic_bytes_per_launch": rec["bytes"]}
-    out.update({"traffic": None, "avg_us": rec["avg_us"], "launches": rec["launches"], "all": per})
-    # the two HBM-bound kernels the north star names, always reported: live CUDA-event figures of this run (cold
-    # launches of an eager pass, launch overhead included) + the ncu capture committed under profiles/ (kernel-only
-    # duration and DRAM traffic at the C2 sizes: profiles/r1_v5_kernels.json)
-    ncu = {"camli_corr2d_lookup": {"ncu_us": 14.8, "ncu_dram_traffic_bytes": 37.4e6, "algorithmic_bytes": 23.7e6},
-           "camli_pointconv_dw_gather_max": {"ncu_us": 14.8, "ncu_dram_traffic_bytes": 35.1e6, "algorithmic_bytes": 35.1e6}}
-    for name, key in (("camli_corr2d_lookup", "corr_lookup"), ("camli_pointconv_dw_gather_max", "knn_gather")):
-        if name in per:
-            out[key] = {"achieved_GBps": per[name]["GBps"], "frac_of_hbm_peak": per[name]["GBps"] / hbm, "avg_us": per[name]["avg_us"]}
-            c = ncu[name]
-            out[key].update({"ncu_us": c["ncu_us"], "traffic": c["ncu_dram_traffic_bytes"],
-                             "ncu_frac_of_hbm_peak_algorithmic": c["algorithmic_bytes"] / (c["ncu_us"] * 1e-6) / 1e9 / hbm,
-                             "ncu_frac_of_hbm_peak_traffic": c["ncu_dram_traffic_bytes"] / (c["ncu_us"] * 1e-6) / 1e9 / hbm})
-    return out
+def profile_end():
+    """Stop; {entry point: {launches, avg_us, total_us, bytes, flops}} -- live measurements of this process only
+    (per-launch averages of the algorithmic bytes / flops each doorway above declares)."""
+    return native.profile_end()

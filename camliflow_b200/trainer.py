@@ -23,12 +23,15 @@ def unwrap(model):
     return model.module if hasattr(model, "module") else model
 
 
-def train_step(model, optimizer, inputs, max_grad_norm=None):
+def train_step(model, optimizer, inputs, max_grad_norm=None, autocast_dtype=None):
     """One optimisation step; returns the (detached) loss tensor.  `inputs` must carry the targets
-    `flow_2d` / `flow_3d` (models/camliraft.py:80-86)."""
+    `flow_2d` / `flow_3d` (models/camliraft.py:80-86).  `autocast_dtype` (torch.bfloat16): forward and loss under
+    autocast as in train.py:147-149 -- the dense layers run in bf16, the fused point / correlation operators and
+    the losses stay fp32 (camliflow_b200/grad.py:f32); bf16 needs no GradScaler."""
     optimizer.zero_grad(set_to_none=True)
-    model(inputs)
-    loss = unwrap(model).loss
+    with torch.autocast("cuda", dtype=autocast_dtype, enabled=autocast_dtype is not None):
+        model(inputs)
+        loss = unwrap(model).loss
     loss.backward()
     if max_grad_norm is not None:
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
