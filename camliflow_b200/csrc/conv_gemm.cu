@@ -35,8 +35,11 @@
 //   warp 1     MMA issuer: 12 x tcgen05.mma kind::tf32 (M=128, N=BN, K=8) per k-block (4 main, 8 correction);
 //              tcgen05.commit frees the stage / publishes a chunk or the tile's corrections;
 //   warps 2-5  converters (hi/lo split of the A tile, generic -> async proxy fence, arrive);
-//   warps 6-13 epilogue (two per TMEM lane quarter, half of the columns each): tcgen05.ld of every chunk (register sum), + corrections, bias + residual +
-//              activation, 128-bit stores to [rows, ldo].
+//   warps 6-13 epilogue (two per TMEM lane quarter, half of the columns each): tcgen05.ld of every chunk (register sum),
+//              + corrections; the finished 32-row x 32-column block of a warp is transposed through a private shared-
+//              memory pad (TMEM hands every thread one ROW, but global memory wants a warp on one row: a thread-per-row
+//              store touches 32 lines per instruction), then bias + residual + activation / ConvGRU arithmetic and the
+//              store run with the lanes along the columns: 128-byte coalesced side loads and stores.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -52,7 +55,9 @@ constexpr int CG_CHUNK = 2;                       // k-blocks (of 32 channels) a
 template <int BN> struct CgCfg {
     static constexpr int kStageBytes = 2 * CG_A_BYTES + 2 * BN * CG_BK * 4;
     static constexpr int kStages = (BN >= 128) ? 3 : 4;
-    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kEpiWarps = BN >= 64 ? 8 : 4;
+    static constexpr int kPadFloats = 16 * 36;    // one 16-row x 32-column transpose pad per epilogue warp (row pitch 36 floats)
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiWarps * kPadFloats * 4;
     static constexpr int kTmemCols = 4 * BN;      // two [main | correction] accumulator buffers (ping-pong per chunk)
 };
 
@@ -88,80 +93,136 @@ __device__ __forceinline__ float cg_activate(float v, float slope) {
     return v;
 }
 
-// ConvGRU epilogues (reference models/raft_core.py:125-138), same arithmetic as gru_gate_kernel / gru_update_kernel:
-//   GATE   : sigmoid(v), times a1 (the hidden state) for the reset-gate columns (a1 != null)
+// Per-element epilogue arithmetic.  Plain layers: activation of v (= accumulator + bias + residual).  ConvGRU
+// (reference models/raft_core.py:125-138), same arithmetic as gru_gate_kernel / gru_update_kernel:
+//   GATE   : sigmoid(v), times a1 (the hidden state) for the reset-gate columns (gated)
 //   UPDATE : (1 - z) * h + z * tanh(v) with z = a1, h = a2; the _FIX variant adds torch.nan_to_num
 template <int ACT>
-__device__ __forceinline__ float cg_gru(float v, float a1, float a2, bool has_a1) {
+__device__ __forceinline__ float cg_finish(float v, float slope, float a1, float a2, bool gated) {
+    if (ACT == CAMLI_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == CAMLI_ACT_LEAKY) return v > 0.f ? v : v * slope;
+    if (ACT == CAMLI_ACT_TANH) return tanhf(v);
+    if (ACT == CAMLI_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     if (ACT == CAMLI_ACT_GRU_GATE) {
         const float g = 1.f / (1.f + expf(-v));
-        return has_a1 ? g * a1 : g;
+        return gated ? g * a1 : g;
     }
-    float r = (1.f - a1) * a2 + a1 * tanhf(v);
-    if (ACT == CAMLI_ACT_GRU_UPDATE_FIX) {
-        if (isnan(r)) r = 0.f;
-        else if (isinf(r)) r = r > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+    if (ACT == CAMLI_ACT_GRU_UPDATE || ACT == CAMLI_ACT_GRU_UPDATE_FIX) {
+        float r = (1.f - a1) * a2 + a1 * tanhf(v);
+        if (ACT == CAMLI_ACT_GRU_UPDATE_FIX) {
+            if (isnan(r)) r = 0.f;
+            else if (isinf(r)) r = r > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+        }
+        return r;
     }
-    return r;
+    return v;
 }
 
-template <int ACT>
-__device__ __forceinline__ void cg_store32_gru(float (&v)[32], float* __restrict__ orow, const float* __restrict__ rrow,
-                                               const float* __restrict__ bias, const float* __restrict__ a1,
-                                               const float* __restrict__ a2, int col0, int n_cols) {
-    const bool vec = col0 + 32 <= n_cols &&
-                     (((reinterpret_cast<uintptr_t>(orow) | reinterpret_cast<uintptr_t>(rrow) | reinterpret_cast<uintptr_t>(a1) |
-                        reinterpret_cast<uintptr_t>(a2)) & 15) == 0);
-    if (vec) {                                           // 128-bit side loads and stores (null pointers count as aligned)
-        if (bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + col0 + j);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 r = rrow ? __ldg(reinterpret_cast<const float4*>(rrow + j)) : z4;
-            const float4 p = a1 ? __ldg(reinterpret_cast<const float4*>(a1 + j)) : z4;
-            const float4 q = a2 ? __ldg(reinterpret_cast<const float4*>(a2 + j)) : z4;
-            *reinterpret_cast<float4*>(orow + j) =
-                make_float4(cg_gru<ACT>(v[j] + r.x, p.x, q.x, a1 != nullptr), cg_gru<ACT>(v[j + 1] + r.y, p.y, q.y, a1 != nullptr),
-                            cg_gru<ACT>(v[j + 2] + r.z, p.z, q.z, a1 != nullptr), cg_gru<ACT>(v[j + 3] + r.w, p.w, q.w, a1 != nullptr));
-        }
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (col0 + j >= n_cols) break;
-        const float x = v[j] + (bias ? __ldg(bias + col0 + j) : 0.f) + (rrow ? __ldg(rrow + j) : 0.f);
-        orow[j] = cg_gru<ACT>(x, a1 ? __ldg(a1 + j) : 0.f, a2 ? __ldg(a2 + j) : 0.f, a1 != nullptr);
-    }
+// What one warp needs to finish a 16-row x 32-column block that sits in its pad ([16][36] floats: rows 16-byte
+// aligned, conflict-free for the thread-per-row 128-bit writes and the 8-lanes-per-row 128-bit reads).  Read side:
+// lane = (row within a group of 4) * 8 + (float4 of the 32 columns).
+struct CgBlock {
+    uint32_t pad;                     // shared-window address of the warp's pad
+    int mypix;                        // pixel index of this LANE's row (lane = row of the 32-row block), -1 outside the image
+    int row0;                         // first row (0 or 16) of the half that sits in the pad
+    int n_ok;                         // valid columns among this lane's four (0..4)
+    bool vec, gated;                  // vec: every pointer / pitch allows 128-bit accesses
+    float4 bias;
+    float slope;
+    float* dst; long long ldd;        // already offset to this lane's first column
+    const float* res; long long ldr;
+    const float* a1; long long ld1;
+    const float* a2; long long ld2;
+};
+
+__device__ __forceinline__ float4 cg_ld4(const float* p, bool vec, int n_ok) {
+    if (vec) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n_ok > 0) v.x = __ldg(p);
+    if (n_ok > 1) v.y = __ldg(p + 1);
+    if (n_ok > 2) v.z = __ldg(p + 2);
+    if (n_ok > 3) v.w = __ldg(p + 3);
+    return v;
 }
 
-// One thread's 32 consecutive output columns: + bias, + residual, activation, store (masked at the ragged edge).
+// One activation's store loop for the 16 x 32 block in the pad.
 template <int ACT>
-__device__ __forceinline__ void cg_store32(float (&v)[32], float* __restrict__ orow, const float* __restrict__ rrow,
-                                           const float* __restrict__ bias, int col0, int n_cols, bool vec_ok, float slope) {
-    const bool full = col0 + 32 <= n_cols;
-    if (bias) {
+__device__ __forceinline__ void cg_store_block(const CgBlock& k, int lane) {
+    const int sub = lane >> 3, l8 = lane & 7;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += (full || col0 + j < n_cols) ? __ldg(bias + col0 + j) : 0.f;
-    }
-    if (full && vec_ok) {
-        if (rrow) {
+    for (int it0 = 0; it0 < 4; it0 += 2) {                              // two rows per lane in flight (register budget)
+        float4 v[2], rs[2], a1[2], a2[2];
+        int pix[2];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + j));
-                v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+        for (int u = 0; u < 2; ++u) {
+            const int rl = (it0 + u) * 4 + sub;                           // row within the 16-row half
+            pix[u] = __shfl_sync(0xffffffffu, k.mypix, k.row0 + rl);
+            const bool ok = pix[u] >= 0 && k.n_ok > 0;
+            const size_t pp = ok ? (size_t)pix[u] : 0;
+            v[u] = lds_v4(k.pad + (rl * 36 + l8 * 4) * 4);
+            rs[u] = (k.res && ok) ? cg_ld4(k.res + pp * k.ldr, k.vec, k.n_ok) : z4;
+            a1[u] = (ACT >= CAMLI_ACT_GRU_GATE && k.a1 && ok) ? cg_ld4(k.a1 + pp * k.ld1, k.vec, k.n_ok) : z4;
+            a2[u] = (ACT > CAMLI_ACT_GRU_GATE && k.a2 && ok) ? cg_ld4(k.a2 + pp * k.ld2, k.vec, k.n_ok) : z4;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (pix[u] < 0 || k.n_ok <= 0) continue;
+            float4 o;
+            o.x = cg_finish<ACT>((v[u].x + k.bias.x) + rs[u].x, k.slope, a1[u].x, a2[u].x, k.gated);
+            o.y = cg_finish<ACT>((v[u].y + k.bias.y) + rs[u].y, k.slope, a1[u].y, a2[u].y, k.gated);
+            o.z = cg_finish<ACT>((v[u].z + k.bias.z) + rs[u].z, k.slope, a1[u].z, a2[u].z, k.gated);
+            o.w = cg_finish<ACT>((v[u].w + k.bias.w) + rs[u].w, k.slope, a1[u].w, a2[u].w, k.gated);
+            float* d = k.dst + (size_t)pix[u] * k.ldd;
+            if (k.vec) {
+                *reinterpret_cast<float4*>(d) = o;
+            } else {
+                d[0] = o.x;
+                if (k.n_ok > 1) d[1] = o.y;
+                if (k.n_ok > 2) d[2] = o.z;
+                if (k.n_ok > 3) d[3] = o.w;
             }
         }
+    }
+}
+
+// A warp's whole 32-row x CW-column share of a tile: per 32-column group and 16-row half, registers -> pad -> rows.
+template <int ACT, int CW>
+__device__ __forceinline__ void cg_store_tile(float (&sum)[CW], const CgParams& P, uint32_t pad, int mypix, int n0, int lane) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(orow + j) = make_float4(cg_activate<ACT>(v[j], slope), cg_activate<ACT>(v[j + 1], slope),
-                                                               cg_activate<ACT>(v[j + 2], slope), cg_activate<ACT>(v[j + 3], slope));
-    } else {
+    for (int c = 0; c < CW / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= P.Cout) break;                                              // (warp-uniform)
+        const int col = col0 + (lane & 7) * 4;                                  // this lane's four columns (read side)
+        // destination and side inputs of this 32-column group (split is a multiple of 32: a group never straddles it)
+        const bool hi_part = ACT == CAMLI_ACT_GRU_GATE && col0 >= P.split;
+        CgBlock k;
+        k.pad = pad; k.mypix = mypix; k.gated = hi_part; k.slope = P.slope;
+        k.n_ok = min(4, max(0, P.Cout - col));
+        k.dst = (P.out2 && hi_part) ? P.out2 + (col - P.split) : P.out + col;
+        k.ldd = (P.out2 && hi_part) ? P.ldo2 : P.ldo;
+        k.res = P.residual ? P.residual + col : nullptr; k.ldr = P.ldr;
+        k.a1 = nullptr; k.a2 = nullptr; k.ld1 = P.ld1; k.ld2 = P.ld2;
+        if (hi_part) k.a1 = P.aux1 + (col - P.split);
+        else if (ACT > CAMLI_ACT_GRU_GATE) { k.a1 = P.aux1 + col; k.a2 = P.aux2 + col; }
+        k.vec = k.n_ok == 4 && ((k.ldd | k.ldr | k.ld1 | k.ld2) & 3) == 0 &&
+                ((reinterpret_cast<uintptr_t>(k.dst) | reinterpret_cast<uintptr_t>(k.res) | reinterpret_cast<uintptr_t>(k.a1) |
+                  reinterpret_cast<uintptr_t>(k.a2)) & 15) == 0;
+        k.bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.bias) k.bias = cg_ld4(P.bias + col, k.n_ok == 4 && (reinterpret_cast<uintptr_t>(P.bias + col) & 15) == 0, k.n_ok);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (col0 + j < n_cols) orow[j] = cg_activate<ACT>(v[j] + (rrow ? __ldg(rrow + j) : 0.f), slope);
+        for (int h = 0; h < 2; ++h) {
+            __syncwarp();
+            if ((lane >> 4) == h) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    sts_v4(pad + ((lane & 15) * 36 + j) * 4,
+                           make_float4(sum[c * 32 + j], sum[c * 32 + j + 1], sum[c * 32 + j + 2], sum[c * 32 + j + 3]));
+            }
+            __syncwarp();
+            k.row0 = h * 16;
+            cg_store_block<ACT>(k, lane);
+        }
     }
 }
 
@@ -304,14 +365,13 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 if (t == 0 && tile == blockIdx.x && kb < 16) CG_STAMP(32 + kb);
-                const float4* a_hi = reinterpret_cast<const float4*>(smem + stage * Cfg::kStageBytes);
-                float4* a_lo = reinterpret_cast<float4*>(smem + stage * Cfg::kStageBytes + CG_A_BYTES);
+                const uint32_t a_hi = tiles_base + stage * Cfg::kStageBytes + t * 16, a_lo = a_hi + CG_A_BYTES;
                 float4 v[CG_A_BYTES / 16 / 128];                        // 8 chunks of 16 bytes per thread
 #pragma unroll
-                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i) v[i] = a_hi[t + i * 128];
+                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i) v[i] = lds_v4(a_hi + i * 2048);
 #pragma unroll
                 for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i)
-                    a_lo[t + i * 128] = make_float4(cg_lo_part(v[i].x), cg_lo_part(v[i].y), cg_lo_part(v[i].z), cg_lo_part(v[i].w));
+                    sts_v4(a_lo + i * 2048, make_float4(cg_lo_part(v[i].x), cg_lo_part(v[i].y), cg_lo_part(v[i].z), cg_lo_part(v[i].w)));
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to UMMA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_conv + 8 * stage);              // one arrival per converter warp
@@ -327,6 +387,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int row = q * 32 + lane;                                  // accumulator row = pixel of the tile
         const int ty = row / P.tw, tx = row - ty * P.tw;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + half * CW;
+        const uint32_t pad = tiles_base + STAGES * Cfg::kStageBytes + 256 + (warp - 6) * Cfg::kPadFloats * 4;
         int ch = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int b = tile / tiles_per_img;
@@ -358,41 +419,19 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 if (lane == 0) mbar_arrive(bar_aempty + 8 * acc);
             }
             if (warp == 6 && lane == 0 && tile == blockIdx.x) CG_STAMP(9);
-            // ---- bias / residual / activation / store
-            if (x < P.W && y < P.H) {
-                const size_t pix = ((size_t)b * P.H + y) * P.W + x;
-                float* __restrict__ orow = P.out + pix * P.ldo + n0;
-                const float* __restrict__ rrow = P.residual ? P.residual + pix * P.ldr + n0 : nullptr;
-                const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
-                                    (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-#pragma unroll
-                for (int c = 0; c < CW / 32; ++c) {
-                    const int col0 = n0 + c * 32;
-                    if (col0 >= P.Cout) break;
-                    float (&v)[32] = *reinterpret_cast<float (*)[32]>(&sum[c * 32]);
-                    const float* rr = rrow ? rrow + c * 32 : nullptr;
-                    if (P.act >= CAMLI_ACT_GRU_GATE) {
-                        const bool hi_part = col0 >= P.split;
-                        float* dst = (P.out2 && hi_part) ? P.out2 + pix * P.ldo2 + (col0 - P.split) : orow + c * 32;
-                        if (P.act == CAMLI_ACT_GRU_GATE) {
-                            const float* a1 = hi_part ? P.aux1 + pix * P.ld1 + (col0 - P.split) : nullptr;
-                            cg_store32_gru<CAMLI_ACT_GRU_GATE>(v, dst, rr, P.bias, a1, nullptr, col0, P.Cout);
-                        } else {
-                            const float* a1 = P.aux1 + pix * P.ld1 + col0;
-                            const float* a2 = P.aux2 + pix * P.ld2 + col0;
-                            if (P.act == CAMLI_ACT_GRU_UPDATE) cg_store32_gru<CAMLI_ACT_GRU_UPDATE>(v, dst, rr, P.bias, a1, a2, col0, P.Cout);
-                            else cg_store32_gru<CAMLI_ACT_GRU_UPDATE_FIX>(v, dst, rr, P.bias, a1, a2, col0, P.Cout);
-                        }
-                        continue;
-                    }
-                    switch (P.act) {
-                        case CAMLI_ACT_RELU: cg_store32<CAMLI_ACT_RELU>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
-                        case CAMLI_ACT_LEAKY: cg_store32<CAMLI_ACT_LEAKY>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
-                        case CAMLI_ACT_TANH: cg_store32<CAMLI_ACT_TANH>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
-                        case CAMLI_ACT_SIGMOID: cg_store32<CAMLI_ACT_SIGMOID>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
-                        default: cg_store32<CAMLI_ACT_NONE>(v, orow + c * 32, rr, P.bias, col0, P.Cout, vec_ok, P.slope); break;
-                    }
-                }
+            // ---- transpose through the pad (16 rows at a time), then bias / residual / activation / store with 8 lanes
+            // ---- on each row: 128-bit coalesced side loads and stores.  One switch per tile: only the taken activation's
+            // ---- (inlined, unrolled) code is ever fetched.
+            const int mypix = (x < P.W && y < P.H) ? (b * P.H + y) * P.W + x : -1;       // pixel of this lane's row
+            switch (P.act) {
+                case CAMLI_ACT_RELU: cg_store_tile<CAMLI_ACT_RELU, CW>(sum, P, pad, mypix, n0, lane); break;
+                case CAMLI_ACT_LEAKY: cg_store_tile<CAMLI_ACT_LEAKY, CW>(sum, P, pad, mypix, n0, lane); break;
+                case CAMLI_ACT_TANH: cg_store_tile<CAMLI_ACT_TANH, CW>(sum, P, pad, mypix, n0, lane); break;
+                case CAMLI_ACT_SIGMOID: cg_store_tile<CAMLI_ACT_SIGMOID, CW>(sum, P, pad, mypix, n0, lane); break;
+                case CAMLI_ACT_GRU_GATE: cg_store_tile<CAMLI_ACT_GRU_GATE, CW>(sum, P, pad, mypix, n0, lane); break;
+                case CAMLI_ACT_GRU_UPDATE: cg_store_tile<CAMLI_ACT_GRU_UPDATE, CW>(sum, P, pad, mypix, n0, lane); break;
+                case CAMLI_ACT_GRU_UPDATE_FIX: cg_store_tile<CAMLI_ACT_GRU_UPDATE_FIX, CW>(sum, P, pad, mypix, n0, lane); break;
+                default: cg_store_tile<CAMLI_ACT_NONE, CW>(sum, P, pad, mypix, n0, lane); break;
             }
             if (warp == 6 && lane == 0 && tile == blockIdx.x) CG_STAMP(10);
         }

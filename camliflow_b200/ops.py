@@ -137,7 +137,8 @@ def bilinear_sample(feat2d, uv):
 
 
 def convex_upsample(flow, mask, s=8):
-    """models/utils.py:191-204 (once per forward at inference)."""
+    """models/utils.py:191-204 (once per forward at inference); fp32 like the reference's explicit casts."""
+    flow, mask = grad.f32(flow, mask)
     _need_cuda(flow, mask)
     B, _, H, W = flow.shape
     mask = torch.softmax(mask.float().reshape(B, 1, 9, s, s, H, W), 2)

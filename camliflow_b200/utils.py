@@ -120,7 +120,7 @@ def resize_flow2d(flow, target_h, target_w):
     if (h, w) == (target_h, target_w):
         return flow
     flow = F.interpolate(flow, size=(target_h, target_w), mode="bilinear", align_corners=True)
-    return flow * torch.tensor([target_w / w, target_h / h], device=flow.device).view(1, 2, 1, 1)
+    return torch.stack([flow[:, 0] * (target_w / w), flow[:, 1] * (target_h / h)], dim=1)      # (no host tensor: capturable)
 
 
 def resize_to_64x(inputs, target, x=64):
@@ -132,7 +132,7 @@ def resize_to_64x(inputs, target, x=64):
     inputs = F.interpolate(inputs, size=(rh, rw), mode="bilinear", align_corners=True)
     if target is not None:
         target = F.interpolate(target, size=(rh, rw), mode="bilinear", align_corners=True)
-        target = target * torch.tensor([rw / w, rh / h], device=target.device).view(1, 2, 1, 1)
+        target = torch.cat([torch.stack([target[:, 0] * (rw / w), target[:, 1] * (rh / h)], dim=1), target[:, 2:]], dim=1)
     return inputs, target
 
 
