@@ -48,7 +48,18 @@ class CamLiRAFT_Core(nn.Module):
 
         def encode_3d():
             xyzs1, xyzs2, _, _ = build_pc_pyramid(pc1, pc2, [4096, 2048, 1024, 512, 256])
-            feats = b3.fnet(xyzs1[:3])[2], b3.fnet(xyzs2[:3])[2], b3.cnet(xyzs1[:3])[2]
+            B = pc1.shape[0]
+            # neighbour tables depend on the geometry only: ONE search per level for both clouds, shared by the feature
+            # and the context encoder of frame 1 (the reference searches again in each of the 3 encoder passes)
+            both = [torch.cat([a, b], dim=0) for a, b in zip(xyzs1[:3], xyzs2[:3])]
+            tables = b3.fnet.neighbor_tables(both)
+            t1 = [t[:B] for t in tables]
+            if not (self.training and torch.is_grad_enabled()):
+                # both frames through the feature encoder as one batch (eval-mode BatchNorm: samples stay independent)
+                f12 = b3.fnet(both, tables)[2]
+                feats = f12[:B], f12[B:], b3.cnet(xyzs1[:3], t1)[2]
+            else:
+                feats = b3.fnet(xyzs1[:3], t1)[2], b3.fnet(xyzs2[:3], [t[B:] for t in tables])[2], b3.cnet(xyzs1[:3], t1)[2]
             return xyzs1, xyzs2, [ops.rows_of(f) for f in feats]      # channel-last point features from here on
 
         (feat1_2d, feat2_2d, featc_2d), (xyzs1, xyzs2, (feat1_3d, feat2_3d, featc_3d)) = par.run(encode_2d, encode_3d)

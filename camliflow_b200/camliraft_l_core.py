@@ -22,12 +22,18 @@ class Encoder3D(nn.Module):
             self.mlps.append(MLP1d(c_in, [c_in, c_out]))
             self.convs.append(PointConv(c_out, c_out, norm=norm, k=k))
 
-    def forward(self, xyzs):
+    def forward(self, xyzs, knn_tables=None):
+        """`knn_tables[i]` (optional): the level i -> i+1 neighbour table [B,S,>=k]; it depends on the geometry
+        only, so encoders that see the same cloud (fnet / cnet of frame 1) share one search."""
         assert len(xyzs) == len(self.mlps) + 1
         feats = [self.level0_mlp(xyzs[0])]
         for i, (mlp, conv) in enumerate(zip(self.mlps, self.convs)):
-            feats.append(conv(xyzs[i], mlp(feats[-1]), xyzs[i + 1]))
+            feats.append(conv(xyzs[i], mlp(feats[-1]), xyzs[i + 1], None if knn_tables is None else knn_tables[i]))
         return feats
+
+    def neighbor_tables(self, xyzs):
+        """The k-NN tables forward() would search for (one launch per level for the whole batch)."""
+        return [k_nearest_neighbor(xyzs[i], xyzs[i + 1], conv.k) for i, conv in enumerate(self.convs)]
 
 
 class Correlation3D(nn.Module):

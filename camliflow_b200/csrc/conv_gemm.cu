@@ -43,6 +43,12 @@
 #include "common.cuh"
 #include "tcgen05.cuh"
 
+// Programmatic dependent launch of the kernel (its setup overlaps the previous kernel's tail); camli_conv_gemm_set_pdl.
+// Off by default: measured on the C2 graph it gains nothing in latency (13.86 vs 13.78 ms) and costs 4 % throughput
+// with three graphs in flight -- the early-resident CTAs (one per SM, ~200 KB of shared memory each) sit on SMs the
+// other streams' kernels would have used.
+static int camli_cg_pdl = 0;
+
 namespace {
 
 using namespace camli_tc;
@@ -279,6 +285,11 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touches no global data
+    // and may overlap the tail of the previous kernel of the stream; from here on its results are needed (and our
+    // writes may alias its inputs), so wait for it -- then let the NEXT kernel's CTAs start their own setup.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) CG_STAMP(1);
 
     const int cblocks = (P.Cin + CG_BK - 1) / CG_BK;
@@ -475,7 +486,18 @@ int launch_conv_gemm(const CUtensorMap& mx, const CUtensorMap& mwh, const CUtens
     if (e != cudaSuccess) return (int)e;
     const int n_sms = sm_count();
     const int grid = total < n_sms ? total : n_sms;
-    conv_gemm_tf32x3_kernel<BN><<<grid, CG_THREADS, Cfg::kSmem, st>>>(mx, mwh, mwl, P);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(CG_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = camli_cg_pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, conv_gemm_tf32x3_kernel<BN>, mx, mwh, mwl, P);
+    if (e != cudaSuccess) return (int)e;
     CAMLI_RETURN_LAUNCH_STATUS();
 }
 
@@ -487,6 +509,12 @@ static long long* camli_cg_timeline = nullptr;
 extern "C" int camli_conv_gemm_set_timeline(long long* device_buffer) {
     camli_cg_timeline = device_buffer;
     return CAMLI_OK;
+}
+
+extern "C" int camli_conv_gemm_set_pdl(int enabled) {
+    const int old = camli_cg_pdl;
+    camli_cg_pdl = enabled ? 1 : 0;
+    return old;
 }
 
 extern "C" int camli_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {

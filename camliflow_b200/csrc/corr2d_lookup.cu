@@ -37,7 +37,19 @@ struct LookupLevels {
 
 // (Forcing 8 CTAs per SM -- the whole 1020-CTA grid of a 68x120 map resident at once instead of 1.4 waves -- was
 // measured and changes nothing: the kernel sits at ~2.5 TB/s of 64-byte-sector scattered DRAM reads either way.)
-template <bool NHWC>
+// Footprint load.  KEEP: tagged L2 evict-last.  The flow moves by a fraction of a pixel per refinement iteration, so
+// iteration i+1 reads almost exactly the sectors iteration i read (~37 MB of the 354 MB pyramid); nothing else in the
+// iteration is read twice, so keeping just these sectors resident in the 126 MB L2 turns every lookup after the first
+// into an L2 read instead of 64-byte-granular scattered DRAM reads.
+template <bool KEEP>
+__device__ __forceinline__ float lk_load(const float* p, uint64_t policy) {
+    if (!KEEP) return __ldg(p);
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+template <bool NHWC, bool KEEP>
 __global__ void __launch_bounds__(LK_THREADS)
 corr2d_lookup_kernel(const __grid_constant__ LookupLevels lv, const float* __restrict__ coords,   // [B,2,HW]
                      float* __restrict__ out, int HW, int n_levels) {
@@ -48,6 +60,8 @@ corr2d_lookup_kernel(const __grid_constant__ LookupLevels lv, const float* __res
     const int level = blockIdx.y, b = blockIdx.z;
     const int p0 = blockIdx.x * LK_TP;
     const int t = threadIdx.x;
+    uint64_t policy = 0;
+    if (KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
     const int h = lv.h[level], w = lv.w[level];
     const float* __restrict__ vol = lv.vol[level] + (size_t)b * HW * h * w;
 
@@ -94,7 +108,7 @@ corr2d_lookup_kernel(const __grid_constant__ LookupLevels lv, const float* __res
             const int yy = y0 + ry[i], xx = x0 + rx[i];
             v[q][i] = 0.f;
             if (off[i] >= 0 && p < HW && (unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w)
-                v[q][i] = __ldg(slice + yy * w + xx);
+                v[q][i] = lk_load<KEEP>(slice + yy * w + xx, policy);
         }
     }
 #pragma unroll
@@ -215,6 +229,16 @@ corr2d_pool_pyramid_kernel(const float* __restrict__ vol0, const __grid_constant
 
 }  // namespace
 
+// 1: footprint loads carry an L2 evict-last policy (see lk_load); 0 (default): plain read-only loads.  Measured on the
+// C2 graph (12 lookups, CUPTI): 13-17 us per lookup either way -- the hint does not turn the revisited sectors into L2
+// hits across the ~100 MB of other traffic of an iteration, so it stays off.
+static int camli_lookup_keep_l2 = 0;
+extern "C" int camli_corr2d_lookup_set_l2_keep(int enabled) {
+    const int old = camli_lookup_keep_l2;
+    camli_lookup_keep_l2 = enabled ? 1 : 0;
+    return old;
+}
+
 extern "C" int camli_corr2d_lookup(const float* const* volumes, const int* level_h, const int* level_w,
                                    int n_levels, const float* coords, float* out, int B, int H, int W,
                                    int radius, int out_nhwc, void* stream) {
@@ -229,8 +253,14 @@ extern "C" int camli_corr2d_lookup(const float* const* volumes, const int* level
     }
     const int HW = H * W;
     dim3 grid(camli_div_up(HW, LK_TP), n_levels, B);
-    if (out_nhwc) corr2d_lookup_kernel<true><<<grid, LK_THREADS, 0, (cudaStream_t)stream>>>(lv, coords, out, HW, n_levels);
-    else          corr2d_lookup_kernel<false><<<grid, LK_THREADS, 0, (cudaStream_t)stream>>>(lv, coords, out, HW, n_levels);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (camli_lookup_keep_l2) {
+        if (out_nhwc) corr2d_lookup_kernel<true, true><<<grid, LK_THREADS, 0, st>>>(lv, coords, out, HW, n_levels);
+        else          corr2d_lookup_kernel<false, true><<<grid, LK_THREADS, 0, st>>>(lv, coords, out, HW, n_levels);
+    } else {
+        if (out_nhwc) corr2d_lookup_kernel<true, false><<<grid, LK_THREADS, 0, st>>>(lv, coords, out, HW, n_levels);
+        else          corr2d_lookup_kernel<false, false><<<grid, LK_THREADS, 0, st>>>(lv, coords, out, HW, n_levels);
+    }
     CAMLI_RETURN_LAUNCH_STATUS();
 }
 

@@ -39,6 +39,10 @@ def lib():
         if handle.camli_abi_version() != ABI_VERSION:
             raise RuntimeError("libcamli_b200.so ABI %d != expected %d: rebuild the library"
                                % (handle.camli_abi_version(), ABI_VERSION))
+        if os.environ.get("CAMLI_PDL") is not None:         # A/B switch for the benchmarks (default: on)
+            handle.camli_conv_gemm_set_pdl(int(os.environ["CAMLI_PDL"]))
+        if os.environ.get("CAMLI_LOOKUP_KEEP_L2") is not None:
+            handle.camli_corr2d_lookup_set_l2_keep(int(os.environ["CAMLI_LOOKUP_KEEP_L2"]))
         _lib = handle
     return _lib
 

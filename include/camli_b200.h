@@ -366,6 +366,16 @@ int camli_conv_small_cin(const float* x, int B, int H, int W, int Cin, int64_t l
                          int kh, int kw, const float* bias, int act, float slope, float* out, int64_t ldo,
                          void* stream);
 
+/* Tuning switch (no reference counterpart): 1 tags the footprint loads of camli_corr2d_lookup L2 evict-last (meant to keep the
+ * ~10 % of the volume pyramid the refinement revisits in the L2 across iterations; measured: no gain, default 0).  Returns the
+ * previous setting. */
+int camli_corr2d_lookup_set_l2_keep(int enabled);
+
+/* Tuning switch (no reference counterpart): launch the implicit-GEMM kernel with programmatic dependent launch
+ * (default 0; 1: its barrier / TMEM / descriptor setup overlaps the tail of the previous kernel of the stream; it
+ * still waits for that kernel's completion before touching global memory).  Returns the previous setting. */
+int camli_conv_gemm_set_pdl(int enabled);
+
 /* Diagnostics for camli_conv_gemm: a device buffer of >= 128 int64 that CTA 0 of every following launch stamps
  * with SM-clock values of its pipeline events (scripts/conv_gemm_timeline.py); NULL detaches (default). */
 int camli_conv_gemm_set_timeline(long long* device_buffer);
