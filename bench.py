@@ -420,8 +420,6 @@ def run_train(args, rank, world, local_rank, steps=None, warmup=None, workload=N
     torch.backends.cudnn.allow_tf32 = precision != "fp32"
     torch.backends.cuda.matmul.allow_tf32 = precision != "fp32"
     model = build_model(workload).to(dev).train()
-    ddp = trainer.wrap_ddp(model, dev)
-    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, weight_decay=1e-6)
     inputs = synthetic_inputs(B, H, W, N, seed=shard_seed(rank))
     g = torch.Generator().manual_seed(1000 + shard_seed(rank))
     inputs["flow_2d"] = torch.randn(B, 2, H, W, generator=g) * 5.0           # SURVEY 8(d) targets
@@ -448,20 +446,35 @@ def run_train(args, rank, world, local_rank, steps=None, warmup=None, workload=N
         return max_over_ranks(s.elapsed_time(e), world, dev)
 
     losses = []
+    c0 = native.launch_count()
+    if args.no_graph:
+        ddp = trainer.wrap_ddp(model, dev)
+        opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, weight_decay=1e-6)
+        mode = "eager: DistributedDataParallel (bucketed all-reduce overlapped with the backward)"
 
-    def step_resident():
-        losses.append(trainer.train_step(ddp, opt, dev_in, max_grad_norm=1.0, autocast_dtype=amp))
+        def step_resident():
+            losses.append(trainer.train_step(ddp, opt, dev_in, max_grad_norm=1.0, autocast_dtype=amp))
 
-    def step_e2e():
-        batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        losses.append(float(trainer.train_step(ddp, opt, batch, max_grad_norm=1.0, autocast_dtype=amp)))   # D2H read of the loss
+        def step_e2e():
+            batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            losses.append(float(trainer.train_step(ddp, opt, batch, max_grad_norm=1.0, autocast_dtype=amp)))   # D2H read of the loss
+        step_resident()
+        launches = native.launch_count() - c0
+    else:
+        captured = trainer.CapturedTrainStep(model, dev_in, lr=1e-4, weight_decay=1e-6, max_grad_norm=1.0, autocast_dtype=amp)
+        launches = (native.launch_count() - c0) // 4          # 3 warm-up steps + the captured one
+        mode = "whole step in ONE CUDA graph: fwd + losses + bwd + one flat gradient all-reduce (NCCL) + clip + AdamW"
+
+        def step_resident():
+            losses.append(captured(dev_in))
+
+        def step_e2e():
+            losses.append(float(captured(pinned)))            # pinned H2D of the batch, D2H read of the loss
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    c0 = native.launch_count()
     ms_dev = timed(step_resident, steps, warmup)
-    launches = (native.launch_count() - c0) // (steps + warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, steps, warmup)
     pairs = B * world
@@ -473,10 +486,9 @@ def run_train(args, rank, world, local_rank, steps=None, warmup=None, workload=N
         "dtype": {"bf16": "bf16 autocast (fp32 islands as in the reference: fused point / correlation operators, losses)",
                   "tf32": "f32 (tf32 library layers)", "fp32": "f32"}[precision], "data": "synthetic",
         "config": {"workload": workload_name(workload), "pairs_per_step": pairs,
-                   "parallelism": "dp%d (DDP gradient all-reduce over NCCL, %.1f MB fp32 per step, bucketed, overlapped with the "
-                                  "backward)" % (world, grad_bytes / 1e6),
+                   "parallelism": "dp%d (gradient all-reduce over NCCL, %.1f MB fp32 per step)" % (world, grad_bytes / 1e6),
                    "l2": "working set (activations of %d iterations) larger than L2" % iters,
-                   "precision": precision, "grad_clip": 1.0, "final_loss": float(losses[-1])},
+                   "step": mode, "precision": precision, "grad_clip": 1.0, "final_loss": float(losses[-1])},
         "e2e": {"value": pairs * steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": sum(v.numel() * 4 for v in pinned.values()), "d2h_bytes_per_step": 4},
         "gpu_launches": launches * steps, "clocks": clocks,

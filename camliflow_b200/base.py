@@ -15,6 +15,7 @@ class BaseModel(nn.Module):
     def __init__(self):
         super().__init__()
         self.loss = None
+        self.track_metrics = True       # False: forward() skips the bookkeeping (whole-step CUDA-graph capture)
         self._metric_rows = {}          # name -> device tensor [2] = (sum, count), float64
 
     def clear_metrics(self):
@@ -24,6 +25,8 @@ class BaseModel(nn.Module):
     def update_metrics(self, name, var, mask=None):
         """Accumulates sum(var[mask]) and its element count under `name` (models/base.py:16-32).  `var`: tensor
         (any shape; bool is counted as 0/1) or a python number (count 1)."""
+        if not self.track_metrics:
+            return
         if not isinstance(var, torch.Tensor):
             var = torch.tensor(float(var))
         v = var.detach().to(torch.float64)
@@ -64,6 +67,8 @@ class FlowModel(BaseModel):
 
     @torch.no_grad()
     def update_2d_metrics(self, pred, target):
+        if not self.track_metrics:
+            return
         if target.shape[1] == 3:                         # sparse ground truth: channel 2 is the validity mask
             mask, target = target[:, 2] > 0, target[:, :2]
         else:
@@ -76,6 +81,8 @@ class FlowModel(BaseModel):
 
     @torch.no_grad()
     def update_3d_metrics(self, pred, target, occ_mask=None):
+        if not self.track_metrics:
+            return
         if target.shape[1] == 4:
             mask, target = target[:, 3] > 0, target[:, :3]
         else:

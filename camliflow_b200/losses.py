@@ -3,8 +3,16 @@ per-iteration predictions of the masked l2-norm / l1 / robust end-point error.""
 import torch
 
 
+def _masked_mean(err, mask):
+    """mean of err over mask (None = everywhere) without a data-dependent shape: capturable in a CUDA graph."""
+    if mask is None:
+        return err.mean()
+    m = mask.to(err.dtype)
+    return (err * m).sum() / m.sum()
+
+
 def _sequence_loss(preds, target, n_flow, cfgs):
-    mask = target[:, n_flow] > 0 if target.shape[1] == n_flow + 1 else torch.ones_like(target[:, 0], dtype=torch.bool)
+    mask = target[:, n_flow] > 0 if target.shape[1] == n_flow + 1 else None
     total = 0
     for i, pred in enumerate(preds):
         diff = pred - target[:, :n_flow]
@@ -16,7 +24,7 @@ def _sequence_loss(preds, target, n_flow, cfgs):
             err = torch.pow(diff.abs().sum(dim=1) + 0.01, 0.4)
         else:
             raise ValueError(cfgs.order)
-        total = total + cfgs.gamma ** (len(preds) - i - 1) * err[mask].mean()
+        total = total + cfgs.gamma ** (len(preds) - i - 1) * _masked_mean(err, mask)
     return total
 
 
@@ -49,7 +57,7 @@ def calc_pyramid_loss_2d(flows, target, cfgs):
     for pred, weight in zip(flows, cfgs.level_weights):
         assert pred.shape[1] == 2
         err = _level_error(torch.abs(resize_flow2d(pred, target.shape[2], target.shape[3]) - target[:, :2]), cfgs.order)
-        total = total + weight * (err[mask].mean() if mask is not None else err.mean())
+        total = total + weight * _masked_mean(err, mask)
     return total
 
 
@@ -62,5 +70,5 @@ def calc_pyramid_loss_3d(flows, target, cfgs, indices):
     for lvl, (flow, weight) in enumerate(zip(flows, cfgs.level_weights)):
         level_target = batch_indexing(target, indices[lvl])
         err = _level_error(flow - level_target[:, :3], cfgs.order)
-        total = total + weight * (err[level_target[:, 3] > 0].mean() if level_target.shape[1] == 4 else err.mean())
+        total = total + weight * _masked_mean(err, level_target[:, 3] > 0 if level_target.shape[1] == 4 else None)
     return total

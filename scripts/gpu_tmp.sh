@@ -1,12 +1,9 @@
-for keep in 0 1; do
-echo "== CAMLI_LOOKUP_KEEP_L2=$keep"
-CAMLI_LOOKUP_KEEP_L2=$keep timeout 600 python scripts/trace_forward.py --out gpurun_out/trace_keep$keep 2>&1 | grep -E "^graph|corr2d_lookup|span" | cut -c1-200
-python - <<PY
-import json
-ev=json.load(open("gpurun_out/trace_keep${keep}_graph.json"))["traceEvents"]
-ks=sorted([e for e in ev if e.get("cat")=="kernel" and "corr2d_lookup" in e["name"]], key=lambda e:e["ts"])
-print("lookup durations per iteration:", [round(e["dur"],1) for e in ks])
-PY
-rm -f gpurun_out/trace_keep${keep}_graph.json
-done
-timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "corr2d or lookup" 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_grad.py -m gpu -q -x -s -k "captured or golden" 2>&1 | grep -v Warn | tail -8
+timeout 900 python bench.py --workload c5 --steps 4 --warmup 3 2>&1 | tail -1 | python -c "
+import json,sys
+b=json.loads(sys.stdin.read())
+print('c5 graph: %.2f pairs/s %.1f ms/step e2e %.2f loss %.3f launches %d' % (b['value'], b['ms_per_step'], b['e2e']['value'], b['config']['final_loss'], b['gpu_launches']))"
+timeout 900 python bench.py --workload c5 --steps 4 --warmup 3 --no-graph 2>&1 | tail -1 | python -c "
+import json,sys
+b=json.loads(sys.stdin.read())
+print('c5 eager: %.2f pairs/s %.1f ms/step e2e %.2f loss %.3f' % (b['value'], b['ms_per_step'], b['e2e']['value'], b['config']['final_loss']))"

@@ -99,3 +99,40 @@ def test_two_rank_training_step_allreduces_gradients(tmp_path):
         ref.loss.backward()
         grads.append(ref.lin.weight.grad.clone())
     assert torch.allclose(r[0]["g"], (grads[0] + grads[1]) / 2, atol=1e-6)
+
+
+def _flat_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from camliflow_b200 import trainer
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = _TinyFlow().train()
+    g = torch.Generator().manual_seed(100 + rank)
+    inputs = {"x": torch.randn(8, 4, generator=g), "flow_2d": torch.randn(8, 2, generator=g)}
+    step = trainer.CapturedTrainStep(model, inputs, lr=0.1, weight_decay=0.0, max_grad_norm=None, use_graph=False)
+    loss = step(inputs)
+    torch.save({"w": model.lin.weight.detach().clone(), "g": model.lin.weight.grad.clone(), "loss": loss.clone(),
+                "flat": step.flat.clone(), "x": inputs["x"], "y": inputs["flow_2d"]}, os.path.join(out_dir, "f%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_allreduce_step(tmp_path):
+    """trainer.CapturedTrainStep (eager mode on CPU): every parameter's gradient is a view of ONE flat buffer, the
+    buffer is mean-reduced over the ranks with a single all-reduce, and both ranks apply the same update."""
+    world, port = 2, 33500 + os.getpid() % 2000
+    mp.spawn(_flat_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(tmp_path / ("f%d.pt" % i)) for i in range(world)]
+    assert torch.equal(r[0]["w"], r[1]["w"]) and torch.equal(r[0]["flat"], r[1]["flat"])
+    assert r[0]["flat"].numel() == 4 * 2 + 2                     # weight + bias of the tiny model, one buffer
+    torch.manual_seed(0)
+    ref = _TinyFlow()
+    grads = []
+    for i in range(world):
+        ref.zero_grad()
+        ref({"x": r[i]["x"], "flow_2d": r[i]["y"]})
+        ref.loss.backward()
+        grads.append(ref.lin.weight.grad.clone())
+    assert torch.allclose(r[0]["g"], (grads[0] + grads[1]) / 2, atol=1e-6)
+    assert r[0]["loss"] != r[1]["loss"]                          # (each rank reports the loss of its own pairs)

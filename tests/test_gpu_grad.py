@@ -263,3 +263,34 @@ def test_camlipwc_training_step_vs_reference_golden(dev):
     from camliflow_b200.init import seed_module_
     _golden_train_step(lambda: seed_module_(CamLiPWC(camlipwc_config()), seed=0),
                        "train_camlipwc.npz", (128, 192, 8192, 2, 21, 22), dev)
+
+
+def test_captured_train_step_matches_eager(dev):
+    """trainer.CapturedTrainStep: the whole step (forward, losses, backward, flat gradient buffer, clip, AdamW) replayed
+    from ONE CUDA graph gives the losses of the same step run eagerly, over several consecutive steps (i.e. the
+    captured optimizer really updates the weights the next replay reads)."""
+    from camliflow_b200 import trainer
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.init import seed_module_
+    from oracle import camliraft_oracle as co
+    from tests.test_train_golden import train_targets
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, H, W, N = 1, 128, 160, 8192
+    inputs = dict(co.synthetic_inputs(B, H, W, N, 31), **train_targets(B, H, W, N, 32))
+    inputs = {k: v.to(dev) for k, v in inputs.items()}
+    out = {}
+    for mode in (False, True):
+        model = seed_module_(CamLiRAFT(camliraft_config(n_iters_train=2)), seed=0).to(dev).train()
+        step = trainer.CapturedTrainStep(model, inputs, lr=1e-3, use_graph=mode, warmup=0 if not mode else 2)
+        if mode:     # the warm-up steps already moved the weights: restart from the seeded ones, in place
+            seed_module_(model, seed=0)
+            for st in step.opt.state.values():
+                for v in st.values():
+                    v.zero_()
+        out[mode] = [float(step(inputs)) for _ in range(3)]
+    print("captured step losses", out[True], "eager", out[False])
+    assert out[True][0] != out[True][2]                          # the weights move
+    for a, b in zip(out[True], out[False]):
+        assert abs(a - b) <= 2e-4 * abs(b), (out[True], out[False])
