@@ -67,11 +67,12 @@ class FlowEngine:
         with torch.cuda.stream(self.stream):
             for k, dst in self.dev_in.items():
                 src = inputs[k]
-                if src.device.type == "cpu":
-                    self.host_in[k].copy_(src)
+                if src.device.type == "cpu" and not src.is_pinned():
+                    self.host_in[k].copy_(src)              # pageable host memory: stage through the pinned buffer
                     dst.copy_(self.host_in[k], non_blocking=True)
                 else:
-                    dst.copy_(src, non_blocking=True)
+                    dst.copy_(src, non_blocking=True)       # device tensor, or pinned already: DMA straight from the caller's
+                                                            # buffer (which must stay untouched until the step has run)
 
     def step(self):
         """One forward over the resident inputs (no host traffic)."""
@@ -117,12 +118,17 @@ class FlowEngine:
         consumed = [torch.cuda.Event(), torch.cuda.Event()]     # compute stream finished reading in_dev[slot]
 
         def upload(slot, inputs):
+            srcs = {}
             for k, dst in P["in_host"][slot].items():
-                dst.copy_(inputs[k])
+                if inputs[k].is_pinned():
+                    srcs[k] = inputs[k]                     # pinned already: no staging memcpy
+                else:
+                    dst.copy_(inputs[k])
+                    srcs[k] = dst
             with torch.cuda.stream(copy):
                 copy.wait_event(consumed[slot])
                 for k, dst in P["in_dev"][slot].items():
-                    dst.copy_(P["in_host"][slot][k], non_blocking=True)
+                    dst.copy_(srcs[k], non_blocking=True)
                 loaded[slot].record(copy)
 
         it = iter(batches)
