@@ -103,8 +103,18 @@ __device__ __forceinline__ float cg_activate(float v, float slope) {
 // (reference models/raft_core.py:125-138), same arithmetic as gru_gate_kernel / gru_update_kernel:
 //   GATE   : sigmoid(v), times a1 (the hidden state) for the reset-gate columns (gated)
 //   UPDATE : (1 - z) * h + z * tanh(v) with z = a1, h = a2; the _FIX variant adds torch.nan_to_num
+__device__ __forceinline__ float cg_nan_to_num(float r) {
+    if (isnan(r)) return 0.f;
+    if (isinf(r)) return r > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+    return r;
+}
+
 template <int ACT>
 __device__ __forceinline__ float cg_finish(float v, float slope, float a1, float a2, bool gated) {
+    if (ACT >= CAMLI_ACT_FIX_NONFINITE) {            // plain activation + torch.nan_to_num (torch's relu keeps a nan)
+        if (ACT == (CAMLI_ACT_RELU | CAMLI_ACT_FIX_NONFINITE)) return isnan(v) ? 0.f : fminf(fmaxf(v, 0.f), 3.402823466e+38f);
+        return cg_nan_to_num(cg_finish<ACT & (CAMLI_ACT_FIX_NONFINITE - 1)>(v, slope, a1, a2, gated));
+    }
     if (ACT == CAMLI_ACT_RELU) return fmaxf(v, 0.f);
     if (ACT == CAMLI_ACT_LEAKY) return v > 0.f ? v : v * slope;
     if (ACT == CAMLI_ACT_TANH) return tanhf(v);
@@ -168,8 +178,8 @@ __device__ __forceinline__ void cg_store_block(const CgBlock& k, int lane) {
             const size_t pp = ok ? (size_t)pix[u] : 0;
             v[u] = lds_v4(k.pad + (rl * 36 + l8 * 4) * 4);
             rs[u] = (k.res && ok) ? cg_ld4(k.res + pp * k.ldr, k.vec, k.n_ok) : z4;
-            a1[u] = (ACT >= CAMLI_ACT_GRU_GATE && k.a1 && ok) ? cg_ld4(k.a1 + pp * k.ld1, k.vec, k.n_ok) : z4;
-            a2[u] = (ACT > CAMLI_ACT_GRU_GATE && k.a2 && ok) ? cg_ld4(k.a2 + pp * k.ld2, k.vec, k.n_ok) : z4;
+            a1[u] = (ACT >= CAMLI_ACT_GRU_GATE && ACT < CAMLI_ACT_FIX_NONFINITE && k.a1 && ok) ? cg_ld4(k.a1 + pp * k.ld1, k.vec, k.n_ok) : z4;
+            a2[u] = (ACT > CAMLI_ACT_GRU_GATE && ACT < CAMLI_ACT_FIX_NONFINITE && k.a2 && ok) ? cg_ld4(k.a2 + pp * k.ld2, k.vec, k.n_ok) : z4;
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -210,7 +220,7 @@ __device__ __forceinline__ void cg_store_tile(float (&sum)[CW], const CgParams& 
         k.res = P.residual ? P.residual + col : nullptr; k.ldr = P.ldr;
         k.a1 = nullptr; k.a2 = nullptr; k.ld1 = P.ld1; k.ld2 = P.ld2;
         if (hi_part) k.a1 = P.aux1 + (col - P.split);
-        else if (ACT > CAMLI_ACT_GRU_GATE) { k.a1 = P.aux1 + col; k.a2 = P.aux2 + col; }
+        else if (ACT > CAMLI_ACT_GRU_GATE && ACT < CAMLI_ACT_FIX_NONFINITE) { k.a1 = P.aux1 + col; k.a2 = P.aux2 + col; }
         k.vec = k.n_ok == 4 && ((k.ldd | k.ldr | k.ld1 | k.ld2) & 3) == 0 &&
                 ((reinterpret_cast<uintptr_t>(k.dst) | reinterpret_cast<uintptr_t>(k.res) | reinterpret_cast<uintptr_t>(k.a1) |
                   reinterpret_cast<uintptr_t>(k.a2)) & 15) == 0;
@@ -435,6 +445,10 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             // ---- (inlined, unrolled) code is ever fetched.
             const int mypix = (x < P.W && y < P.H) ? (b * P.H + y) * P.W + x : -1;       // pixel of this lane's row
             switch (P.act) {
+                case CAMLI_ACT_RELU | CAMLI_ACT_FIX_NONFINITE:
+                    cg_store_tile<CAMLI_ACT_RELU | CAMLI_ACT_FIX_NONFINITE, CW>(sum, P, pad, mypix, n0, lane); break;
+                case CAMLI_ACT_NONE | CAMLI_ACT_FIX_NONFINITE:
+                    cg_store_tile<CAMLI_ACT_NONE | CAMLI_ACT_FIX_NONFINITE, CW>(sum, P, pad, mypix, n0, lane); break;
                 case CAMLI_ACT_RELU: cg_store_tile<CAMLI_ACT_RELU, CW>(sum, P, pad, mypix, n0, lane); break;
                 case CAMLI_ACT_LEAKY: cg_store_tile<CAMLI_ACT_LEAKY, CW>(sum, P, pad, mypix, n0, lane); break;
                 case CAMLI_ACT_TANH: cg_store_tile<CAMLI_ACT_TANH, CW>(sum, P, pad, mypix, n0, lane); break;
@@ -529,7 +543,7 @@ extern "C" int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int
                                const float* w_hi, const float* w_lo, int Cout, int kh, int kw,
                                const float* bias, const float* residual, int64_t ldr,
                                int act, float slope, float* out, int64_t ldo, int tile_n, void* stream) {
-    if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
+    if (act < CAMLI_ACT_NONE || (act & ~CAMLI_ACT_FIX_NONFINITE) > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
     return camli_conv_gemm_fused(x, B, H, W, Cin, ldx, w_hi, w_lo, Cout, kh, kw, bias, residual, ldr, act, slope, out, ldo,
                                  nullptr, 0, nullptr, 0, 0, nullptr, 0, tile_n, stream);
 }
@@ -542,11 +556,14 @@ extern "C" int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Ci
                                      float* out2, int64_t ldo2, int tile_n, void* stream) {
     if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin) return CAMLI_EINVAL;
     if (residual && ldr < Cout) return CAMLI_EINVAL;
-    if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_GRU_UPDATE_FIX) return CAMLI_EINVAL;
+    if (act & CAMLI_ACT_FIX_NONFINITE) {            // only NONE / RELU carry the nan_to_num flag on this kernel
+        const int base = act & ~CAMLI_ACT_FIX_NONFINITE;
+        if (base != CAMLI_ACT_NONE && base != CAMLI_ACT_RELU) return CAMLI_EUNSUPPORTED;
+    } else if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_GRU_UPDATE_FIX) return CAMLI_EINVAL;
+    const bool gru_update = !(act & CAMLI_ACT_FIX_NONFINITE) && act > CAMLI_ACT_GRU_GATE;
     if (act == CAMLI_ACT_GRU_GATE && (!aux1 || split < 0 || split > Cout || (split & 31) || ld1 < Cout - split)) return CAMLI_EINVAL;
-    if (act > CAMLI_ACT_GRU_GATE && (!aux1 || !aux2 || ld1 < Cout || ld2 < Cout)) return CAMLI_EINVAL;
-    if (act < CAMLI_ACT_GRU_GATE) { split = Cout; out2 = nullptr; }
-    if (act > CAMLI_ACT_GRU_GATE) { split = Cout; out2 = nullptr; }
+    if (gru_update && (!aux1 || !aux2 || ld1 < Cout || ld2 < Cout)) return CAMLI_EINVAL;
+    if (act != CAMLI_ACT_GRU_GATE) { split = Cout; out2 = nullptr; }
     if (out2 ? (ldo < split || ldo2 < Cout - split) : ldo < Cout) return CAMLI_EINVAL;
     // TMA: 16-byte aligned bases and strides; odd windows only ("same" padding)
     if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (Cin & 3) || (ldx & 3)) return CAMLI_EUNSUPPORTED;

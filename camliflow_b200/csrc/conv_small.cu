@@ -13,7 +13,18 @@ namespace {
 constexpr int CS_WARPS = 8;
 constexpr int CS_MAX_OUT = 4;
 
+__device__ __forceinline__ float cs_activate_base(float v, int act, float slope);
+
+// act may carry CAMLI_ACT_FIX_NONFINITE: torch.nan_to_num of the activated value
 __device__ __forceinline__ float cs_activate(float v, int act, float slope) {
+    const float r = cs_activate_base(v, act & (CAMLI_ACT_FIX_NONFINITE - 1), slope);
+    if (!(act & CAMLI_ACT_FIX_NONFINITE)) return r;
+    if (isnan(r)) return 0.f;
+    if (isinf(r)) return r > 0.f ? 3.402823466e+38f : -3.402823466e+38f;
+    return r;
+}
+
+__device__ __forceinline__ float cs_activate_base(float v, int act, float slope) {
     switch (act) {
         case CAMLI_ACT_RELU: return fmaxf(v, 0.f);
         case CAMLI_ACT_LEAKY: return v > 0.f ? v : v * slope;
@@ -70,7 +81,7 @@ extern "C" int camli_conv_small_n(const float* x, int B, int H, int W, int Cin, 
                                   int kh, int kw, const float* bias, int act, float slope, float* out, int64_t ldo,
                                   void* stream) {
     if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin || ldo < Cout) return CAMLI_EINVAL;
-    if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
+    if (act < CAMLI_ACT_NONE || (act & ~CAMLI_ACT_FIX_NONFINITE) > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
     if (Cout > CS_MAX_OUT || (kh & 1) == 0 || (kw & 1) == 0 || (Cin & 3) || (ldx & 3)) return CAMLI_EUNSUPPORTED;
     const size_t smem = (size_t)Cout * kh * kw * Cin * sizeof(float);
     if (smem > 160 * 1024) return CAMLI_EUNSUPPORTED;
@@ -175,7 +186,7 @@ extern "C" int camli_conv_small_cin(const float* x, int B, int H, int W, int Cin
                                     int kh, int kw, const float* bias, int act, float slope, float* out, int64_t ldo,
                                     void* stream) {
     if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin || ldo < Cout) return CAMLI_EINVAL;
-    if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
+    if (act < CAMLI_ACT_NONE || (act & ~CAMLI_ACT_FIX_NONFINITE) > CAMLI_ACT_SIGMOID) return CAMLI_EINVAL;
     if (Cin > CI_MAX_CIN || (kh & 1) == 0 || (kw & 1) == 0 || kh > CI_MAX_K || kw > CI_MAX_K || B > 65535) return CAMLI_EUNSUPPORTED;
     if (B == 0) return CAMLI_OK;
     if (!x || !w || !out) return CAMLI_EINVAL;

@@ -189,8 +189,10 @@ dw_gather_max_kernel(int N, int S, int K, int k, int O, int chunks,
 
 // 128-bit variant for O % 128 == 0 (the 128- and 256-channel layers that dominate the traffic): one warp owns a
 // centroid and 128 consecutive channels, lane = 4 channels, so every request is a full 512-byte row segment (the
-// k weight rows of a centroid are one contiguous 16 KB block) and the instruction count drops 4x.
-template <int WARPS, int KT>
+// k weight rows of a centroid are one contiguous 16 KB block) and the instruction count drops 4x.  k = KT * NCH
+// neighbours are processed in NCH chunks of KT (2 * KT 128-bit loads in flight per lane: 128 registers at KT = 16),
+// the running maximum carried across chunks.
+template <int WARPS, int KT, int NCH>
 __global__ void __launch_bounds__(WARPS * 32)
 dw_gather_max_vec4_kernel(int N, int S, int K, int O, int chunks,          // chunks = O / 128
                           const float* __restrict__ feat, long long ldf, const float* __restrict__ wc,
@@ -201,21 +203,24 @@ dw_gather_max_vec4_kernel(int N, int S, int K, int O, int chunks,          // ch
     const int s = (int)(wid / chunks), o = (int)(wid % chunks) * 128 + lane * 4;
     const int b = blockIdx.y;
     const int64_t* ip = idx + ((size_t)b * S + s) * K;
-    const int my = (lane < KT) ? (int)__ldg(ip + lane) : 0;
+    const int my = (lane < KT * NCH) ? (int)__ldg(ip + lane) : 0;          // k <= 32: one index per lane
     const float* fb = feat + (size_t)b * N * ldf + o;
-    const float* wp = wc + ((size_t)b * S + s) * KT * O + o;
-    float4 f[KT], w[KT];
-#pragma unroll
-    for (int j = 0; j < KT; ++j) {
-        const int ij = __shfl_sync(CAMLI_FULL_MASK, my, j);
-        f[j] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)ij * ldf));
-        w[j] = __ldcs(reinterpret_cast<const float4*>(wp + (size_t)j * O));
-    }
+    const float* wp = wc + ((size_t)b * S + s) * (KT * NCH) * O + o;
     float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-    for (int j = 0; j < KT; ++j) {
-        best.x = fmaxf(best.x, f[j].x * w[j].x); best.y = fmaxf(best.y, f[j].y * w[j].y);
-        best.z = fmaxf(best.z, f[j].z * w[j].z); best.w = fmaxf(best.w, f[j].w * w[j].w);
+    for (int c = 0; c < NCH; ++c) {
+        float4 f[KT], w[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            const int ij = __shfl_sync(CAMLI_FULL_MASK, my, c * KT + j);
+            f[j] = __ldg(reinterpret_cast<const float4*>(fb + (size_t)ij * ldf));
+            w[j] = __ldcs(reinterpret_cast<const float4*>(wp + (size_t)(c * KT + j) * O));
+        }
+#pragma unroll
+        for (int j = 0; j < KT; ++j) {
+            best.x = fmaxf(best.x, f[j].x * w[j].x); best.y = fmaxf(best.y, f[j].y * w[j].y);
+            best.z = fmaxf(best.z, f[j].z * w[j].z); best.w = fmaxf(best.w, f[j].w * w[j].w);
+        }
     }
     *reinterpret_cast<float4*>(out + ((size_t)b * S + s) * ldo + o) = best;
 }
@@ -269,18 +274,20 @@ extern "C" int camli_pointconv_dw_gather_max(int B, int N, int S, int K, int k, 
     const int chunks = camli_div_up(O, 32);
     dim3 grid((unsigned)camli_div_up_ll((long long)S * chunks, WARPS), B);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec4 = (O % 128 == 0) && (ld_feat % 4 == 0) && (ld_out % 4 == 0) && (k == 4 || k == 8 || k == 16) &&
+    const bool vec4 = (O % 128 == 0) && (ld_feat % 4 == 0) && (ld_out % 4 == 0) && (k == 4 || k == 8 || k == 16 || k == 32) &&
                       ((reinterpret_cast<uintptr_t>(feat_rows) | reinterpret_cast<uintptr_t>(weights) |
                         reinterpret_cast<uintptr_t>(out_rows)) % 16 == 0);
-    if (vec4) {          // (k = 32 would need 256 registers for the 2k float4 values in flight: scalar kernel below)
+    if (vec4) {          // (k = 32: two chunks of 16 neighbours, 128 registers of loads in flight each)
         const int ch = O / 128;
-        dim3 g4((unsigned)camli_div_up_ll((long long)S * ch, WARPS), B);
-#define CAMLI_DW_LAUNCH4(KT)                                                                                      \
-        dw_gather_max_vec4_kernel<WARPS, KT><<<g4, WARPS * 32, 0, st>>>(N, S, K, O, ch, feat_rows, ld_feat, weights, \
-                                                                        knn_idx, out_rows, ld_out)
-        if (k == 4) CAMLI_DW_LAUNCH4(4);
-        else if (k == 8) CAMLI_DW_LAUNCH4(8);
-        else CAMLI_DW_LAUNCH4(16);
+        constexpr int W4 = 2;          // 2-warp CTAs: S * ch / 2 = 1024+ CTAs, ~7 per SM -- an even spread over 148 SMs
+        dim3 g4((unsigned)camli_div_up_ll((long long)S * ch, W4), B);
+#define CAMLI_DW_LAUNCH4(KT, NCH)                                                                                       \
+        dw_gather_max_vec4_kernel<W4, KT, NCH><<<g4, W4 * 32, 0, st>>>(N, S, K, O, ch, feat_rows, ld_feat, weights, \
+                                                                       knn_idx, out_rows, ld_out)
+        if (k == 4) CAMLI_DW_LAUNCH4(4, 1);
+        else if (k == 8) CAMLI_DW_LAUNCH4(8, 1);
+        else if (k == 16) CAMLI_DW_LAUNCH4(16, 1);
+        else CAMLI_DW_LAUNCH4(16, 2);
 #undef CAMLI_DW_LAUNCH4
         CAMLI_RETURN_LAUNCH_STATUS();
     }

@@ -77,7 +77,38 @@ def knn_interpolate(input_xyz, input_feat, query_xyz, k=3):
     input_xyz [B,3,m], input_feat [B,F,m], query_xyz [B,3,n] -> [B,F,n]."""
     input_xyz, input_feat, query_xyz = grad.f32(input_xyz, input_feat, query_xyz)
     _need_cuda(input_xyz, input_feat, query_xyz)
+    if grad.needs_grad(input_feat) and not grad.needs_grad(input_xyz, query_xyz):
+        with torch.autocast("cuda", enabled=False):          # weights are constants of the geometry: scatter kernel
+            return _ThreeNN.apply(input_xyz, input_feat, query_xyz, k)
     return grad.recompute(_knn_interpolate, grad.f_knn_interpolate, input_xyz, input_feat, query_xyz, k)
+
+
+class _ThreeNN(torch.autograd.Function):
+    """knn_interpolate with a gradient for the features only: d feat[idx_j] += w_j * g (camli_three_nn_interpolate_backward
+    repeats the search and the inverse-distance weights)."""
+
+    @staticmethod
+    def forward(ctx, input_xyz, input_feat, query_xyz, k):
+        ctx.save_for_backward(input_xyz, query_xyz)
+        ctx.k, ctx.feat_shape = k, input_feat.shape
+        return _knn_interpolate(input_xyz, input_feat, query_xyz, k)
+
+    @staticmethod
+    def backward(ctx, g):
+        input_xyz, query_xyz = ctx.saved_tensors
+        B, Fc, m = ctx.feat_shape
+        n = query_xyz.shape[-1]
+        g = g.contiguous()
+        gfeat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=g.device)
+        qs, xs, gs, fs = query_xyz.stride(), input_xyz.stride(), g.stride(), gfeat.stride()
+        with torch.cuda.device(g.device):
+            native.call("camli_three_nn_interpolate_backward", i32(B), i32(n), i32(m), i32(ctx.k), i32(Fc),
+                        ptr(query_xyz), i64(qs[0]), i64(qs[2]), i64(qs[1]),
+                        ptr(input_xyz), i64(xs[0]), i64(xs[2]), i64(xs[1]),
+                        ptr(g), i64(gs[0]), i64(gs[1]), i64(gs[2]),
+                        ptr(gfeat), i64(fs[0]), i64(fs[1]), i64(fs[2]), stream(),
+                        algo_bytes=B * ((n + m) * 12 + n * ctx.k * (Fc * 8 + 12) + n * Fc * 4), flops=B * n * m * 8)
+        return None, gfeat, None, None
 
 
 def _knn_interpolate(input_xyz, input_feat, query_xyz, k):
@@ -199,7 +230,9 @@ def _allpairs(a_rows, b_rows, scale):
 
 # ---------------------------------------------------------------- tensor-core linear / convolution
 ACT_CODES = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "tanh": 3, "sigmoid": 4,
-             "gru_gate": 5, "gru_update": 6, "gru_update_fix": 7}
+             "gru_gate": 5, "gru_update": 6, "gru_update_fix": 7,
+             # + torch.nan_to_num of the activated value (CAMLI_ACT_FIX_NONFINITE)
+             "none_fix": 16, "relu_fix": 17}
 _TC_WEIGHTS = {}
 
 
@@ -338,7 +371,34 @@ def corr2d_build(fmap1, fmap2, num_levels):
     a = nhwc_rows(fmap1).view(B, H * W, C)
     b = nhwc_rows(fmap2).view(B, H * W, C)
     vol = allpairs(a, b, 1.0 / C ** 0.5).view(B, H * W, H, W)
-    return grad.recompute(_corr2d_pool, grad.f_corr2d_pool, vol, num_levels)
+    if grad.needs_grad(vol):
+        with torch.autocast("cuda", enabled=False):
+            return [vol] + list(_Corr2dPool.apply(vol, num_levels))
+    return _corr2d_pool(vol, num_levels)
+
+
+class _Corr2dPool(torch.autograd.Function):
+    """The coarser pyramid levels of `vol`; backward = the chained avg_pool2d backward as one pass
+    (camli_corr2d_pool_backward)."""
+
+    @staticmethod
+    def forward(ctx, vol, num_levels):
+        ctx.shape, ctx.num_levels = vol.shape, num_levels
+        return tuple(_corr2d_pool(vol, num_levels)[1:])
+
+    @staticmethod
+    def backward(ctx, *gs):
+        B, P, H, W = ctx.shape
+        dev = next(g for g in gs if g is not None).device
+        h, w, coarse = H, W, []
+        for g in gs:
+            h, w = h // 2, w // 2
+            coarse.append(torch.zeros((B, P, h, w), dtype=torch.float32, device=dev) if g is None else g.contiguous())
+        g0 = torch.zeros(ctx.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            native.call("camli_corr2d_pool_backward", ptr(g0), _ptr_array(coarse), i32(ctx.num_levels), i64(B * P), i32(H), i32(W),
+                        stream(), algo_bytes=(2 * g0.numel() + sum(c.numel() for c in coarse)) * 4)
+        return g0, None
 
 
 def _corr2d_pool(vol, num_levels):
@@ -426,8 +486,34 @@ def corr3d_build(feat1, feat2, xyzs2, k=3):
     pyr = [vol]
     for i in range(1, len(xyzs2)):
         idx = k_nearest_neighbor(xyzs2[i - 1].detach(), xyzs2[i].detach(), k)
-        pyr.append(grad.recompute(_corr3d_pool, grad.f_corr3d_pool, pyr[-1], idx))
+        if grad.needs_grad(pyr[-1]):
+            with torch.autocast("cuda", enabled=False):
+                pyr.append(_Corr3dPool.apply(pyr[-1], idx))
+        else:
+            pyr.append(_corr3d_pool(pyr[-1], idx))
     return pyr
+
+
+class _Corr3dPool(torch.autograd.Function):
+    """k-NN mean pooling of the point volume; backward: d vol_in[p, idx[q,j]] += g[p,q] / k (camli_corr3d_pool_backward)."""
+
+    @staticmethod
+    def forward(ctx, vol, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = vol.shape
+        return _corr3d_pool(vol, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        B, n1, n_in = ctx.shape
+        n_out, k = idx.shape[1], idx.shape[2]
+        g = g.contiguous()
+        g_in = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            native.call("camli_corr3d_pool_backward", i32(B), i32(n1), i32(n_in), i32(n_out), i32(k), ptr(g), ptr(idx.contiguous()),
+                        ptr(g_in), stream(), algo_bytes=B * n1 * (n_in + n_out * (1 + 2 * k)) * 4)
+        return g_in, None
 
 
 def _corr3d_pool(vol, idx):
@@ -447,7 +533,48 @@ def corr3d_lookup_rows(xyz1, xyzs2, pyramid, W1, b1, W2, b2):
     xyz1, xyzs2, pyramid = grad.f32(xyz1), [grad.f32(x) for x in xyzs2], [grad.f32(v) for v in pyramid]
     _need_cuda(xyz1, *xyzs2, *pyramid)
     L = len(pyramid)
+    if grad.needs_grad(W1, b1, W2, b2, *pyramid) and not grad.needs_grad(xyz1, *xyzs2):
+        with torch.autocast("cuda", enabled=False):          # (CamLiRAFT: the clouds are warped by a detached flow)
+            return _Corr3dLookup.apply(xyz1, W1, b1, W2, b2, L, *xyzs2, *pyramid)
     return grad.recompute(_corr3d_lookup_rows, grad.f_corr3d_lookup_rows, xyz1, W1, b1, W2, b2, 16, L, *xyzs2, *pyramid)
+
+
+def _xyz_strides(xyzs2):
+    strides = []
+    for x in xyzs2:
+        sb, sd, sp = x.stride()
+        strides += [sb, sp, sd]
+    return strides
+
+
+class _Corr3dLookup(torch.autograd.Function):
+    """Point-correlation lookup with gradients for the volumes and the cost MLP (camli_corr3d_lookup_backward: one
+    launch for all levels, the neighbour search repeated instead of stored)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, W1, b1, W2, b2, L, *rest):
+        ctx.L = L
+        ctx.save_for_backward(xyz1, W1, b1, W2, b2, *rest)
+        return _corr3d_lookup_rows(xyz1, W1, b1, W2, b2, 16, L, *rest)
+
+    @staticmethod
+    def backward(ctx, g):
+        xyz1, W1, b1, W2, b2, *rest = ctx.saved_tensors
+        L = ctx.L
+        xyzs2, pyramid = list(rest[:L]), [v.contiguous() for v in rest[L:]]
+        B, _, n1 = xyz1.shape
+        g = g.contiguous()
+        gvol = [torch.zeros_like(v) for v in pyramid]
+        gW1, gb1, gW2, gb2 = (torch.zeros_like(t, memory_format=torch.contiguous_format) for t in (W1, b1, W2, b2))
+        with torch.cuda.device(g.device):
+            native.call("camli_corr3d_lookup_backward", i32(B), i32(n1), i32(L), ptr(xyz1.contiguous()), _ptr_array(xyzs2),
+                        _int_array(_xyz_strides(xyzs2), ctypes.c_int64), _int_array([x.shape[-1] for x in xyzs2]),
+                        _ptr_array(pyramid), _ptr_array(gvol),
+                        ptr(W1.contiguous()), ptr(b1.contiguous()), ptr(W2.contiguous()), ptr(b2.contiguous()),
+                        ptr(g), i32(g.shape[-1]), ptr(gW1), ptr(gb1), ptr(gW2), ptr(gb2), stream(),
+                        algo_bytes=B * sum(n1 * 12 + x.shape[-1] * 12 + n1 * 16 * 24 + n1 * 128 for x in xyzs2),
+                        flops=B * sum(n1 * x.shape[-1] * 8 + n1 * 16 * 6 * (4 * 32 + 32 * 32) for x in xyzs2))
+        return (None, gW1, gb1, gW2, gb2, None) + (None,) * L + tuple(gvol)
 
 
 def _corr3d_lookup_rows(xyz1, W1, b1, W2, b2, k, L, *rest):
@@ -613,7 +740,35 @@ def clfm_interp(uv, nn_idx, feat3d_rows, score_net, H, W):
     uv, feat3d_rows = grad.f32(uv, feat3d_rows)
     _need_cuda(uv, nn_idx, feat3d_rows)
     (w1, b1), (w2, b2) = score_net[0].folded(), score_net[1].folded()
+    if grad.needs_grad(w1, b1, w2, b2) and not grad.needs_grad(uv, feat3d_rows):
+        with torch.autocast("cuda", enabled=False):          # (CLFM detaches both cross-modal inputs, models/clfm.py:34-38)
+            return _ClfmInterp.apply(uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W)
     return grad.recompute(_clfm_interp, grad.f_clfm_interp, uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W)
+
+
+class _ClfmInterp(torch.autograd.Function):
+    """FusionAwareInterp before out_conv with gradients for the ScoreNet parameters (camli_clfm_interp_backward)."""
+
+    @staticmethod
+    def forward(ctx, uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W):
+        ctx.save_for_backward(uv, nn_idx, feat3d_rows, w1, b1, w2, b2)
+        ctx.hw = (H, W)
+        return _clfm_interp(uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W)
+
+    @staticmethod
+    def backward(ctx, g):
+        uv, nn_idx, feat3d_rows, w1, b1, w2, b2 = ctx.saved_tensors
+        H, W = ctx.hw
+        feat3d_rows = feat3d_rows.contiguous()
+        B, N, C = feat3d_rows.shape
+        g_rows = nhwc_rows(g)                                  # [B,H,W,C] channel-last storage
+        gw1, gb1, gw2, gb2 = (torch.zeros_like(t, memory_format=torch.contiguous_format) for t in (w1, b1, w2, b2))
+        with torch.cuda.device(g.device):
+            native.call("camli_clfm_interp_backward", i32(B), i32(H), i32(W), i32(N), i32(C), ptr(uv.contiguous()),
+                        ptr(nn_idx.contiguous()), ptr(feat3d_rows), i64(C), ptr(w1.contiguous()), ptr(b1.contiguous()),
+                        ptr(w2.contiguous()), ptr(b2.contiguous()), ptr(g_rows), ptr(gw1), ptr(gb1), ptr(gw2), ptr(gb2), stream(),
+                        algo_bytes=B * H * W * (16 + 2 * C * 4), flops=2 * B * H * W * C * 16 * 6)
+        return None, None, None, gw1, gb1, gw2, gb2, None, None
 
 
 def _clfm_interp(uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W):

@@ -267,8 +267,14 @@ class MotionEncoder2D(nn.Module):
             if cf is None:
                 cf = self.flow_features(flow)
             tc.conv2d(tc.conv2d(corr, self.conv_c1, "relu"), self.conv_c2, "relu", out=cf[..., :192])
-            out = torch.nan_to_num(tc.conv2d(cf.permute(0, 3, 1, 2), self.conv, "relu"))
-            return torch.cat([out, flow], dim=1)
+            # the last convolution (ReLU + nan_to_num in its epilogue) and the flow land in one channel-last buffer
+            # [out | flow]: no nan_to_num, cat or layout-conversion kernels
+            B, _, H, W = flow.shape
+            n_out = self.conv.out_channels
+            mf = torch.empty((B, H, W, n_out + 2), dtype=torch.float32, device=flow.device)
+            tc.conv2d(cf.permute(0, 3, 1, 2), self.conv, "relu_fix", out=mf[..., :n_out])
+            mf[..., n_out:].copy_(flow.permute(0, 2, 3, 1))
+            return mf.permute(0, 3, 1, 2)
         c = F.relu(self.conv_c2(F.relu(self.conv_c1(corr))))
         f = F.relu(self.conv_f2(F.relu(self.conv_f1(flow))))
         out = torch.nan_to_num(F.relu(self.conv(torch.cat([c, f], dim=1))))
@@ -284,6 +290,8 @@ class FlowHead2D(nn.Module):
         self.conv2 = nn.Conv2d(hidden_dim, 2, kernel_size=3, padding=1)
 
     def forward(self, x):
+        if tc.fused(x):
+            return tc.conv2d(tc.conv2d(x, self.conv1, "relu"), self.conv2, "none_fix")      # nan_to_num in the epilogue
         return torch.nan_to_num(tc.conv2d(tc.conv2d(x, self.conv1, "relu"), self.conv2).float())
 
 

@@ -19,6 +19,8 @@ _TORCH_ACTS = {
     "leaky_relu": lambda v, s: F.leaky_relu(v, s),
     "tanh": lambda v, s: torch.tanh(v),
     "sigmoid": lambda v, s: torch.sigmoid(v),
+    "relu_fix": lambda v, s: torch.nan_to_num(torch.relu(v)),
+    "none_fix": lambda v, s: torch.nan_to_num(v),
 }
 
 

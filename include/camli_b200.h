@@ -291,6 +291,9 @@ int camli_gru_update(int64_t n, const float* z, const float* h, const float* q, 
 #define CAMLI_ACT_GRU_GATE       5   /* sigmoid(v); columns >= split are multiplied by aux1[p, n - split] (r * h)      */
 #define CAMLI_ACT_GRU_UPDATE     6   /* (1 - z) * h + z * tanh(v) with z = aux1[p, n], h = aux2[p, n]                */
 #define CAMLI_ACT_GRU_UPDATE_FIX 7   /* ... followed by torch.nan_to_num                                              */
+/* OR-ed onto NONE / RELU / LEAKY / TANH / SIGMOID: torch.nan_to_num of the activated value (nan -> 0, +-inf -> +-FLT_MAX),
+ * the guard the reference puts behind its motion encoder and flow heads (models/raft_core.py:164,180) */
+#define CAMLI_ACT_FIX_NONFINITE  16
 
 /* x -> (hi, lo) with hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand split of the 3xTF32
  * tensor-core kernels; used once per weight tensor. */
@@ -365,6 +368,42 @@ int camli_pointconv_dw_gather_max_backward(int B, int N, int S, int K, int k, in
 int camli_conv_small_cin(const float* x, int B, int H, int W, int Cin, int64_t ldx, const float* w, int Cout,
                          int kh, int kw, const float* bias, int act, float slope, float* out, int64_t ldo,
                          void* stream);
+
+/*
+ * Backward kernels of the point-branch / fusion operators (camliflow_b200/csrc/backward_point.cu).  The reference
+ * differentiates these stages through torch autograd (models/utils.py:130-146, models/camliraft_l_core.py:56-98,
+ * models/clfm.py:57-75, models/raft_core.py:65-68); here each gradient is one launch.  Every grad_* output must be
+ * zero-initialised by the caller unless noted; coordinates receive no gradient.
+ *
+ * camli_three_nn_interpolate_backward : grad_feat[b,f,idx_j(q)] += w_j(q) * grad_out[b,f,q]   (same search + weights as
+ *                                       camli_three_nn_interpolate; strides as there)
+ * camli_corr3d_lookup_backward        : grad_volumes[l][b,q,idx_j] = d cost entry (plain stores), and the gradients of the
+ *                                       4 -> 32 -> 32 cost MLP (grad_W1 [32,4], grad_b1 [32], grad_W2 [32,32], grad_b2 [32])
+ * camli_corr3d_pool_backward          : grad_in[b,p,idx[b,q,j]] += grad_out[b,p,q] / k
+ * camli_corr2d_pool_backward          : grad_vol0 (IN/OUT, holds level 0's own gradient) += sum_l up(grad_coarser[l-1]) / 4^l
+ * camli_clfm_interp_backward          : gradients of the ScoreNet parameters (grad_W1 [16,3], grad_b1 [16], grad_W2 [C,16],
+ *                                       grad_b2 [C]); grad_out_rows is [B,H*W,C] channel-last
+ */
+int camli_three_nn_interpolate_backward(int B, int n, int m, int k, int F,
+                                        const float* query_xyz, int64_t q_sb, int64_t q_sp, int64_t q_sd,
+                                        const float* input_xyz, int64_t i_sb, int64_t i_sp, int64_t i_sd,
+                                        const float* grad_out, int64_t g_sb, int64_t g_sc, int64_t g_sp,
+                                        float* grad_feat, int64_t f_sb, int64_t f_sc, int64_t f_sp, void* stream);
+int camli_corr3d_lookup_backward(int B, int n1, int n_levels, const float* xyz1,
+                                 const float* const* xyz2_levels_host, const int64_t* xyz2_strides_host,
+                                 const int* n2_host, const float* const* volumes_host, float* const* grad_volumes_host,
+                                 const float* W1, const float* b1, const float* W2, const float* b2,
+                                 const float* grad_out_rows, int ld_grad,
+                                 float* grad_W1, float* grad_b1, float* grad_W2, float* grad_b2, void* stream);
+int camli_corr3d_pool_backward(int B, int n1, int n_in, int n_out, int k, const float* grad_out,
+                               const int64_t* knn_idx, float* grad_in, void* stream);
+int camli_corr2d_pool_backward(float* grad_vol0, const float* const* grad_coarser_host, int n_levels, int64_t rows,
+                               int h0, int w0, void* stream);
+int camli_clfm_interp_backward(int B, int H, int W, int N, int C, const float* uv, const int64_t* nn_idx,
+                               const float* feat3d_rows, int64_t ld_feat,
+                               const float* W1, const float* b1, const float* W2, const float* b2,
+                               const float* grad_out_rows,
+                               float* grad_W1, float* grad_b1, float* grad_W2, float* grad_b2, void* stream);
 
 /* Tuning switch (no reference counterpart): 1 tags the footprint loads of camli_corr2d_lookup L2 evict-last (meant to keep the
  * ~10 % of the volume pyramid the refinement revisits in the L2 across iterations; measured: no gain, default 0).  Returns the
