@@ -176,7 +176,7 @@ def pairs_per_step(B, world, forwards=1):
     return B * world * forwards
 
 
-TENSOR_KERNELS = ("camli_conv_gemm_fused", "camli_conv_gemm", "camli_allpairs_correlation")
+TENSOR_KERNELS = ("camli_conv_gemm_strided", "camli_conv_gemm_fused", "camli_conv_gemm", "camli_allpairs_correlation")
 NAMED_HBM_KERNELS = (("camli_corr2d_lookup", "corr_lookup"), ("camli_pointconv_dw_gather_max", "knn_gather"))
 
 

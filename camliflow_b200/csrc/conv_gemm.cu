@@ -69,7 +69,8 @@ template <int BN> struct CgCfg {
 
 struct CgParams {
     int B, H, W, Cin, Cout;        // activation geometry, channels
-    int kh, kw;                    // window (odd), "same" padding, stride 1
+    int kh, kw;                    // window (odd), padding k/2
+    int stride;                    // 1 or 2: H, W above are the OUTPUT grid, the input grid is sampled every `stride` pixels
     int th, tw;                    // pixel tile: th * tw = 128
     int tiles_y, tiles_x, tiles_n;
     const float* bias;             // [Cout] or null
@@ -325,7 +326,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     const uint32_t dst = tiles_base + stage * Cfg::kStageBytes;
                     mbar_expect_tx(full, CG_A_BYTES + 2 * W_BYTES);
                     if (tile == blockIdx.x && kb == 0) CG_STAMP(14);
-                    tma_load_4d(dst, &map_x, full, cb * CG_BK, x0 + dx, y0 + dy, b);
+                    tma_load_4d(dst, &map_x, full, cb * CG_BK, x0 * P.stride + dx, y0 * P.stride + dy, b);
                     if (tile == blockIdx.x && kb == 0) CG_STAMP(15);
                     tma_load_2d(dst + CG_A_BYTES * 2, &map_whi, full, tap * P.Cin + cb * CG_BK, nt * BN);
                     tma_load_2d(dst + CG_A_BYTES * 2 + W_BYTES, &map_wlo, full, tap * P.Cin + cb * CG_BK, nt * BN);
@@ -482,10 +483,12 @@ split_tf32_pair_kernel(const float* __restrict__ x, float* __restrict__ hi, floa
 }
 
 int encode_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, int pixel_stride = 1) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return (int)cudaErrorNotSupported;
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    // traversal stride of the two pixel dimensions (a strided convolution reads every `pixel_stride`-th input pixel:
+    // the box then spans pixel_stride * tile pixels and delivers tile of them)
+    const cuuint32_t estr[4] = {1, (cuuint32_t)pixel_stride, (cuuint32_t)pixel_stride, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides_bytes,
                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -554,7 +557,19 @@ extern "C" int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Ci
                                      int act, float slope, float* out, int64_t ldo,
                                      const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,
                                      float* out2, int64_t ldo2, int tile_n, void* stream) {
-    if (B < 0 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin) return CAMLI_EINVAL;
+    return camli_conv_gemm_strided(x, B, H, W, Cin, ldx, w_hi, w_lo, Cout, kh, kw, 1, bias, residual, ldr, act, slope, out, ldo,
+                                   aux1, ld1, aux2, ld2, split, out2, ldo2, tile_n, stream);
+}
+
+extern "C" int camli_conv_gemm_strided(const float* x, int B, int Hin, int Win, int Cin, int64_t ldx,
+                                       const float* w_hi, const float* w_lo, int Cout, int kh, int kw, int stride,
+                                       const float* bias, const float* residual, int64_t ldr,
+                                       int act, float slope, float* out, int64_t ldo,
+                                       const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,
+                                       float* out2, int64_t ldo2, int tile_n, void* stream) {
+    if (stride != 1 && stride != 2) return CAMLI_EUNSUPPORTED;
+    if (B < 0 || Hin < 1 || Win < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin) return CAMLI_EINVAL;
+    const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;       // output grid (padding k/2, odd k)
     if (residual && ldr < Cout) return CAMLI_EINVAL;
     if (act & CAMLI_ACT_FIX_NONFINITE) {            // only NONE / RELU carry the nan_to_num flag on this kernel
         const int base = act & ~CAMLI_ACT_FIX_NONFINITE;
@@ -574,7 +589,7 @@ extern "C" int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Ci
     if ((long long)B * H * W > 2147483647LL) return CAMLI_EUNSUPPORTED;
 
     CgParams P;
-    P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.kh = kh; P.kw = kw;
+    P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.kh = kh; P.kw = kw; P.stride = stride;
     // pixel tile th x tw = 128 with the least padding waste (a linear layer, H = 1, gets 1 x 128)
     int best_th = 1;
     long long best = -1;
@@ -600,10 +615,10 @@ extern "C" int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Ci
 
     CUtensorMap mx, mwh, mwl;
     {
-        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * W * 4, (cuuint64_t)ldx * W * H * 4};
-        const cuuint32_t box[4] = {CG_BK, (cuuint32_t)P.tw, (cuuint32_t)P.th, 1};
-        int rc = encode_map(&mx, x, 4, dims, strides, box);
+        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * Win * 4, (cuuint64_t)ldx * Win * Hin * 4};
+        const cuuint32_t box[4] = {CG_BK, (cuuint32_t)(P.tw * stride), (cuuint32_t)(P.th * stride), 1};
+        int rc = encode_map(&mx, x, 4, dims, strides, box, stride);
         if (rc) return rc;
     }
     {

@@ -275,13 +275,14 @@ def conv_gemm_ok(x_bhwc, kh=1, kw=1):
 
 
 def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residual=None, out=None, tile_n=0,
-              aux1=None, aux2=None, split=0, out2=None):
+              aux1=None, aux2=None, split=0, out2=None, stride=1):
     """Linear layer / stride-1 "same" convolution + bias + residual + activation in one tcgen05 kernel
     (include/camli_b200.h: camli_conv_gemm).  x_bhwc [B,H,W,Cin] channel-last view (a linear layer over rows
     is [1,1,R,K]); w_hi/w_lo [Cout, kh*kw*Cin] from tc_weight(); residual / out [B,H,W,Cout] channel-last views
     (out may be a channel slice of a wider buffer).  act "gru_gate" / "gru_update[_fix]" fuse the ConvGRU
     arithmetic (camli_conv_gemm_fused): aux1 / aux2 [B,H,W,*] channel-last side inputs, columns >= split of a gate
-    convolution go to out2.  Returns out."""
+    convolution go to out2.  stride 2 (padding k/2): the output grid is ceil(H/2) x ceil(W/2) (camli_conv_gemm_strided).
+    Returns out."""
     _need_cuda(x_bhwc, w_hi, w_lo)
     _no_grad("conv_gemm", x_bhwc, w_hi)
     B, H, W, Cin = x_bhwc.shape
@@ -291,23 +292,24 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
     if not ok or Cin % 4:
         raise RuntimeError("conv_gemm: input must be a 16-byte aligned channel-last view with Cin % 4 == 0")
     n_out = split if out2 is not None else Cout
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     if out is None:
-        out = torch.empty((B, H, W, n_out), dtype=torch.float32, device=x_bhwc.device)
-    assert tuple(out.shape) == (B, H, W, n_out)
+        out = torch.empty((B, Ho, Wo, n_out), dtype=torch.float32, device=x_bhwc.device)
+    assert tuple(out.shape) == (B, Ho, Wo, n_out)
     ldo = _pixel_layout(out)[0]
     ldr = 0
     if residual is not None:
-        assert tuple(residual.shape) == (B, H, W, Cout)
+        assert tuple(residual.shape) == (B, Ho, Wo, Cout)
         ldr = _pixel_layout(residual)[0]
     with torch.cuda.device(x_bhwc.device):
-        native.call("camli_conv_gemm_fused", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w_hi), ptr(w_lo),
-                    i32(Cout), i32(kh), i32(kw), ptr(bias), ptr(residual), i64(ldr), i32(ACT_CODES[act]),
+        native.call("camli_conv_gemm_strided", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w_hi), ptr(w_lo),
+                    i32(Cout), i32(kh), i32(kw), i32(stride), ptr(bias), ptr(residual), i64(ldr), i32(ACT_CODES[act]),
                     ctypes.c_float(slope), ptr(out), i64(ldo),
                     ptr(aux1), i64(_pixel_layout(aux1)[0] if aux1 is not None else 0),
                     ptr(aux2), i64(_pixel_layout(aux2)[0] if aux2 is not None else 0), i32(split),
                     ptr(out2), i64(_pixel_layout(out2)[0] if out2 is not None else 0), i32(tile_n), stream(),
-                    algo_bytes=B * H * W * (Cin + Cout) * 4 + Cout * kh * kw * Cin * 4,
-                    flops=2 * B * H * W * Cout * kh * kw * Cin)
+                    algo_bytes=B * (H * W * Cin + Ho * Wo * Cout) * 4 + Cout * kh * kw * Cin * 4,
+                    flops=2 * B * Ho * Wo * Cout * kh * kw * Cin)
     return out
 
 

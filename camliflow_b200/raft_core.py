@@ -53,20 +53,13 @@ class _Bottleneck(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(c_in, c_out, 1, stride, bias=False), nn.BatchNorm2d(c_out))
 
     def _forward_fused(self, x):
-        """conv+BN(+residual)+ReLU groups as single kernels: the stride-1 ones on the tcgen05 implicit-GEMM
-        kernel (fp32-accurate 3xTF32), the two stride-2 ones of layer2.0 through cuDNN's fused epilogues."""
-        one, zero = (1, 1), (0, 0)
+        """conv+BN(+residual)+ReLU groups as single kernels on the tcgen05 implicit-GEMM kernel (fp32-accurate 3xTF32)."""
+        # (the two stride-2 convolutions of layer2.0 included: the kernel's activation tensor map then traverses the
+        # input with a pixel stride of 2)
         y = tc.conv2d(x, self.conv1, "relu", bn=self.bn1)
-        if self.conv2.stride == one:
-            y = tc.conv2d(y, self.conv2, "relu", bn=self.bn2)
-        else:
-            y = torch.cudnn_convolution_relu(y, *_folded(self, "2", self.conv2, self.bn2), self.conv2.stride, one, one, 1)
+        y = tc.conv2d(y, self.conv2, "relu", bn=self.bn2)
         if self.downsample is not None:
-            if self.downsample[0].stride == one:
-                x = tc.conv2d(x, self.downsample[0], None, bn=self.downsample[1])
-            else:
-                w, b = _folded(self, "d", self.downsample[0], self.downsample[1])
-                x = F.conv2d(x, w, b, self.downsample[0].stride)
+            x = tc.conv2d(x, self.downsample[0], None, bn=self.downsample[1])
         return tc.conv2d(y, self.conv3, "relu", bn=self.bn3, residual=x)
 
     def forward(self, x):

@@ -86,8 +86,9 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
 
         w2d, bias = _plain_weight(_key_params(conv.weight, conv.bias, bn), build_small)
         return ops.conv_small_cin(rows, w2d, kh, kw, bias, act, slope, out).permute(0, 3, 1, 2)
-    if (fused(x) and _bn_foldable(bn) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+    if (fused(x) and _bn_foldable(bn) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1) and conv.groups == 1
             and conv.padding == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1 and conv.in_channels % 4 == 0):
+        stride = conv.stride[0]
         rows = x.permute(0, 2, 3, 1)
         if not ops.conv_gemm_ok(rows, kh, kw):
             rows = rows.contiguous()
@@ -98,7 +99,7 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
                 w, b = _fold(conv.weight, conv.bias, bn)
                 return w.permute(0, 2, 3, 1).reshape(O, -1), b
 
-            if O <= 4 and residual is None and O * kh * kw * conv.in_channels * 4 <= 160 * 1024:
+            if stride == 1 and O <= 4 and residual is None and O * kh * kw * conv.in_channels * 4 <= 160 * 1024:
                 w2d, bias = _plain_weight(_key_params(conv.weight, conv.bias, bn), build)
                 return ops.conv_small_n(rows, w2d, kh, kw, bias, act, slope, out).permute(0, 3, 1, 2)
 
@@ -108,7 +109,7 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
                 res = residual.permute(0, 2, 3, 1)
                 if not ops._pixel_layout(res)[1]:
                     res = res.contiguous()
-            y = ops.conv_gemm(rows, w_hi, w_lo, kh, kw, bias, act, slope, res, out)
+            y = ops.conv_gemm(rows, w_hi, w_lo, kh, kw, bias, act, slope, res, out, stride=stride)
             return y.permute(0, 3, 1, 2)
     y = conv(x)
     if bn is not None:

@@ -307,6 +307,52 @@ def test_conv_gemm_tcgen05(dev, B, H, W, Cin, Cout, kh, kw, act, res, tile_n):
     assert out.shape == fp32.shape
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,act,res", [
+    (2, 136, 240, 128, 128, 3, "relu", False),      # layer2.0 conv2 of the ResNet encoder (stride 2 on the 3x3)
+    (1, 136, 240, 256, 512, 1, None, False),        # layer2.0 downsample
+    (2, 37, 61, 64, 96, 3, "relu", True),           # odd input grid: ceil(H/2) x ceil(W/2) outputs, ragged tiles
+    (1, 20, 33, 32, 40, 5, "relu_fix", False),
+])
+def test_conv_gemm_stride2(dev, B, H, W, Cin, Cout, k, act, res):
+    """Stride-2 convolution through the TMA element-stride tensor map against an fp64 convolution."""
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(B, Cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=2, padding=k // 2)
+    r = None
+    if res:
+        r = torch.randn(ref.shape, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        ref = ref + r.double()
+    ref = torch.relu(ref) if act else ref
+    w_hi, w_lo, bias = _tc_weight(w, b)
+    out = _ops().conv_gemm(x.permute(0, 2, 3, 1), w_hi, w_lo, k, k, bias, act, 0.1,
+                           None if r is None else r.permute(0, 2, 3, 1), stride=2).permute(0, 3, 1, 2)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    err = (out.double() - ref).abs().max().item()
+    print("conv_gemm stride 2 %s: max err %.3e" % ((B, H, W, Cin, Cout, k), err))
+    assert err <= 2e-5, err
+
+
+def test_conv_gemm_nan_to_num_epilogue(dev):
+    """act "relu_fix" / "none_fix" = torch.nan_to_num(act(conv)) (models/raft_core.py:164,180): outputs reached by a
+    NaN activation become 0.  (An INFINITE activation turns into NaN inside the tf32 hi/lo split -- inf - inf -- so it
+    also ends as 0 where the reference would write FLT_MAX; neither value means anything downstream.)"""
+    g = torch.Generator().manual_seed(34)
+    x = torch.randn(1, 16, 12, 32, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    x[0, 0, 3, 5] = float("nan")
+    x[0, 1, 7, 9] = float("nan")
+    w = (torch.randn(40, 16, 3, 3, generator=g) / 12).to(dev)
+    w_hi, w_lo, _ = _tc_weight(w, None)
+    for act, fn in (("relu_fix", torch.relu), ("none_fix", lambda v: v)):
+        out = _ops().conv_gemm(x.permute(0, 2, 3, 1), w_hi, w_lo, 3, 3, None, act).permute(0, 3, 1, 2)
+        ref = torch.nan_to_num(fn(torch.nn.functional.conv2d(x, w, padding=1)))
+        assert torch.isfinite(out).all()
+        finite = torch.isfinite(torch.nn.functional.conv2d(x, w, padding=1))
+        assert torch.allclose(out[finite], ref[finite], atol=2e-5)
+        assert torch.equal(out[~finite] == 0, ref[~finite] == 0)         # nan -> 0, +-inf -> +-FLT_MAX (or 0 after relu)
+
+
 def test_conv_gemm_channel_slices(dev):
     """Input read from, and output written into, channel slices of wider channel-last buffers (how the
     update block avoids torch.cat)."""
