@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import tc
 from .camlipwc_l_core import PYRAMID_CHANNELS_3D, Correlation3D, FeaturePyramid3D, FlowEstimator3D
 from .clfm import CLFM
 from .csrc import correlation2d
@@ -99,7 +100,7 @@ class CamLiPWC_Core(nn.Module):
                 feat_2d = self.branch_2d_flow_estimator(x_2d)
                 feat_3d = self.branch_3d_flow_estimator(xyz1, x_3d, knn1)
                 feat_2d, feat_3d = self.estimator_clfm(uv1, feat_2d, feat_3d)
-                delta_2d, delta_3d = self.branch_2d_conv_last(feat_2d), self.branch_3d_conv_last(feat_3d)
+                delta_2d, delta_3d = tc.conv2d(feat_2d, self.branch_2d_conv_last), self.branch_3d_conv_last(feat_3d)
             else:
                 feat_2d, delta_2d = self.branch_2d_flow_estimator(x_2d)
                 feat_3d, delta_3d = self.branch_3d_flow_estimator(xyz1, x_3d, knn1)

@@ -71,6 +71,7 @@ struct CgParams {
     int B, H, W, Cin, Cout;        // activation geometry, channels
     int kh, kw;                    // window (odd), padding k/2
     int stride;                    // 1 or 2: H, W above are the OUTPUT grid, the input grid is sampled every `stride` pixels
+    int dil;                       // dilation: tap (i, j) reads the input at offset (i - kh/2, j - kw/2) * dil
     int th, tw;                    // pixel tile: th * tw = 128
     int tiles_y, tiles_x, tiles_n;
     const float* bias;             // [Cout] or null
@@ -326,7 +327,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     const uint32_t dst = tiles_base + stage * Cfg::kStageBytes;
                     mbar_expect_tx(full, CG_A_BYTES + 2 * W_BYTES);
                     if (tile == blockIdx.x && kb == 0) CG_STAMP(14);
-                    tma_load_4d(dst, &map_x, full, cb * CG_BK, x0 * P.stride + dx, y0 * P.stride + dy, b);
+                    tma_load_4d(dst, &map_x, full, cb * CG_BK, x0 * P.stride + dx * P.dil, y0 * P.stride + dy * P.dil, b);
                     if (tile == blockIdx.x && kb == 0) CG_STAMP(15);
                     tma_load_2d(dst + CG_A_BYTES * 2, &map_whi, full, tap * P.Cin + cb * CG_BK, nt * BN);
                     tma_load_2d(dst + CG_A_BYTES * 2 + W_BYTES, &map_wlo, full, tap * P.Cin + cb * CG_BK, nt * BN);
@@ -557,17 +558,17 @@ extern "C" int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Ci
                                      int act, float slope, float* out, int64_t ldo,
                                      const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,
                                      float* out2, int64_t ldo2, int tile_n, void* stream) {
-    return camli_conv_gemm_strided(x, B, H, W, Cin, ldx, w_hi, w_lo, Cout, kh, kw, 1, bias, residual, ldr, act, slope, out, ldo,
+    return camli_conv_gemm_strided(x, B, H, W, Cin, ldx, w_hi, w_lo, Cout, kh, kw, 1, 1, bias, residual, ldr, act, slope, out, ldo,
                                    aux1, ld1, aux2, ld2, split, out2, ldo2, tile_n, stream);
 }
 
 extern "C" int camli_conv_gemm_strided(const float* x, int B, int Hin, int Win, int Cin, int64_t ldx,
-                                       const float* w_hi, const float* w_lo, int Cout, int kh, int kw, int stride,
+                                       const float* w_hi, const float* w_lo, int Cout, int kh, int kw, int stride, int dilation,
                                        const float* bias, const float* residual, int64_t ldr,
                                        int act, float slope, float* out, int64_t ldo,
                                        const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,
                                        float* out2, int64_t ldo2, int tile_n, void* stream) {
-    if (stride != 1 && stride != 2) return CAMLI_EUNSUPPORTED;
+    if ((stride != 1 && stride != 2) || dilation < 1 || dilation > 64) return CAMLI_EUNSUPPORTED;
     if (B < 0 || Hin < 1 || Win < 1 || Cin < 1 || Cout < 1 || kh < 1 || kw < 1 || ldx < Cin) return CAMLI_EINVAL;
     const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;       // output grid (padding k/2, odd k)
     if (residual && ldr < Cout) return CAMLI_EINVAL;
@@ -589,7 +590,7 @@ extern "C" int camli_conv_gemm_strided(const float* x, int B, int Hin, int Win, 
     if ((long long)B * H * W > 2147483647LL) return CAMLI_EUNSUPPORTED;
 
     CgParams P;
-    P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.kh = kh; P.kw = kw; P.stride = stride;
+    P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.kh = kh; P.kw = kw; P.stride = stride; P.dil = dilation;
     // pixel tile th x tw = 128 with the least padding waste (a linear layer, H = 1, gets 1 x 128)
     int best_th = 1;
     long long best = -1;

@@ -275,7 +275,7 @@ def conv_gemm_ok(x_bhwc, kh=1, kw=1):
 
 
 def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residual=None, out=None, tile_n=0,
-              aux1=None, aux2=None, split=0, out2=None, stride=1):
+              aux1=None, aux2=None, split=0, out2=None, stride=1, dilation=1):
     """Linear layer / stride-1 "same" convolution + bias + residual + activation in one tcgen05 kernel
     (include/camli_b200.h: camli_conv_gemm).  x_bhwc [B,H,W,Cin] channel-last view (a linear layer over rows
     is [1,1,R,K]); w_hi/w_lo [Cout, kh*kw*Cin] from tc_weight(); residual / out [B,H,W,Cout] channel-last views
@@ -303,7 +303,7 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
         ldr = _pixel_layout(residual)[0]
     with torch.cuda.device(x_bhwc.device):
         native.call("camli_conv_gemm_strided", ptr(x_bhwc), i32(B), i32(H), i32(W), i32(Cin), i64(ldx), ptr(w_hi), ptr(w_lo),
-                    i32(Cout), i32(kh), i32(kw), i32(stride), ptr(bias), ptr(residual), i64(ldr), i32(ACT_CODES[act]),
+                    i32(Cout), i32(kh), i32(kw), i32(stride), i32(dilation), ptr(bias), ptr(residual), i64(ldr), i32(ACT_CODES[act]),
                     ctypes.c_float(slope), ptr(out), i64(ldo),
                     ptr(aux1), i64(_pixel_layout(aux1)[0] if aux1 is not None else 0),
                     ptr(aux2), i64(_pixel_layout(aux2)[0] if aux2 is not None else 0), i32(split),

@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import tc
 from .csrc import correlation2d
 from .mlp import Conv2dNormRelu
 from .utils import backwarp_2d, convex_upsample
@@ -24,6 +25,12 @@ class ResidualBlock(nn.Module):
         self.conv1 = Conv2dNormRelu(out_channels, out_channels, kernel_size=3, stride=1, padding=1, norm=norm, act=None)
 
     def forward(self, x):
+        if tc.fused(x) and not isinstance(self.down0, nn.Identity) and self.conv0._foldable():
+            # three kernels: the strided 1x1 shortcut, the strided 3x3, and the second 3x3 with the shortcut and the
+            # leaky ReLU in its epilogue (BatchNorms folded)
+            r = tc.conv2d(x, self.down0.conv_fn, None, bn=self.down0.norm_fn)
+            y = tc.conv2d(x, self.conv0.conv_fn, "leaky_relu", 0.1, bn=self.conv0.norm_fn)
+            return tc.conv2d(y, self.conv1.conv_fn, "leaky_relu", 0.1, bn=self.conv1.norm_fn, residual=r)
         return F.leaky_relu(self.conv1(self.conv0(x)) + self.down0(x), 0.1)
 
 
@@ -70,7 +77,7 @@ class _FlowEstimator2D(nn.Module):
             x4 = self.conv4(torch.cat([x2, x3], dim=1))
             x5 = self.conv5(torch.cat([x3, x4], dim=1))
             feat = torch.cat([x4, x5], dim=1)
-        return feat if self.conv_last is None else (feat, self.conv_last(feat))
+        return feat if self.conv_last is None else (feat, tc.conv2d(feat, self.conv_last))
 
 
 class FlowEstimatorDense2D(_FlowEstimator2D):
@@ -94,7 +101,7 @@ class ContextNetwork2D(nn.Module):
     def forward(self, x):
         for conv in self.convs:
             x = conv(x)
-        return x, self.conv_last(x)
+        return x, tc.conv2d(x, self.conv_last)
 
 
 def up_mask_head():
@@ -109,7 +116,8 @@ def upsample2x(t, scale=1.0):
 def finish_flows_2d(flows_2d, flow_feat, mask_head):
     """Finest level by convex up-sampling (x4), the others bilinearly (pwc_core.py:218-224)."""
     flows = [f.float() for f in flows_2d][::-1]
-    flows[0] = convex_upsample(flows[0], mask_head(flow_feat), scale_factor=4)
+    mask = tc.conv2d(tc.conv2d(flow_feat, mask_head[0], "relu"), mask_head[2]) if tc.fused(flow_feat) else mask_head(flow_feat)
+    flows[0] = convex_upsample(flows[0], mask, scale_factor=4)
     for i in range(1, len(flows)):
         flows[i] = F.interpolate(flows[i] * 4, scale_factor=4, mode="bilinear", align_corners=True)
     return flows

@@ -86,9 +86,17 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
 
         w2d, bias = _plain_weight(_key_params(conv.weight, conv.bias, bn), build_small)
         return ops.conv_small_cin(rows, w2d, kh, kw, bias, act, slope, out).permute(0, 3, 1, 2)
-    if (fused(x) and _bn_foldable(bn) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1) and conv.groups == 1
-            and conv.padding == (kh // 2, kw // 2) and kh % 2 == 1 and kw % 2 == 1 and conv.in_channels % 4 == 0):
+    dil = conv.dilation[0]
+    if fused(x) and conv.in_channels > 4 and x.shape[1] == conv.in_channels and conv.in_channels % 4:
+        x = padded_rows(x)                  # TMA rows are 16-byte granular: zero-pad the channels (one copy), the weight
+                                            # gets matching zero columns below
+    if (fused(x) and _bn_foldable(bn) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (dil, dil) and conv.groups == 1
+            and conv.padding == (dil * (kh // 2), dil * (kw // 2)) and kh % 2 == 1 and kw % 2 == 1
+            and x.shape[1] % 4 == 0 and 0 <= x.shape[1] - conv.in_channels < 8):
         stride = conv.stride[0]
+        # `x` may carry the input channels padded with zeros up to a multiple of 4 (TMA rows are 16-byte granular):
+        # the weight then gets matching zero columns (see padded_rows)
+        cpad = x.shape[1] - conv.in_channels
         rows = x.permute(0, 2, 3, 1)
         if not ops.conv_gemm_ok(rows, kh, kw):
             rows = rows.contiguous()
@@ -97,9 +105,12 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
 
             def build():
                 w, b = _fold(conv.weight, conv.bias, bn)
-                return w.permute(0, 2, 3, 1).reshape(O, -1), b
+                w = w.permute(0, 2, 3, 1)
+                if cpad:
+                    w = F.pad(w, (0, cpad))
+                return w.reshape(O, -1), b
 
-            if stride == 1 and O <= 4 and residual is None and O * kh * kw * conv.in_channels * 4 <= 160 * 1024:
+            if stride == 1 and dil == 1 and O <= 4 and residual is None and O * kh * kw * x.shape[1] * 4 <= 160 * 1024:
                 w2d, bias = _plain_weight(_key_params(conv.weight, conv.bias, bn), build)
                 return ops.conv_small_n(rows, w2d, kh, kw, bias, act, slope, out).permute(0, 3, 1, 2)
 
@@ -109,7 +120,7 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
                 res = residual.permute(0, 2, 3, 1)
                 if not ops._pixel_layout(res)[1]:
                     res = res.contiguous()
-            y = ops.conv_gemm(rows, w_hi, w_lo, kh, kw, bias, act, slope, res, out, stride=stride)
+            y = ops.conv_gemm(rows, w_hi, w_lo, kh, kw, bias, act, slope, res, out, stride=stride, dilation=dil)
             return y.permute(0, 3, 1, 2)
     y = conv(x)
     if bn is not None:
@@ -121,6 +132,18 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
         out.copy_(y.permute(0, 2, 3, 1))
         return out.permute(0, 3, 1, 2)
     return y
+
+
+def padded_rows(x, multiple=4):
+    """Logical [B,C,H,W] tensor -> channel-last storage with C padded by zeros to a multiple of `multiple`, returned as the
+    logical [B,C+pad,H,W] view conv2d accepts for a layer whose in_channels is not 16-byte granular."""
+    B, C, H, W = x.shape
+    pad = (-C) % multiple
+    buf = torch.empty((B, H, W, C + pad), dtype=torch.float32, device=x.device)
+    buf[..., :C].copy_(x.permute(0, 2, 3, 1))
+    if pad:
+        buf[..., C:].zero_()
+    return buf.permute(0, 3, 1, 2)
 
 
 def conv2d_weights(x, weight, bias, padding, act=None, slope=0.1, out=None, residual=None):

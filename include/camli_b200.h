@@ -332,12 +332,14 @@ int camli_conv_gemm_fused(const float* x, int B, int H, int W, int Cin, int64_t 
                           const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,
                           float* out2, int64_t ldo2, int tile_n, void* stream);
 
-/* The same kernel for a STRIDED convolution (stride 1 or 2, padding k/2): H_in x W_in is the input grid, the output grid
- * is ((H_in - 1) / stride + 1) x ((W_in - 1) / stride + 1); residual / out / aux are indexed by output pixel.  The
- * activation operand is fetched through a TMA tensor map whose pixel dimensions have traversal stride `stride`
- * (reference: the stride-2 3x3 and 1x1 convolutions of the ResNet stage `layer2.0`, models/raft_core.py:10-22). */
+/* The same kernel for a STRIDED and / or DILATED convolution (stride 1 or 2, padding dilation * (k/2)): H_in x W_in is
+ * the input grid, the output grid is ((H_in - 1) / stride + 1) x ((W_in - 1) / stride + 1); residual / out / aux are
+ * indexed by output pixel.  The activation operand is fetched through a TMA tensor map whose pixel dimensions have
+ * traversal stride `stride`; a dilated tap is just a larger coordinate offset of the box (reference: the stride-2
+ * convolutions of the ResNet stage `layer2.0`, models/raft_core.py:10-22, and of PWC's feature pyramid,
+ * models/pwc_core.py:9-29; the dilated context network, models/pwc_core.py:128-141). */
 int camli_conv_gemm_strided(const float* x, int B, int H_in, int W_in, int Cin, int64_t ldx,
-                            const float* w_hi, const float* w_lo, int Cout, int kh, int kw, int stride,
+                            const float* w_hi, const float* w_lo, int Cout, int kh, int kw, int stride, int dilation,
                             const float* bias, const float* residual, int64_t ldr,
                             int act, float slope, float* out, int64_t ldo,
                             const float* aux1, int64_t ld1, const float* aux2, int64_t ld2, int split,

@@ -59,7 +59,7 @@ def main():
     H, W, N, iters, B = bench.WORKLOADS[args.workload]
     dev = torch.device("cuda:0")
     torch.backends.cudnn.benchmark = True
-    model = seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=iters)), seed=0)
+    model = bench.build_model(args.workload)
     engine = FlowEngine(model, B, H, W, N, device=dev, use_graph=True)
     engine.load({k: v.pin_memory() for k, v in bench.synthetic_inputs(B, H, W, N, 0).items()})
     out = {}
