@@ -353,6 +353,27 @@ def conv_small_cin(x_bhwc, w2d, kh, kw, bias=None, act=None, slope=0.1, out=None
     return out
 
 
+def stem_conv_pool(x_bhwc, w_ohwi, bias):
+    """ResNet stem (7x7 stride-2 convolution 3 -> 64 with folded BatchNorm, ReLU, 3x3 stride-2 max-pool) in one kernel
+    (camli_stem_conv_pool): x_bhwc [B,H,W,3] channel-last view -> [B,Hp,Wp,64] channel-last."""
+    _need_cuda(x_bhwc, w_ohwi, bias)
+    _no_grad("stem_conv_pool", x_bhwc, w_ohwi)
+    B, H, W, C = x_bhwc.shape
+    assert C == 3 and tuple(w_ohwi.shape) == (64, 7, 7, 3) and w_ohwi.is_contiguous() and bias.is_contiguous()
+    ldx = _pixel_layout(x_bhwc)[0]
+    sb, sh, sw, sc = x_bhwc.stride()
+    if not (sc == 1 and sw == ldx and sh == W * ldx and (B == 1 or sb == H * W * ldx)):
+        x_bhwc = x_bhwc.contiguous()
+        ldx = 3
+    Hc, Wc = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    Hp, Wp = (Hc - 1) // 2 + 1, (Wc - 1) // 2 + 1
+    out = torch.empty((B, Hp, Wp, 64), dtype=torch.float32, device=x_bhwc.device)
+    with torch.cuda.device(out.device):
+        native.call("camli_stem_conv_pool", ptr(x_bhwc), i32(B), i32(H), i32(W), i64(ldx), ptr(w_ohwi), ptr(bias), ptr(out),
+                    i64(64), stream(), algo_bytes=B * (H * W * 3 + Hp * Wp * 64) * 4, flops=2 * B * Hc * Wc * 64 * 147)
+    return out
+
+
 def linear_rows(x, w_hi, w_lo, bias=None, act=None, slope=0.1, residual=None):
     """x [..., K] contiguous rows -> [..., N] through conv_gemm (1x1)."""
     K = x.shape[-1]

@@ -96,11 +96,15 @@ class Encoder2D(nn.Module):
         return self
 
     def forward(self, x):
-        if _fused_inference(x):
-            x = torch.cudnn_convolution_relu(x, *_folded(self, "stem", self.conv1, self.bn1), (2, 2), (3, 3), (1, 1), 1)
+        if _fused_inference(x) and tc.fused(x):
+            # stem convolution + folded BatchNorm + ReLU + max-pool: one CUDA-core kernel (3 input channels)
+            w, b = _folded(self, "stem", self.conv1, self.bn1)
+            cache = self.__dict__.setdefault("_stem_cache", {})
+            if cache.get("key") is not w:
+                cache["key"], cache["w"] = w, w.permute(0, 2, 3, 1).contiguous()
+            x = ops.stem_conv_pool(x.permute(0, 2, 3, 1), cache["w"], b).permute(0, 3, 1, 2)
         else:
-            x = F.relu(self.bn1(self.conv1(x)), inplace=True)
-        x = F.max_pool2d(x, 3, 2, 1)
+            x = F.max_pool2d(F.relu(self.bn1(self.conv1(x)), inplace=True), 3, 2, 1)
         return self.align(self.layer2(self.layer1(x)))
 
 

@@ -383,6 +383,15 @@ int camli_conv_small_cin(const float* x, int B, int H, int W, int Cin, int64_t l
                          void* stream);
 
 /*
+ * ResNet stem in one kernel: 7x7 stride-2 padding-3 convolution 3 -> 64 (eval-mode BatchNorm folded into w / bias) + ReLU
+ * + 3x3 stride-2 padding-1 max-pool (reference: conv1 / bn1 / relu / maxpool of the mmdet ResNet-50 behind
+ * models/raft_core.py:10-22,35-38).  x [B,H,W,ldx>=3] channel-last, w_ohwi [64,7,7,3], bias [64],
+ * out [B,Hp,Wp,ldo>=64] with Hp = ((H-1)/2)/2 + 1 rounded like torch (H = 544 -> 136).  fp32 FMA on the CUDA cores.
+ */
+int camli_stem_conv_pool(const float* x, int B, int H, int W, int64_t ldx, const float* w_ohwi, const float* bias,
+                         float* out, int64_t ldo, void* stream);
+
+/*
  * Backward kernels of the point-branch / fusion operators (camliflow_b200/csrc/backward_point.cu).  The reference
  * differentiates these stages through torch autograd (models/utils.py:130-146, models/camliraft_l_core.py:56-98,
  * models/clfm.py:57-75, models/raft_core.py:65-68); here each gradient is one launch.  Every grad_* output must be

@@ -1,9 +1,11 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -30 > gpurun_out/tmp_pytest.log
-tail -4 gpurun_out/tmp_pytest.log; grep "camlipwc" gpurun_out/tmp_pytest.log | head
-timeout 600 python bench.py --workload c3 --steps 3 --warmup 3 --pairs-per-step 4 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -3 gpurun_out/bench_c3.err
+tail -4 gpurun_out/tmp_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-training-block > gpurun_out/tmp_bench.json 2> gpurun_out/tmp_bench.err; tail -3 gpurun_out/tmp_bench.err
 python - <<'PY'
 import json
-b=json.load(open("gpurun_out/bench_c3.json"))
-print("c3 value %.1f e2e %.1f latency %.2f ms/pair" % (b["value"], b["e2e"]["value"], b["latency"]["ms_per_pair"]), b["roofline"]["kernel"], b["roofline"]["frac"])
+b=json.loads(open("gpurun_out/tmp_bench.json").read().strip().splitlines()[-1])
+print('c2 value %.1f e2e %.1f latency %.2f ms' % (b['value'], b['e2e']['value'], b['latency']['ms_per_pair']))
+r=b['roofline']; print(r['kernel'], 'frac %.3f fp32eq %.1f share %.2f'%(r['frac'], r['fp32_equivalent_TFLOPs'], r['share_of_step']))
+print({k:(round(v['avg_us'],1), v['launches']) for k,v in r['all'].items() if 'stem' in k})
 PY

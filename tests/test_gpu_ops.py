@@ -353,6 +353,21 @@ def test_conv_gemm_nan_to_num_epilogue(dev):
         assert torch.equal(out[~finite] == 0, ref[~finite] == 0)         # nan -> 0, +-inf -> +-FLT_MAX (or 0 after relu)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 544, 960), (1, 160, 224), (1, 75, 133)])
+def test_stem_conv_pool(dev, B, H, W):
+    """Fused ResNet stem (7x7 s2 conv + bias + ReLU + 3x3 s2 max-pool, fp32 FMA) against torch in fp64."""
+    g = torch.Generator().manual_seed(35)
+    x = torch.randn(B, 3, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 3, 7, 7, generator=g) / 12).to(dev)
+    b = torch.randn(64, generator=g).to(dev)
+    out = _ops().stem_conv_pool(x.permute(0, 2, 3, 1), w.permute(0, 2, 3, 1).contiguous(), b).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=2, padding=3)), 3, 2, 1)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    err = (out.double() - ref).abs().max().item()
+    print("stem %s: max err %.3e" % ((B, H, W), err))
+    assert err <= 2e-5, err
+
+
 def test_conv_gemm_channel_slices(dev):
     """Input read from, and output written into, channel slices of wider channel-last buffers (how the
     update block avoids torch.cat)."""
