@@ -3,7 +3,7 @@ learnable cost volume, PointConv flow estimator."""
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, tc
 from .mlp import Conv1dNormRelu, MLP1d, MLP2d
 from .point_conv import PointConv
 from .utils import backwarp_3d, k_nearest_neighbor, knn_interpolation
@@ -25,6 +25,13 @@ class FeaturePyramid3D(nn.Module):
 
     def forward(self, xyzs):
         assert len(xyzs) == len(self.pyramid_mlps) + 1
+        if tc.fused(xyzs[0]):          # channel-last throughout: every 1x1 layer is one tensor-core GEMM (see Encoder3D)
+            rows = self.level0_mlp.forward_rows(xyzs[0].transpose(1, 2))
+            feats = [ops.cf_of(rows)]
+            for i, (mlp, conv) in enumerate(zip(self.pyramid_mlps, self.pyramid_convs)):
+                rows = conv.forward_rows(xyzs[i], mlp.forward_rows(rows), xyzs[i + 1])
+                feats.append(ops.cf_of(rows))
+            return feats
         feats = [self.level0_mlp(xyzs[0])]
         for i, (mlp, conv) in enumerate(zip(self.pyramid_mlps, self.pyramid_convs)):
             feats.append(conv(xyzs[i], mlp(feats[-1]), xyzs[i + 1]))

@@ -26,6 +26,15 @@ class Encoder3D(nn.Module):
         """`knn_tables[i]` (optional): the level i -> i+1 neighbour table [B,S,>=k]; it depends on the geometry
         only, so encoders that see the same cloud (fnet / cnet of frame 1) share one search."""
         assert len(xyzs) == len(self.mlps) + 1
+        if tc.fused(xyzs[0]):
+            # channel-last throughout: every 1x1 layer is one tensor-core GEMM with its activation in the epilogue (the
+            # channel-first form runs them as cuDNN Conv1d + separate activation kernels)
+            rows = self.level0_mlp.forward_rows(xyzs[0].transpose(1, 2))
+            feats = [ops.cf_of(rows)]
+            for i, (mlp, conv) in enumerate(zip(self.mlps, self.convs)):
+                rows = conv.forward_rows(xyzs[i], mlp.forward_rows(rows), xyzs[i + 1], None if knn_tables is None else knn_tables[i])
+                feats.append(ops.cf_of(rows))
+            return feats
         feats = [self.level0_mlp(xyzs[0])]
         for i, (mlp, conv) in enumerate(zip(self.mlps, self.convs)):
             feats.append(conv(xyzs[i], mlp(feats[-1]), xyzs[i + 1], None if knn_tables is None else knn_tables[i]))

@@ -45,12 +45,19 @@ class PointConv(nn.Module):
         self.act = act
         self._slope = {"relu": 0.0, "leaky_relu": 0.1, None: 1.0}[act]
 
-    def forward(self, xyz, features, sampled_xyz=None, knn_indices=None):
+    def forward_rows(self, xyz, feat_rows, sampled_xyz=None, knn_indices=None):
+        """Channel-last variant: feat_rows [B,N,C] -> rows [B,S,O] (inference fast path of the encoders)."""
+        return self.forward(xyz, None, sampled_xyz, knn_indices, feat_rows=feat_rows).transpose(1, 2)
+
+    def forward(self, xyz, features, sampled_xyz=None, knn_indices=None, feat_rows=None):
         """xyz [B,3,N], features [B,C,N], sampled_xyz [B,3,S] -> [B,O,S]."""
         if sampled_xyz is None:
             sampled_xyz = xyz
         table = _neighbor_table(xyz, sampled_xyz, knn_indices, self.k)
-        rows = ops.rows_of(torch.cat([xyz, features], dim=1))                      # [B,N,3+C]
+        if feat_rows is not None:
+            rows = torch.cat([xyz.transpose(1, 2), feat_rows], dim=-1)                 # [B,N,3+C]
+        else:
+            rows = ops.rows_of(torch.cat([xyz, features], dim=1))                      # [B,N,3+C]
         grouped = ops.pointconv_group(rows, sampled_xyz, table, self.k, self.weight_net, self._slope)
         n = self.norm_fn
         if tc.fused(grouped) and (isinstance(n, nn.Identity) or (isinstance(n, nn.BatchNorm1d) and not n.training)):

@@ -6,6 +6,4 @@ python - <<'PY'
 import json
 b=json.loads(open("gpurun_out/tmp_bench.json").read().strip().splitlines()[-1])
 print('c2 value %.1f e2e %.1f latency %.2f ms' % (b['value'], b['e2e']['value'], b['latency']['ms_per_pair']))
-r=b['roofline']; print(r['kernel'], 'frac %.3f fp32eq %.1f share %.2f'%(r['frac'], r['fp32_equivalent_TFLOPs'], r['share_of_step']))
-print({k:(round(v['avg_us'],1), v['launches']) for k,v in r['all'].items() if 'stem' in k})
 PY
