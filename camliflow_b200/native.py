@@ -97,6 +97,11 @@ def profile_end():
         us = [s.elapsed_time(e) * 1e3 for s, e, _, _ in recs]
         out[name] = {"launches": len(recs), "avg_us": sum(us) / len(us), "total_us": sum(us),
                      "bytes": sum(r[2] for r in recs) / len(recs), "flops": sum(r[3] for r in recs) / len(recs)}
+        groups = {}                                     # the same per problem size (algorithmic bytes, flops)
+        for t, (_, _, by, fl) in zip(us, recs):
+            groups.setdefault((by, fl), []).append(t)
+        out[name]["by_size"] = [{"bytes": by, "flops": fl, "launches": len(ts), "avg_us": sum(ts) / len(ts), "min_us": min(ts)}
+                                for (by, fl), ts in sorted(groups.items(), reverse=True)]
     return out
 
 

@@ -716,7 +716,9 @@ def _pointconv_dw_gather_max(feat_rows, weights, knn_idx, k):
     with torch.cuda.device(out.device):
         native.call("camli_pointconv_dw_gather_max", i32(B), i32(N), i32(S), i32(K), i32(k), i32(O), ptr(feat_rows), i64(O),
                     ptr(weights), ptr(knn_idx), ptr(out), i64(O), stream(),
-                    algo_bytes=B * S * (k * (2 * O * 4 + 8) + O * 4), flops=B * S * k * O * 2)
+                    # gathered neighbour features + indices read, reduced rows written.  (The kernel also streams
+                    # the cached WeightNet rows, another B*S*k*O*4 bytes the reference computes in a separate op.)
+                    algo_bytes=B * S * (k * (O * 4 + 8) + O * 4), flops=B * S * k * O * 2)
     return out
 
 
