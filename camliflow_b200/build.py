@@ -12,7 +12,8 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "_build", "libcamli_b200.so")
+# CAMLI_LIB_PATH: load / build another copy of the library (A/B experiments with -D switches, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("CAMLI_LIB_PATH") or os.path.join(PKG_DIR, "_build", "libcamli_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -42,7 +43,8 @@ def build_library(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libcamli_b200.so")
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CAMLI_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB_PATH] + sources()
     subprocess.check_call(cmd)
     return LIB_PATH
 

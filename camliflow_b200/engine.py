@@ -9,8 +9,12 @@ from . import native
 
 class FlowEngine:
     def __init__(self, model, batch, height, width, n_points, device="cuda:0", use_graph=True, warmup=2,
-                 channels_last=True):
+                 channels_last=True, tile_policy=None):
+        """`tile_policy`: "latency" for an engine that runs ONE graph at a time (64-wide tiles for the layers that would
+        otherwise leave half of the SMs idle), "throughput" (default of ops.TILE_POLICY) for engines that share the GPU
+        with other graphs in flight (EnginePool)."""
         self.device = torch.device(device)
+        self.tile_policy = tile_policy
         self.model = model.to(self.device).eval()
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
@@ -29,8 +33,15 @@ class FlowEngine:
 
     # ------------------------------------------------------------------ setup
     def _forward_static(self):
-        with torch.no_grad():
-            out = self.model(self.dev_in)
+        from . import ops
+        old = ops.TILE_POLICY
+        if self.tile_policy is not None:
+            ops.TILE_POLICY = self.tile_policy
+        try:
+            with torch.no_grad():
+                out = self.model(self.dev_in)
+        finally:
+            ops.TILE_POLICY = old
         if self.dev_out is None:
             self.dev_out = {k: torch.empty_like(v) for k, v in out.items()}
         for k in self.dev_out:

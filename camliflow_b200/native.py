@@ -65,7 +65,7 @@ def check(code, what):
 _profile = None   # name -> [(start_event, end_event, algorithmic_bytes, flops)] while profiling
 
 
-def call(name, *args, algo_bytes=0, flops=0):
+def call(name, *args, algo_bytes=0, flops=0, shape=None):
     """Invoke entry point `name` of the library on the current stream; raise on a non-zero
     return code.  While profiling (profile_begin/profile_end) every call is bracketed by CUDA
     events recorded on the stream it launches on."""
@@ -74,11 +74,14 @@ def call(name, *args, algo_bytes=0, flops=0):
         check(fn(*args), name)
         return
     st = torch.cuda.current_stream()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # inside a stream capture the events become event-record NODES of the graph (external=True): after a replay they
+    # time the kernel as it runs in the graph, back to back with its neighbours -- not an eager launch on an idle GPU
+    ext = torch.cuda.is_current_stream_capturing()
+    s, e = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
     s.record(st)
     code = fn(*args)
     e.record(st)
-    _profile.setdefault(name, []).append((s, e, algo_bytes, flops))
+    _profile.setdefault(name, []).append((s, e, algo_bytes, flops, shape))
     check(code, name)
 
 
@@ -94,14 +97,15 @@ def profile_end():
     torch.cuda.synchronize()
     out = {}
     for name, recs in (prof or {}).items():
-        us = [s.elapsed_time(e) * 1e3 for s, e, _, _ in recs]
+        us = [r[0].elapsed_time(r[1]) * 1e3 for r in recs]
         out[name] = {"launches": len(recs), "avg_us": sum(us) / len(us), "total_us": sum(us),
                      "bytes": sum(r[2] for r in recs) / len(recs), "flops": sum(r[3] for r in recs) / len(recs)}
         groups = {}                                     # the same per problem size (algorithmic bytes, flops)
-        for t, (_, _, by, fl) in zip(us, recs):
-            groups.setdefault((by, fl), []).append(t)
-        out[name]["by_size"] = [{"bytes": by, "flops": fl, "launches": len(ts), "avg_us": sum(ts) / len(ts), "min_us": min(ts)}
-                                for (by, fl), ts in sorted(groups.items(), reverse=True)]
+        for t, (_, _, by, fl, shp) in zip(us, recs):
+            groups.setdefault((by, fl, shp), []).append(t)
+        out[name]["by_size"] = [{"bytes": by, "flops": fl, "shape": shp, "launches": len(ts), "avg_us": sum(ts) / len(ts),
+                                 "min_us": min(ts)}
+                                for (by, fl, shp), ts in sorted(groups.items(), key=lambda kv: kv[0][:2], reverse=True)]
     return out
 
 

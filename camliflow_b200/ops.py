@@ -266,6 +266,12 @@ def _pixel_layout(t):
     return ld, ok and ld % 4 == 0 and t.data_ptr() % 16 == 0
 
 
+# "throughput" (default): the widest N tile that C_out fills -- fewest CTAs, most SMs left to the other stream / the other
+# graphs in flight.  "latency": layers of <= 74 pixel tiles with 64 < C_out <= 128 and a long k-loop use 64-wide tiles (twice
+# the CTAs, ~15-30 % shorter).  A property of the graph being captured: FlowEngine(tile_policy=...) sets it around its capture.
+TILE_POLICY = os.environ.get("CAMLI_TILE_POLICY", "throughput")
+
+
 def conv_gemm_ok(x_bhwc, kh=1, kw=1):
     """Whether conv_gemm can take this input directly (else callers keep the cuDNN / cuBLAS route)."""
     if not (x_bhwc.is_cuda and x_bhwc.dtype == torch.float32 and x_bhwc.dim() == 4):
@@ -293,6 +299,9 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
         raise RuntimeError("conv_gemm: input must be a 16-byte aligned channel-last view with Cin % 4 == 0")
     n_out = split if out2 is not None else Cout
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if tile_n == 0 and TILE_POLICY == "latency" and 64 < Cout <= 128 and B * Ho * Wo <= 74 * 128 and kh * kw * Cin >= 512:
+        # one graph at a time: a 128-wide tile would leave half of the SMs idle -- two 64-wide tiles per pixel tile
+        tile_n = 64
     if out is None:
         out = torch.empty((B, Ho, Wo, n_out), dtype=torch.float32, device=x_bhwc.device)
     assert tuple(out.shape) == (B, Ho, Wo, n_out)
@@ -309,7 +318,7 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
                     ptr(aux2), i64(_pixel_layout(aux2)[0] if aux2 is not None else 0), i32(split),
                     ptr(out2), i64(_pixel_layout(out2)[0] if out2 is not None else 0), i32(tile_n), stream(),
                     algo_bytes=B * (H * W * Cin + Ho * Wo * Cout) * 4 + Cout * kh * kw * Cin * 4,
-                    flops=2 * B * Ho * Wo * Cout * kh * kw * Cin)
+                    flops=2 * B * Ho * Wo * Cout * kh * kw * Cin, shape=(B * Ho * Wo, Cout, kh * kw * Cin))   # GEMM M, N, K
     return out
 
 

@@ -19,7 +19,8 @@ def main():
                                               (1, 1, 2048, 384, 128, 1, 1, 128), (1, 68, 120, 256, 192, 3, 3, 0),
                                               (1, 68, 120, 256, 128, 1, 5, 0), (1, 68, 120, 256, 128, 1, 5, 64),
                                               (1, 68, 120, 256, 126, 3, 3, 64), (1, 68, 120, 128, 128, 1, 1, 0),
-                                              (1, 1, 2048, 4, 32, 1, 1, 0)]:
+                                              (1, 1, 2048, 4, 32, 1, 1, 0), (4, 68, 120, 256, 192, 3, 3, 0),
+                                              (4, 68, 120, 128, 128, 1, 1, 0), (2, 136, 240, 64, 64, 3, 3, 0)]:
         x = torch.randn(B, H, W, Ci, generator=g).to(dev)
         wt = (torch.randn(Co, kh * kw * Ci, generator=g) / (kh * kw * Ci) ** 0.5).to(dev)
         w_hi, w_lo, _ = ops.tc_weight([wt], lambda: (wt, None))
@@ -28,6 +29,10 @@ def main():
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        # accuracy against an fp64 convolution of the same operands
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wt.view(Co, kh, kw, Ci).permute(0, 3, 1, 2).double(),
+                                         padding=(kh // 2, kw // 2)).relu().permute(0, 2, 3, 1)
+        err = float((out.double() - ref).abs().max() / ref.pow(2).mean().sqrt())
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n = 50
         s.record()
@@ -55,8 +60,8 @@ def main():
         t = buf.cpu().tolist()
         t0 = t[0]
         rel = lambda i: (t[i] - t0) if t[i] else None  # noqa: E731
-        print("== %s tile_n=%d: warm back-to-back %.1f us/launch eager, %.1f us/launch in a graph" %
-              ((B, H, W, Ci, Co, kh, kw), tile_n, per, per_g))
+        print("== %s tile_n=%d: warm back-to-back %.1f us/launch eager, %.1f us/launch in a graph, max err / rms %.2e" %
+              ((B, H, W, Ci, Co, kh, kw), tile_n, per, per_g, err))
         print("   setup done %s | cfull committed %s | cfull seen %s | tile stored %s | exit %s  (cycles)" %
               (rel(1), rel(8), rel(9), rel(10), rel(11)))
         print("   epilogue: corr loaded %s, bias/residual done %s | producer: armed %s, first TMA issued %s" %
