@@ -527,6 +527,8 @@ def run_train(args, rank, world, local_rank, steps=None, warmup=None, workload=N
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
     precision = args.train_precision
+    from camliflow_b200 import tc
+    tc.TRAIN_DENSE = args.train_dense
     torch.backends.cudnn.allow_tf32 = precision != "fp32"
     torch.backends.cuda.matmul.allow_tf32 = precision != "fp32"
     model = build_model(workload).to(dev).train()
@@ -593,12 +595,18 @@ def run_train(args, rank, world, local_rank, steps=None, warmup=None, workload=N
         "metric": "CamLiRAFT training frame-pairs/sec 960x540+8192pts", "value": pairs * steps / (ms_dev / 1e3),
         "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16 autocast (fp32 islands as in the reference: fused point / correlation operators, losses)",
+        "dtype": {"bf16": ("bf16 autocast; dense layers, fused point / correlation operators and losses are fp32 islands "
+                           "(hand-written 3xTF32 tensor-core kernels, forward and backward)" if args.train_dense == "tcgen05" else
+                           "bf16 autocast (fp32 islands as in the reference: fused point / correlation operators, losses)"),
                   "tf32": "f32 (tf32 library layers)", "fp32": "f32"}[precision], "data": "synthetic",
         "config": {"workload": workload_name(workload), "pairs_per_step": pairs,
                    "parallelism": "dp%d (gradient all-reduce over NCCL, %.1f MB fp32 per step)" % (world, grad_bytes / 1e6),
                    "l2": "working set (activations of %d iterations) larger than L2" % iters,
-                   "step": mode, "precision": precision, "grad_clip": 1.0, "final_loss": float(losses[-1])},
+                   "step": mode, "precision": precision, "grad_clip": 1.0, "final_loss": float(losses[-1]),
+                   "dense_layers": ("tcgen05: grad.DenseFn -- camli_conv_gemm forward, camli_transpose_split + camli_conv_gemm (mirrored "
+                                    "weights) + camli_conv_wgrad backward, fp32-accurate; layers outside the kernels' coverage "
+                                    "(stride 2, C_in % 4 != 0) through cuDNN" if args.train_dense == "tcgen05" else
+                                    "library: cuDNN / cuBLAS under autograd (bf16 under autocast)")},
         "e2e": {"value": pairs * steps / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": sum(v.numel() * 4 for v in pinned.values()), "d2h_bytes_per_step": 4},
         "gpu_launches": launches * steps, "clocks": clocks,
@@ -622,6 +630,9 @@ def main():
                          "reference trains with when amp is off) or strict fp32")
     ap.add_argument("--concurrent", type=int, default=3,
                     help="engines (CUDA graphs of batch B) in flight for the throughput figures (EnginePool); 1 = single engine")
+    ap.add_argument("--train-dense", default="tcgen05", choices=["tcgen05", "library"],
+                    help="dense layers of the training step: hand-written tensor-core kernels forward + backward (default), or "
+                         "cuDNN / cuBLAS under autograd (A/B)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training-block", action="store_true",

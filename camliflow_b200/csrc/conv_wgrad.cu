@@ -1,0 +1,357 @@
+// Weight gradient of the implicit-GEMM convolution / linear layer (camli_conv_gemm) on the 5th-generation tensor
+// cores: the training-side counterpart of conv_gemm.cu.  In the reference every dense layer's backward is a cuDNN
+// wgrad / cuBLAS GEMM chosen by autograd (models/raft_core.py:110-197, models/mlp.py:41-128, train.py:143-171).
+//
+//   dW[n, tap, c] = sum_p  G[p, n] * X[p (+) tap, c]          G = dL/d(pre-activation) [B*H*W, Cout], X [B*H*W, Cin]
+//
+// As a GEMM the reduction runs over the PIXELS, the dimension both tensors are strided in.  A pre-pass
+// (camli_transpose_split) therefore writes each operand once more as [C, B, H, W] -- pixel-contiguous, i.e. K-major for
+// the tensor core -- already split into tf32 hi / lo parts (3xTF32: hi*hi + hi*lo + lo*hi, fp32-level accuracy); for G it
+// also applies the activation derivative and emits the row-major gradient the data-gradient convolution reads.
+//
+// Kernel (persistent, one CTA per SM, TMA + tcgen05 + TMEM, same skeleton as allpairs_gemm.cu):
+//   * tile = (tap, 128 output channels, 128 input channels, K split); a k-block is 32 consecutive pixels of one image row,
+//     fetched by 5-D tensor maps (W, H, B, C, shift) with a (32, 1, 1, 128, 1) box.  The vertical tap offset is a coordinate
+//     offset of the X box (rows outside the image are skipped: they contribute nothing); the horizontal one cannot be -- a TMA
+//     box must start 16-byte aligned in the contiguous dimension, and a one-pixel shift is 4 bytes -- so the pre-pass writes
+//     X^T once per horizontal tap offset, already shifted (zero outside the row); the ragged row end (W % 32) is TMA's
+//     out-of-bounds fill;
+//   * the pixel range is split over `splits` CTAs per tile so that every SM has work (a 128x128 tile of a 1x1 layer would
+//     otherwise be ONE CTA walking all pixels); partial tiles are added to the zeroed dW with 128-bit `red.global.add`.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace {
+
+using namespace camli_tc;
+
+constexpr int WG_BM = 128, WG_BN = 128, WG_BK = 32;
+constexpr int WG_STAGES = 3;
+constexpr int WG_TILE_BYTES = WG_BM * WG_BK * 4;             // 16 KB
+constexpr int WG_STAGE_BYTES = 4 * WG_TILE_BYTES;            // G_hi, G_lo, X_hi, X_lo
+constexpr int WG_THREADS = 192;
+constexpr int WG_TMEM_COLS = 2 * WG_BN;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t WG_IDESC = tf32_idesc(WG_BM, WG_BN);
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+struct WgParams {
+    int B, H, W, Cout, Cin, kh, kw, dil;
+    int wblocks;                 // k-blocks per image row = ceil(W / 32)
+    int kblocks;                 // B * H * wblocks
+    int splits, kb_per_split;
+    int tiles_m, tiles_n;
+    float* dw;                   // [Cout, kh*kw*Cin], zeroed by the caller
+    long long ldw;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+                         const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                         const __grid_constant__ WgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 4);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + WG_STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * WG_STAGES), bar_tempty = smem_u32(bars + 2 * WG_STAGES + 2);
+    const uint32_t tiles_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)WG_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int taps = P.kh * P.kw;
+    const int total = taps * P.tiles_m * P.tiles_n * P.splits;
+
+    // tile -> (tap, m tile, n tile, split); k-block range of the split
+#define WG_DECODE(tile)                                                                        \
+    int r_ = (tile);                                                                           \
+    const int sp = r_ % P.splits; r_ /= P.splits;                                              \
+    const int nt = r_ % P.tiles_n; r_ /= P.tiles_n;                                            \
+    const int mt = r_ % P.tiles_m;                                                             \
+    const int tap = r_ / P.tiles_m;                                                            \
+    const int kb_lo = sp * P.kb_per_split, kb_hi = min(P.kblocks, kb_lo + P.kb_per_split);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                WG_DECODE(tile)
+                const int dy = (tap / P.kw - P.kh / 2) * P.dil, sx = tap % P.kw;      // sx: which pre-shifted copy of X^T
+                // first k-block of the split -> (image, row, row block), then counted up
+                int xb = kb_lo % P.wblocks, ry = kb_lo / P.wblocks;
+                int y = ry % P.H, b = ry / P.H;
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                    if ((unsigned)(y + dy) < (unsigned)P.H) {                         // (rows above / below the image: zero padding)
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        const uint32_t dst = tiles_base + stage * WG_STAGE_BYTES;
+                        mbar_expect_tx(full, WG_STAGE_BYTES);
+                        tma_load_5d(dst + 0 * WG_TILE_BYTES, &map_g_hi, full, xb * WG_BK, y, b, mt * WG_BM, 0);
+                        tma_load_5d(dst + 1 * WG_TILE_BYTES, &map_g_lo, full, xb * WG_BK, y, b, mt * WG_BM, 0);
+                        tma_load_5d(dst + 2 * WG_TILE_BYTES, &map_x_hi, full, xb * WG_BK, y + dy, b, nt * WG_BN, sx);
+                        tma_load_5d(dst + 3 * WG_TILE_BYTES, &map_x_lo, full, xb * WG_BK, y + dy, b, nt * WG_BN, sx);
+                        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    if (++xb == P.wblocks) { xb = 0; if (++y == P.H) { y = 0; ++b; } }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+                WG_DECODE(tile)
+                (void)mt; (void)nt;
+                const int dy = (tap / P.kw - P.kh / 2) * P.dil;
+                const int acc = it & 1;
+                mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * WG_BN;
+                int xb = kb_lo % P.wblocks, y = (kb_lo / P.wblocks) % P.H;
+                uint32_t started = 0u;
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                    if ((unsigned)(y + dy) < (unsigned)P.H) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t src = tiles_base + stage * WG_STAGE_BYTES;
+                        const uint64_t a_hi = make_kmajor_sw128_desc(src), a_lo = make_kmajor_sw128_desc(src + WG_TILE_BYTES);
+                        const uint64_t b_hi = make_kmajor_sw128_desc(src + 2 * WG_TILE_BYTES),
+                                       b_lo = make_kmajor_sw128_desc(src + 3 * WG_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < WG_BK / 8; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, WG_IDESC, started | (uint32_t)k);
+                            mma_tf32(tmem_d, a_hi + adv, b_lo + adv, WG_IDESC, 1u);
+                            mma_tf32(tmem_d, a_lo + adv, b_hi + adv, WG_IDESC, 1u);
+                        }
+                        started = 1u;
+                        mma_commit(bar_empty + 8 * stage);
+                        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    if (++xb == P.wblocks) { xb = 0; if (++y == P.H) y = 0; }
+                }
+                mma_commit(bar_tfull + 8 * acc);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5): partial tile += into dW =====================
+        const int q = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            WG_DECODE(tile)
+            const int acc = it & 1;
+            mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+            tc_fence_after();
+            const int row = mt * WG_BM + q * 32 + lane;                               // output channel
+            float* __restrict__ drow = P.dw + (size_t)row * P.ldw + (size_t)tap * P.Cin + nt * WG_BN;
+            const bool vec_ok = (((size_t)row * P.ldw + (size_t)tap * P.Cin + nt * WG_BN) & 3) == 0;
+            // nothing accumulated: a split past the end, or every row of its pixel range falls into the vertical padding
+            bool empty = true;
+            {
+                const int dy = (tap / P.kw - P.kh / 2) * P.dil;
+                int y = kb_lo < kb_hi ? (kb_lo / P.wblocks) % P.H : 0;
+                for (int kb = kb_lo; kb < kb_hi && empty; kb += P.wblocks) {          // one probe per image row touched
+                    if ((unsigned)(y + dy) < (unsigned)P.H) empty = false;
+                    if (++y == P.H) y = 0;
+                }
+                if (empty && kb_lo < kb_hi) {                                        // the last (partial) row of the range
+                    const int yl = ((kb_hi - 1) / P.wblocks) % P.H;
+                    if ((unsigned)(yl + dy) < (unsigned)P.H) empty = false;
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < WG_BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + acc * WG_BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                if (row < P.Cout && !empty) {
+                    const int col0 = nt * WG_BN + c * 32;
+                    if (vec_ok && col0 + 32 <= P.Cin) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            atomicAdd(reinterpret_cast<float4*>(drow + c * 32 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < P.Cin) atomicAdd(drow + c * 32 + j, v[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+#undef WG_DECODE
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)WG_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pre-pass: rows [P, C] (pitch ld) -> [C, P] tf32 hi / lo (32 x 32 shared-memory transpose).  With `y` the rows are a
+// gradient: it is first multiplied by the derivative of the layer's activation at its OUTPUT y (relu / leaky: sign of y;
+// tanh: 1 - y^2; sigmoid: y (1 - y)) and -- with `g_rows` -- also written back row-major (the operand of the
+// data-gradient convolution); `colsum` [C] accumulates the bias gradient (atomics, zeroed by the caller).
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ x, long long ld, long long P, int C, const float* __restrict__ y, long long ldy,
+                       int act, float slope, float* __restrict__ hi_t, float* __restrict__ lo_t, long long ldt,
+                       float* __restrict__ g_rows, float* __restrict__ colsum, int W, int n_shift, int shift_step) {
+    __shared__ float s_t[32][33];
+    __shared__ float s_sum[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                          // 32 x 8
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = 0; j < n_shift; ++j) {
+        const int shift = (j - n_shift / 2) * shift_step;                            // copy j holds the rows shifted by `shift` pixels
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long p = p0 + ty + 8 * i;
+            const int c = c0 + tx;
+            float v = 0.f;
+            if (p < P && c < C) {
+                const int xs = (int)(p % W) + shift;                                 // stays inside its image row, or reads zero
+                if ((unsigned)xs < (unsigned)W) v = __ldg(x + (p + shift) * ld + c);
+                if (y) {
+                    const float o = __ldg(y + p * ldy + c);
+                    if (act == CAMLI_ACT_RELU) v = o > 0.f ? v : 0.f;
+                    else if (act == CAMLI_ACT_LEAKY) v = o > 0.f ? v : v * slope;
+                    else if (act == CAMLI_ACT_TANH) v = v * (1.f - o * o);
+                    else if (act == CAMLI_ACT_SIGMOID) v = v * o * (1.f - o);
+                    if (g_rows) g_rows[p * C + c] = v;
+                }
+            }
+            part += v;
+            s_t[ty + 8 * i][tx] = v;
+        }
+        if (colsum) s_sum[ty][tx] = part;
+        __syncthreads();
+        if (colsum && ty == 0 && c0 + tx < C) {                                      // bias gradient: column sums of this block
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += s_sum[i][tx];
+            atomicAdd(colsum + c0 + tx, t);
+        }
+        float* __restrict__ hj = hi_t + (long long)j * C * ldt;
+        float* __restrict__ lj = lo_t + (long long)j * C * ldt;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty + 8 * i;
+            const long long p = p0 + tx;
+            if (c < C && p < P) {
+                float h, l;
+                split_tf32(s_t[tx][ty + 8 * i], h, l);
+                hj[(long long)c * ldt + p] = h;
+                lj[(long long)c * ldt + p] = l;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int wg_encode_map(CUtensorMap* map, const float* base, int B, int H, int W, int C, int S) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    const cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)C, (cuuint64_t)S};
+    const cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * B * 4, (cuuint64_t)W * H * B * C * 4};
+    const cuuint32_t box[5] = {WG_BK, 1, 1, WG_BM, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, int C, const float* y_rows, int64_t ldy,
+                                     int act, float slope, int W, int n_shift, int shift_step,
+                                     float* hi_t, float* lo_t, float* g_rows, float* colsum, void* stream) {
+    if (P < 0 || C < 1 || ld < C || (y_rows && ldy < C) || W < 1 || n_shift < 1 || (n_shift & 1) == 0 || shift_step < 1)
+        return CAMLI_EINVAL;
+    if (n_shift > 1 && (y_rows || g_rows || colsum || P % W)) return CAMLI_EINVAL;   // shifted copies: plain activations only
+    if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EUNSUPPORTED;
+    if (P == 0) return CAMLI_OK;
+    if (!rows || !hi_t || !lo_t) return CAMLI_EINVAL;
+    if (camli_div_up_ll(P, 32) > 2147483647LL) return CAMLI_EUNSUPPORTED;
+    const dim3 grid((unsigned)camli_div_up_ll(P, 32), (unsigned)camli_div_up(C, 32));
+    transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
+                                                                   g_rows, colsum, W, n_shift, shift_step);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
+                                int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation,
+                                float* dw, void* stream) {
+    if (B < 0 || H < 1 || W < 1 || Cout < 1 || Cin < 1 || kh < 1 || kw < 1 || dilation < 1) return CAMLI_EINVAL;
+    if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (W & 3) || (Cin & 3) || dilation > 64) return CAMLI_EUNSUPPORTED;
+    if (B == 0) return CAMLI_OK;
+    if (!g_hi_t || !g_lo_t || !x_hi_t || !x_lo_t || !dw) return CAMLI_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(g_hi_t) | reinterpret_cast<uintptr_t>(g_lo_t) | reinterpret_cast<uintptr_t>(x_hi_t) |
+         reinterpret_cast<uintptr_t>(x_lo_t) | reinterpret_cast<uintptr_t>(dw)) & 15)
+        return CAMLI_EINVAL;
+    WgParams P;
+    P.B = B; P.H = H; P.W = W; P.Cout = Cout; P.Cin = Cin; P.kh = kh; P.kw = kw; P.dil = dilation;
+    P.wblocks = camli_div_up(W, WG_BK);
+    const long long kblocks = (long long)B * H * P.wblocks;
+    if (kblocks > 2147483647LL) return CAMLI_EUNSUPPORTED;
+    P.kblocks = (int)kblocks;
+    P.tiles_m = camli_div_up(Cout, WG_BM); P.tiles_n = camli_div_up(Cin, WG_BN);
+    const int n_sms = sm_count();
+    const long long base_tiles = (long long)kh * kw * P.tiles_m * P.tiles_n;
+    // K splits: enough CTAs for every SM (two rounds when the pixel range is long), never fewer than 8 k-blocks per split
+    long long splits = (2LL * n_sms + base_tiles - 1) / base_tiles;
+    if (splits > kblocks / 8) splits = kblocks / 8;
+    if (splits < 1) splits = 1;
+    P.splits = (int)splits;
+    P.kb_per_split = (int)((kblocks + splits - 1) / splits);
+    P.dw = dw; P.ldw = (long long)kh * kw * Cin;
+    const long long total = base_tiles * splits;
+    if (total > 2147483647LL) return CAMLI_EUNSUPPORTED;
+
+    CUtensorMap m_ghi, m_glo, m_xhi, m_xlo;
+    int rc;
+    if ((rc = wg_encode_map(&m_ghi, g_hi_t, B, H, W, Cout, 1))) return rc;
+    if ((rc = wg_encode_map(&m_glo, g_lo_t, B, H, W, Cout, 1))) return rc;
+    if ((rc = wg_encode_map(&m_xhi, x_hi_t, B, H, W, Cin, kw))) return rc;          // kw horizontally pre-shifted copies
+    if ((rc = wg_encode_map(&m_xlo, x_lo_t, B, H, W, Cin, kw))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(dw, 0, (size_t)Cout * P.ldw * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)(total < n_sms ? total : n_sms);
+    conv_wgrad_tf32x3_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(m_ghi, m_glo, m_xhi, m_xlo, P);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}

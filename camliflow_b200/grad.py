@@ -195,3 +195,82 @@ def recompute(kernel, formula, *args):
     with torch.autocast("cuda", enabled=False):
         out = _Recompute.apply(kernel, formula, *args)
     return list(out) if isinstance(out, tuple) else out
+
+
+# --------------------------------------------------------------------------------------- dense layers
+_DENSE_W = {}      # (data_ptr, version, shape, flipped) -> (weak ref, hi, lo): lives for ONE training step (clear_dense_cache)
+
+
+def clear_dense_cache():
+    """Drop the split weights of the dense-layer autograd node.  trainer.train_step calls it at the start of every step (and
+    CapturedTrainStep after its capture), so a cached split can never outlive the parameter values it was made from."""
+    _DENSE_W.clear()
+
+
+def _dense_weight(weight, flipped):
+    """tf32 hi / lo parts of a conv / linear weight [O,I,kh,kw] as the OHWI matrix conv_gemm reads: [O, kh*kw*I], or --
+    `flipped` -- the matrix of the DATA-gradient convolution, [I, kh*kw*O] with the window mirrored."""
+    import weakref
+    from . import ops
+    owner = weight._base if weight._base is not None else weight       # (a Linear / Conv1d weight arrives as a 4-D view)
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), flipped)
+    hit = _DENSE_W.get(key)
+    if hit is None or hit[0]() is not owner:
+        with torch.no_grad():
+            w = weight.detach().float()
+            if flipped:
+                w2d = w.flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1).contiguous()
+            else:
+                w2d = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+            hit = (weakref.ref(owner),) + ops.split_tf32(w2d)
+        _DENSE_W[key] = hit
+    return hit[1], hit[2]
+
+
+class DenseFn(torch.autograd.Function):
+    """act(conv(x, weight) + bias) for a stride-1 "same" convolution / linear layer on channel-last rows, forward AND backward on
+    the hand-written tensor-core kernels: forward = camli_conv_gemm; backward = camli_transpose_split (activation derivative,
+    bias gradient, K-major operands), camli_conv_gemm on the mirrored weights (data gradient), camli_conv_wgrad (weight
+    gradient).  Replaces, for training, what autograd does with cuDNN / cuBLAS in the reference (train.py:143-171).
+    x_rows [B,H,W,Cin] contiguous fp32, weight [O,I,kh,kw], bias [O] or None -> [B,H,W,O]."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x_rows, weight, bias, act, slope, dilation):
+        from . import ops
+        kh, kw = weight.shape[2:]
+        w_hi, w_lo = _dense_weight(weight, False)
+        x_rows = x_rows.contiguous()
+        y = ops.conv_gemm(x_rows, w_hi, w_lo, kh, kw, None if bias is None else bias.detach().float().contiguous(), act, slope,
+                          dilation=dilation)
+        ctx.act, ctx.slope, ctx.dilation = act, slope, dilation
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x_rows, weight, y if act is not None else None)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        from . import ops
+        x_rows, weight, y = ctx.saved_tensors
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        B, H, W, Cin = x_rows.shape
+        O, _, kh, kw = weight.shape
+        gy = gy.float().contiguous()
+        g_hi, g_lo, g_rows, db = ops.transpose_split(gy, y, ctx.act, ctx.slope, want_rows=need_x, want_colsum=need_b)
+        if y is None:
+            g_rows = gy
+        dx = dw = None
+        if need_x:
+            if O % 4 == 0:
+                wt_hi, wt_lo = _dense_weight(weight, True)
+                dx = ops.conv_gemm(g_rows, wt_hi, wt_lo, kh, kw, dilation=ctx.dilation)
+            else:                                    # TMA rows are 16-byte granular: ragged gradient rows (C_out = 2, 125, 126)
+                pad = (ctx.dilation * (kh // 2), ctx.dilation * (kw // 2))
+                dx = torch.nn.grad.conv2d_input((B, Cin, H, W), weight.float(), g_rows.permute(0, 3, 1, 2), padding=pad,
+                                                dilation=ctx.dilation).permute(0, 2, 3, 1)
+        if need_w:
+            x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation)
+            dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation)
+            dw = dw2d.view(O, kh, kw, Cin).permute(0, 3, 1, 2).to(weight.dtype)
+        return dx, dw, (db.to(weight.dtype) if need_b else None), None, None, None

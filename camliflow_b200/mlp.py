@@ -70,6 +70,14 @@ class _ConvNormAct(nn.Module):
     def forward(self, x):
         if self.ND == 2 and tc.fused(x) and self._foldable():          # conv + norm + activation: one tcgen05 kernel
             return tc.conv2d(x, self.conv_fn, self.act, 0.1, bn=self.norm_fn)
+        if isinstance(self.norm_fn, nn.Identity):
+            y = tc.module_train(self.conv_fn, x, self.act)          # training: forward + backward on the tensor-core kernels
+            if y is not None:
+                return y
+        else:
+            y = tc.module_train(self.conv_fn, x)
+            if y is not None:
+                return self.act_fn(self.norm_fn(y))
         return self.act_fn(self.norm_fn(self.conv_fn(x)))
 
     def forward_rows(self, x):

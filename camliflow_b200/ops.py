@@ -392,6 +392,54 @@ def linear_rows(x, w_hi, w_lo, bias=None, act=None, slope=0.1, residual=None):
     return out.view(*x.shape[:-1], w_hi.shape[0])
 
 
+# ---------------------------------------------------------------- training side of conv_gemm (dense-layer backward)
+def split_tf32(w2d):
+    """(hi, lo) tf32 parts of a contiguous fp32 tensor (camli_split_tf32), uncached."""
+    hi, lo = torch.empty_like(w2d), torch.empty_like(w2d)
+    with torch.cuda.device(w2d.device):
+        native.call("camli_split_tf32", ptr(w2d), ptr(hi), ptr(lo), i64(w2d.numel()), stream())
+    return hi, lo
+
+
+def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_colsum=False, n_shift=1, shift_step=1):
+    """rows [B,H,W,C] channel-last view -> (hi_t, lo_t [C, B*H*W], g_rows, colsum): the transposed tf32 parts the
+    weight-gradient GEMM reads (camli_transpose_split).  With `y` (the layer output, same shape) rows is dL/dy: it is
+    multiplied by act'(y) first; g_rows [B,H,W,C] = that product (operand of the data-gradient convolution), colsum [C] =
+    its sum over the pixels (the bias gradient).  n_shift = kw > 1: [kw, C, B*H*W] horizontally pre-shifted copies (the x
+    operand of a kw-wide window, shift_step = dilation)."""
+    B, H, W, C = rows.shape
+    ld, ok = _pixel_layout(rows)
+    if not ok and rows.stride(-1) != 1:
+        raise RuntimeError("transpose_split: channel-last rows expected")
+    P = B * H * W
+    hi_t = torch.empty((n_shift, C, P) if n_shift > 1 else (C, P), dtype=torch.float32, device=rows.device)
+    lo_t = torch.empty_like(hi_t)
+    g_rows = torch.empty((B, H, W, C), dtype=torch.float32, device=rows.device) if (want_rows and y is not None) else None
+    colsum = torch.zeros((C,), dtype=torch.float32, device=rows.device) if want_colsum else None
+    ldy = _pixel_layout(y)[0] if y is not None else 0
+    with torch.cuda.device(rows.device):
+        native.call("camli_transpose_split", ptr(rows), i64(ld), i64(P), i32(C), ptr(y), i64(ldy), i32(ACT_CODES[act]),
+                    ctypes.c_float(slope), i32(W), i32(n_shift), i32(shift_step), ptr(hi_t), ptr(lo_t), ptr(g_rows), ptr(colsum),
+                    stream(), algo_bytes=P * C * 4 * (1 + 2 * n_shift + (2 if y is not None else 0)))
+    return hi_t, lo_t, g_rows, colsum
+
+
+def conv_wgrad(g_t, x_t, B, H, W, Cout, Cin, kh, kw, dilation=1):
+    """dW [Cout, kh*kw*Cin] (OHWI) of the stride-1 "same" convolution from the transposed hi / lo operand pairs of
+    transpose_split (camli_conv_wgrad: 3xTF32 on tcgen05, K split over the SMs)."""
+    dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=g_t[0].device)
+    with torch.cuda.device(dw.device):
+        native.call("camli_conv_wgrad", ptr(g_t[0]), ptr(g_t[1]), ptr(x_t[0]), ptr(x_t[1]), i32(B), i32(H), i32(W), i32(Cout),
+                    i32(Cin), i32(kh), i32(kw), i32(dilation), ptr(dw), stream(),
+                    algo_bytes=2 * B * H * W * (Cout + Cin) * 4 + Cout * kh * kw * Cin * 4,
+                    flops=2 * B * H * W * Cout * kh * kw * Cin, shape=(Cout, kh * kw * Cin, B * H * W))
+    return dw
+
+
+def conv_wgrad_ok(B, H, W, Cin):
+    return W % 4 == 0 and Cin % 4 == 0
+
+
 # ---------------------------------------------------------------- RAFT all-pairs correlation
 def corr2d_build(fmap1, fmap2, num_levels):
     """All-pairs volume of two [B,C,H,W] maps scaled by 1/sqrt(C) and its 2x2 average-pooled pyramid

@@ -63,7 +63,8 @@ class PointConv(nn.Module):
         if tc.fused(grouped) and (isinstance(n, nn.Identity) or (isinstance(n, nn.BatchNorm1d) and not n.training)):
             # Linear + BatchNorm (running statistics, folded) + activation: one tensor-core kernel
             return tc.linear(grouped, self.linear.weight, self.linear.bias, self.act, 0.1, bn=n).transpose(1, 2)
-        out = self.linear(grouped).transpose(1, 2)                                 # [B,O,S]
+        out = tc.module_train(self.linear, grouped)                                # training: grad.DenseFn
+        out = (self.linear(grouped) if out is None else out).transpose(1, 2)       # [B,O,S]
         return self.act_fn(self.norm_fn(out))
 
 

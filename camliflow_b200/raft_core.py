@@ -65,6 +65,10 @@ class _Bottleneck(nn.Module):
     def forward(self, x):
         if _fused_inference(x):
             return self._forward_fused(x)
+        if tc._train_route(x):
+            # training: the BatchNorms still run on their running statistics (norm_eval), so they fold into the convolutions
+            # differentiably; every stride-1 layer then runs forward AND backward on the tensor-core kernels (grad.DenseFn)
+            return self._forward_fused(x)
         y = F.relu(self.bn1(self.conv1(x)), inplace=True)
         y = F.relu(self.bn2(self.conv2(y)), inplace=True)
         y = self.bn3(self.conv3(y))
@@ -143,9 +147,9 @@ class GRU2D(nn.Module):
 
     def _half(self, h, x, convz, convr, convq):
         hx = torch.cat([h, x], dim=1)
-        z = torch.sigmoid(convz(hx))
-        r = torch.sigmoid(convr(hx))
-        q = torch.tanh(convq(torch.cat([r * h, x], dim=1)))
+        z = tc.conv2d(hx, convz, "sigmoid")              # (under autograd: grad.DenseFn, activation in the epilogue)
+        r = tc.conv2d(hx, convr, "sigmoid")
+        q = tc.conv2d(torch.cat([r * h, x], dim=1), convq, "tanh")
         return (1 - z) * h + z * q
 
     def _merged_zr(self, convz, convr):
@@ -272,9 +276,9 @@ class MotionEncoder2D(nn.Module):
             tc.conv2d(cf.permute(0, 3, 1, 2), self.conv, "relu_fix", out=mf[..., :n_out])
             mf[..., n_out:].copy_(flow.permute(0, 2, 3, 1))
             return mf.permute(0, 3, 1, 2)
-        c = F.relu(self.conv_c2(F.relu(self.conv_c1(corr))))
-        f = F.relu(self.conv_f2(F.relu(self.conv_f1(flow))))
-        out = torch.nan_to_num(F.relu(self.conv(torch.cat([c, f], dim=1))))
+        c = tc.conv2d(tc.conv2d(corr, self.conv_c1, "relu"), self.conv_c2, "relu")
+        f = tc.conv2d(tc.conv2d(flow, self.conv_f1, "relu"), self.conv_f2, "relu")
+        out = torch.nan_to_num(tc.conv2d(torch.cat([c, f], dim=1), self.conv, "relu"))
         return torch.cat([out, flow], dim=1)
 
 

@@ -2,9 +2,13 @@
 
 `conv2d` / `linear` evaluate an nn.Conv2d / nn.Conv1d(1) / nn.Linear -- optionally followed by an
 eval-mode BatchNorm (folded), a residual add and an activation -- as ONE kernel on channel-last
-data.  They are inference paths (no autograd): under autograd, or for a layer the kernel does not
-cover (stride 2, C_in % 4 != 0, training-mode norm), the same arithmetic runs through torch
-(cuDNN / cuBLAS) so callers never branch."""
+data.  Without autograd that is the inference path.  Under autograd (training) a stride-1 layer runs
+through grad.DenseFn: the same forward kernel, and a backward made of the hand-written transpose /
+split pre-pass, the forward kernel on mirrored weights (data gradient) and the split-K weight-gradient
+kernel (camli_conv_wgrad).  Only a layer the kernels do not cover (stride 2 under autograd, C_in % 4 != 0,
+training-mode norm statistics) runs through torch (cuDNN / cuBLAS) -- explicitly, so callers never branch."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -12,6 +16,59 @@ import torch.nn.functional as F
 from . import ops
 
 ENABLED = True          # tests / A-B benchmarks flip this to route everything through torch
+# dense layers under autograd: "tcgen05" = grad.DenseFn (hand-written forward + backward kernels), "library" = cuDNN / cuBLAS
+TRAIN_DENSE = os.environ.get("CAMLI_TRAIN_DENSE", "tcgen05")
+_DENSE_ACTS = (None, "relu", "leaky_relu", "tanh", "sigmoid")
+
+
+def _train_route(x):
+    return (ENABLED and TRAIN_DENSE == "tcgen05" and x.is_cuda and torch.is_grad_enabled()
+            and x.dtype in (torch.float32, torch.bfloat16, torch.float16))
+
+
+def conv_train(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1, act=None, slope=0.1):
+    """Training route of a convolution on a logical [B,C,H,W] tensor: act(conv(x) + bias) through grad.DenseFn, or None when
+    the layer is outside what the kernels cover (the caller then runs torch)."""
+    from . import grad
+    if not _train_route(x) or weight.dim() != 4 or act not in _DENSE_ACTS:
+        return None
+    O, I, kh, kw = weight.shape
+    d = dilation[0]
+    if (tuple(stride) != (1, 1) or groups != 1 or tuple(dilation) != (d, d) or kh % 2 == 0 or kw % 2 == 0
+            or tuple(padding) != (d * (kh // 2), d * (kw // 2)) or x.dim() != 4 or x.shape[1] != I):
+        return None
+    B, _, H, W = x.shape
+    if not ops.conv_wgrad_ok(B, H, W, I) or B * H * W < 128:
+        return None
+    return grad.DenseFn.apply(x.permute(0, 2, 3, 1), weight, bias, act, slope, d).permute(0, 3, 1, 2)
+
+
+def linear_train(x, weight2d, bias, act=None, slope=0.1):
+    """The same for a linear layer on rows x [..., K]: [..., N], or None."""
+    from . import grad
+    if not _train_route(x) or act not in _DENSE_ACTS:
+        return None
+    N, K = weight2d.shape
+    rows = x.reshape(1, 1, -1, K)
+    R = rows.shape[2]
+    if x.shape[-1] != K or not ops.conv_wgrad_ok(1, 1, R, K) or R < 128:
+        return None
+    y = grad.DenseFn.apply(rows, weight2d.view(N, K, 1, 1), bias, act, slope, 1)
+    return y.view(*x.shape[:-1], N)
+
+
+def module_train(module, x, act=None, slope=0.1):
+    """Training route of an nn.Conv2d / nn.Conv1d(kernel 1) / nn.Linear applied to its usual input layout, or None."""
+    if isinstance(module, nn.Conv2d):
+        return conv_train(x, module.weight, module.bias, module.stride, module.padding, module.dilation, module.groups, act, slope)
+    if isinstance(module, nn.Conv1d):
+        if module.kernel_size != (1,) or module.stride != (1,) or module.groups != 1 or x.dim() != 3:
+            return None
+        y = linear_train(x.transpose(1, 2), module.weight[:, :, 0], module.bias, act, slope)
+        return None if y is None else y.transpose(1, 2)
+    if isinstance(module, nn.Linear):
+        return linear_train(x, module.weight, module.bias, act, slope)
+    return None
 
 _TORCH_ACTS = {
     None: lambda v, s: v,
@@ -122,12 +179,26 @@ def conv2d(x, conv, act=None, slope=0.1, bn=None, residual=None, out=None):
                     res = res.contiguous()
             y = ops.conv_gemm(rows, w_hi, w_lo, kh, kw, bias, act, slope, res, out, stride=stride, dilation=dil)
             return y.permute(0, 3, 1, 2)
-    y = conv(x)
+    # ---- under autograd (or outside the kernels' coverage): the training route, else torch
+    fuse_act = residual is None and act in _DENSE_ACTS
+    y = None
+    if _train_route(x) and _bn_foldable(bn):
+        w, b = _fold(conv.weight, conv.bias, bn)         # (eval-mode BatchNorm: differentiable w.r.t. its affine parameters)
+        y = conv_train(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups, act if fuse_act else None, slope)
+        if y is not None:
+            bn = None
+    elif _train_route(x):
+        y = conv_train(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups, None, slope)
+        fuse_act = False
+    if y is None:
+        y = conv(x)
+        fuse_act = False
     if bn is not None:
         y = bn(y)
     if residual is not None:
         y = y + residual
-    y = _TORCH_ACTS[act](y, slope)
+    if not fuse_act:
+        y = _TORCH_ACTS[act](y, slope)
     if out is not None:
         out.copy_(y.permute(0, 2, 3, 1))
         return out.permute(0, 3, 1, 2)
@@ -162,10 +233,15 @@ def conv2d_weights(x, weight, bias, padding, act=None, slope=0.1, out=None, resi
                 if not ops._pixel_layout(res)[1]:
                     res = res.contiguous()
             return ops.conv_gemm(rows, w_hi, w_lo, kh, kw, b, act, slope, res, out).permute(0, 3, 1, 2)
-    y = F.conv2d(x, weight, bias, padding=padding)
+    fuse_act = residual is None and act in _DENSE_ACTS
+    y = conv_train(x, weight, bias, (1, 1), tuple(padding), (1, 1), 1, act if fuse_act else None, slope)
+    if y is None:
+        y = F.conv2d(x, weight, bias, padding=padding)
+        fuse_act = False
     if residual is not None:
         y = y + residual
-    y = _TORCH_ACTS[act](y, slope)
+    if not fuse_act:
+        y = _TORCH_ACTS[act](y, slope)
     if out is not None:
         out.copy_(y.permute(0, 2, 3, 1))
         return out.permute(0, 3, 1, 2)
@@ -194,7 +270,13 @@ def linear(x, weight, bias=None, act=None, slope=0.1, bn=None):
             return ops.linear_rows(rows, w_hi, w_lo, b, act, slope)
     if bn is not None and not isinstance(bn, nn.Identity):
         if not _bn_foldable(bn):
-            y = bn(F.linear(x, w2, bias).movedim(-1, 1)).movedim(1, -1)
+            y = linear_train(x, w2, bias)
+            if y is None:
+                y = F.linear(x, w2, bias)
+            y = bn(y.movedim(-1, 1)).movedim(1, -1)
             return _TORCH_ACTS[act](y, slope)
         w2, bias = _fold(w2, bias, bn)
+    y = linear_train(x, w2, bias, act if act in _DENSE_ACTS else None, slope)
+    if y is not None:
+        return y if act in _DENSE_ACTS else _TORCH_ACTS[act](y, slope)
     return _TORCH_ACTS[act](F.linear(x, w2, bias), slope)

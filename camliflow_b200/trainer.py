@@ -37,8 +37,10 @@ def _world():
 def train_step(model, optimizer, inputs, max_grad_norm=None, autocast_dtype=None):
     """One optimisation step; returns the (detached) loss tensor.  `inputs` must carry the targets
     `flow_2d` / `flow_3d` (models/camliraft.py:80-86).  `autocast_dtype` (torch.bfloat16): forward and loss under
-    autocast as in train.py:147-149 -- the dense layers run in bf16, the fused point / correlation operators and
-    the losses stay fp32 (camliflow_b200/grad.py:f32); bf16 needs no GradScaler."""
+    autocast as in train.py:147-149 -- dense layers the kernels do not cover run in bf16 (cuDNN / cuBLAS), the ones they do
+    (grad.DenseFn), the fused point / correlation operators and the losses stay fp32 (camliflow_b200/grad.py:f32); bf16 needs no GradScaler."""
+    from . import grad
+    grad.clear_dense_cache()                 # split weights of the dense-layer nodes live for one step
     optimizer.zero_grad(set_to_none=True)
     with torch.autocast("cuda", dtype=autocast_dtype, enabled=autocast_dtype is not None):
         model(inputs)
@@ -102,8 +104,12 @@ class CapturedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step()
+        from . import grad
+        grad.clear_dense_cache()                          # (its entries live in the graph's memory pool)
 
     def _step(self):
+        from . import grad
+        grad.clear_dense_cache()                          # every weight is split once per step, inside the step
         self.flat.zero_()
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             self.model(self.static_in)

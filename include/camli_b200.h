@@ -254,6 +254,30 @@ int camli_allpairs_correlation(const float* a_rows, const float* b_rows, float* 
                                int B, int M, int N, int K, float scale, void* stream);
 
 /*
+ * Training side of camli_conv_gemm (in the reference: the cuDNN wgrad / cuBLAS GEMMs autograd picks for every dense layer,
+ * models/raft_core.py:110-197, models/mlp.py:41-128, train.py:143-171).
+ *
+ * camli_transpose_split: rows [P, C] (pitch ld) -> hi_t, lo_t [C, P], the tf32 hi / lo parts of the TRANSPOSED tensor
+ * (pixel-contiguous = K-major for the weight-gradient GEMM).  With y_rows != NULL the rows are dL/d(layer output): they are
+ * multiplied by the derivative of activation `act` (CAMLI_ACT_NONE / RELU / LEAKY / TANH / SIGMOID) evaluated at the layer
+ * OUTPUT y_rows [P, >= C] (pitch ldy) first; g_rows [P, C] (optional) receives that product row-major, colsum [C] (optional,
+ * zeroed by the caller) its column sums = the bias gradient.  n_shift (odd) > 1: hi_t / lo_t are [n_shift, C, P], copy j
+ * holding the rows shifted by (j - n_shift/2) * shift_step pixels inside their image row of W pixels (zero outside) -- the
+ * x operand of a kw-wide window, because a TMA box cannot start at a 4-byte pixel offset of the contiguous dimension.
+ *
+ * camli_conv_wgrad: dw[n, tap*Cin + c] = sum over pixels of g[p, n] * x[p (+) tap, c] for the stride-1 "same" convolution /
+ * linear layer of camli_conv_gemm (OHWI layout, [Cout, kh*kw*Cin]); operands are the [C, B, H, W] hi / lo tensors of
+ * camli_transpose_split, x with n_shift = kw, shift_step = dilation.  3xTF32 on tcgen05, K split over the SMs, partial tiles added with 128-bit atomics (dw is zeroed
+ * inside).  W % 4 == 0, Cin % 4 == 0, odd windows.  The data gradient needs no kernel of its own: it is camli_conv_gemm of
+ * g_rows with the spatially flipped, in/out-transposed weights.
+ */
+int camli_transpose_split(const float* rows, int64_t ld, int64_t P, int C, const float* y_rows, int64_t ldy,
+                          int act, float slope, int W, int n_shift, int shift_step,
+                          float* hi_t, float* lo_t, float* g_rows, float* colsum, void* stream);
+int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
+                     int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, float* dw, void* stream);
+
+/*
  * SK fusion tail (SKFusion.forward after the align layers, models/clfm.py:199-214):
  *   a = leaky(a_rows), b = leaky(b_rows)   (negative_slope; 1 => inputs already activated)
  *   w = softmax_pair(sigmoid(W_out relu(W_mid mean_p(a + b))))      [B,C,2]

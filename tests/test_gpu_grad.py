@@ -49,6 +49,83 @@ def test_dw_gather_max_backward(dev):
     assert _rel(gf, rf) <= 1e-5 and _rel(gw, rw) <= 1e-6      # g_feat is an atomic sum: order-dependent rounding
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw,dil,act,bias", [
+    (1, 68, 120, 256, 192, 3, 3, 1, "relu", True),        # motion encoder conv_c2 at C2 size
+    (2, 20, 36, 64, 126, 3, 3, 1, "relu", True),          # ragged rows (W % 32 != 0), C_out % 4 != 0 (library data gradient)
+    (1, 17, 40, 128, 128, 1, 5, 1, "sigmoid", True),      # ConvGRU gate
+    (1, 17, 40, 128, 128, 5, 1, 1, "tanh", True),
+    (2, 24, 32, 32, 64, 3, 3, 2, "leaky_relu", False),    # dilated (PWC context network)
+    (1, 1, 2048, 384, 256, 1, 1, 1, None, True),          # point-branch linear
+    (1, 1, 520, 128, 64, 1, 1, 1, "leaky_relu", True),
+])
+def test_dense_layer_backward_kernels(dev, B, H, W, Cin, Cout, kh, kw, dil, act, bias):
+    """grad.DenseFn (forward conv_gemm; backward transpose_split + conv_gemm on mirrored weights + conv_wgrad) against fp64
+    autograd through F.conv2d: output, data gradient, weight gradient, bias gradient."""
+    import torch.nn.functional as F
+    from camliflow_b200 import grad
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).to(dev).requires_grad_(True)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev).requires_grad_(True) if bias else None
+    gy = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    grad.clear_dense_cache()
+    y = grad.DenseFn.apply(x, w, b, act, 0.1, dil)
+    got = torch.autograd.grad(y, [x, w] + ([b] if bias else []), gy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=(dil * (kh // 2), dil * (kw // 2)), dilation=dil)
+    yd = {None: lambda v: v, "relu": torch.relu, "leaky_relu": lambda v: F.leaky_relu(v, 0.1), "tanh": torch.tanh,
+          "sigmoid": torch.sigmoid}[act](yd).permute(0, 2, 3, 1)
+    ref = torch.autograd.grad(yd, [xd, wd] + ([bd] if bias else []), gy.double())
+    names = ["dx", "dw", "db"]
+    print("dense %s: y %.2e %s" % ((B, H, W, Cin, Cout, kh, kw, dil, act), _rel(y.double(), yd),
+                                    " ".join("%s %.2e" % (n, _rel(a.double(), r)) for n, a, r in zip(names, got, ref))))
+    assert _rel(y.double(), yd) <= 1e-5
+    for n, a, r in zip(names, got, ref):
+        assert a.shape == r.shape
+        assert _rel(a.double(), r) <= 2e-5, n            # fp32-level: 3xTF32 products, fp32 accumulation
+
+
+def test_dense_layers_route_through_the_kernels_under_autograd(dev):
+    """nn.Conv2d / nn.Conv1d / nn.Linear applied through the tc doorways under autograd give the gradients of the library
+    route (cuDNN / cuBLAS, strict fp32) -- and really take the kernel route (launch counter)."""
+    import torch.nn as nn
+    from camliflow_b200 import native, tc, grad
+    g = torch.Generator().manual_seed(5)
+    conv = nn.Conv2d(128, 256, 3, padding=1).to(dev)
+    lin = nn.Linear(128, 64).to(dev)
+    c1d = nn.Conv1d(64, 32, 1).to(dev)
+    x = torch.randn(2, 128, 24, 40, generator=g).to(dev).requires_grad_(True)
+    p = torch.randn(2, 600, 128, generator=g).to(dev).requires_grad_(True)
+
+    def run(route):
+        old = tc.TRAIN_DENSE
+        tc.TRAIN_DENSE = route
+        try:
+            grad.clear_dense_cache()
+            for m in (conv, lin, c1d):
+                m.zero_grad()
+            n0 = native.launch_count()
+            y = tc.conv2d(x, conv, "relu")
+            f = tc.linear(p, lin.weight, lin.bias, "leaky_relu")
+            q = tc.module_train(c1d, f.transpose(1, 2))
+            q = c1d(f.transpose(1, 2)) if q is None else q
+            loss = y.square().mean() + q.square().mean()
+            gx, gp = torch.autograd.grad(loss, [x, p], retain_graph=True)
+            loss.backward()
+            grads = [gx, gp] + [t.grad.clone() for m in (conv, lin, c1d) for t in m.parameters()]
+            return float(loss), grads, native.launch_count() - n0
+        finally:
+            tc.TRAIN_DENSE = old
+
+    l_lib, g_lib, n_lib = run("library")
+    l_tc, g_tc, n_tc = run("tcgen05")
+    assert n_lib == 0 and n_tc >= 15                     # forward + backward kernels of three layers went through the C ABI
+    assert abs(l_lib - l_tc) <= 1e-6 * abs(l_lib)
+    for a, b in zip(g_tc, g_lib):
+        assert _rel(a, b) <= 2e-5
+
+
 @pytest.mark.parametrize("B,C,H,W", [(1, 64, 24, 40), (2, 32, 17, 30)])
 def test_corr2d_build_lookup_backward(dev, B, C, H, W):
     g = torch.Generator().manual_seed(42)
