@@ -101,11 +101,19 @@ def f_corr3d_lookup_rows(xyz1, W1, b1, W2, b2, k, n_levels, *rest):
     return torch.cat(costs, 1).transpose(1, 2)
 
 
+def _pointwise_relu(x, w, b):
+    """relu(conv1x1(x)) on [B,C,S,k]; on the GPU, where the layer qualifies (C % 4 == 0), forward and backward through the
+    hand-written dense-layer kernels (tc.conv_train -> DenseFn) instead of cuDNN."""
+    from . import tc
+    y = tc.conv_train(x, w[:, :, None, None], b, act="relu") if x.is_cuda else None
+    return F.relu(F.conv2d(x, w[:, :, None, None], b)) if y is None else y
+
+
 def f_pointconv_dw_weights(xyz, sampled_xyz, knn_idx, k, *params):
     """models/point_conv.py:122-127 -> [B,S,k,O]."""
     x = gather_cf(xyz, knn_idx[:, :, :k]) - sampled_xyz[:, :, :, None]
     for w, b in zip(params[0::2], params[1::2]):
-        x = F.relu(F.conv2d(x, w[:, :, None, None], b))
+        x = _pointwise_relu(x, w, b)
     return x.permute(0, 2, 3, 1)
 
 

@@ -63,6 +63,23 @@ def main():
             w_hi, w_lo, _ = ops.tc_weight([wt], lambda wt=wt: (wt, None))
             cases["conv_gemm_%dx%dx%d_%d->%d_%dx%d" % (cb, ch, cw, ci, co, kh, kw)] = \
                 lambda xin=xin, w_hi=w_hi, w_lo=w_lo, kh=kh, kw=kw: ops.conv_gemm(xin, w_hi, w_lo, kh, kw, None, "relu")
+        # the same layer at the three accumulator tile widths (tensor-pipe use per width)
+        xin = torch.randn(1, 68, 120, 256, generator=g).to(dev)
+        wt = (torch.randn(128, 5 * 256, generator=g) / (5 * 256) ** 0.5).to(dev)
+        w_hi, w_lo, _ = ops.tc_weight([wt], lambda: (wt, None))
+        for tn in (128, 64, 32):
+            cases["conv_gemm_1x68x120_256->128_1x5_tile%d" % tn] = \
+                lambda tn=tn: ops.conv_gemm(xin, w_hi, w_lo, 1, 5, None, "relu", tile_n=tn)
+        # training side: weight gradient of the motion encoder's 3x3 256 -> 192 layer and its pre-passes
+        xw = torch.randn(1, 68, 120, 256, generator=g).to(dev)
+        gw = torch.randn(1, 68, 120, 192, generator=g).to(dev)
+        gt = ops.transpose_split(gw)[:2]
+        xt = ops.transpose_split(xw, n_shift=3)[:2]
+        cases["transpose_split_x_3shifts_8160x256"] = lambda: ops.transpose_split(xw, n_shift=3)
+        cases["conv_wgrad_1x68x120_256->192_3x3"] = lambda: ops.conv_wgrad(gt, xt, 1, 68, 120, 192, 256, 3, 3)
+        cases["conv_wgrad_linear_2048x384->256"] = lambda: ops.conv_wgrad(
+            ops.transpose_split(torch.randn(1, 1, 2048, 256, device=dev))[:2], ops.transpose_split(torch.randn(1, 1, 2048, 384, device=dev))[:2],
+            1, 1, 2048, 256, 384, 1, 1)
         out = {}
         for name, fn in cases.items():
             fn()

@@ -108,6 +108,7 @@ ENTRY_POINTS = {          # ncu kernel name prefix -> C-ABI entry point (the key
     "corr2d_lookup_kernel": "camli_corr2d_lookup",
     "dw_gather_max": "camli_pointconv_dw_gather_max",
     "conv_gemm_tf32x3_kernel": "camli_conv_gemm_strided",
+    "conv_wgrad_tf32x3_kernel": "camli_conv_wgrad",
     "allpairs_tf32x3_kernel": "camli_allpairs_correlation",
     "fps_cluster_async_kernel": "camli_furthest_point_sampling",
     "corr3d_lookup_kernel": "camli_corr3d_lookup",
