@@ -86,6 +86,7 @@ struct CgParams {
     const float* aux2; long long ld2;
     int split;                     // columns >= split: GATE multiplies by aux1[:, n - split]; with out2 they go to out2
     float* out2; long long ldo2;
+    int passes;                    // 3: fp32-accurate 3xTF32 (default); 1: single tf32 product (10-bit mantissa operands, fp32 accumulate)
     long long* timeline;           // diagnostics: SM-clock stamps of CTA 0's pipeline events (null in production)
 };
 
@@ -325,12 +326,12 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t dst = tiles_base + stage * Cfg::kStageBytes;
-                    mbar_expect_tx(full, CG_A_BYTES + 2 * W_BYTES);
+                    mbar_expect_tx(full, CG_A_BYTES + (P.passes == 1 ? 1 : 2) * W_BYTES);
                     if (tile == blockIdx.x && kb == 0) CG_STAMP(14);
                     tma_load_4d(dst, &map_x, full, cb * CG_BK, x0 * P.stride + dx * P.dil, y0 * P.stride + dy * P.dil, b);
                     if (tile == blockIdx.x && kb == 0) CG_STAMP(15);
                     tma_load_2d(dst + CG_A_BYTES * 2, &map_whi, full, tap * P.Cin + cb * CG_BK, nt * BN);
-                    tma_load_2d(dst + CG_A_BYTES * 2 + W_BYTES, &map_wlo, full, tap * P.Cin + cb * CG_BK, nt * BN);
+                    if (P.passes != 1) tma_load_2d(dst + CG_A_BYTES * 2 + W_BYTES, &map_wlo, full, tap * P.Cin + cb * CG_BK, nt * BN);
                     if (tile == blockIdx.x && kb < 16) CG_STAMP(16 + kb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     if (++cb == cblocks) {
@@ -364,11 +365,17 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                         const uint32_t src = tiles_base + stage * Cfg::kStageBytes;
                         const uint64_t a_hi = make_kmajor_sw128_desc(src), a_lo = make_kmajor_sw128_desc(src + CG_A_BYTES);
                         const uint64_t b_hl = make_kmajor_sw128_desc(src + 2 * CG_A_BYTES);     // W_hi rows, then W_lo rows
+                        if (P.passes == 1) {                             // single product: A (truncated to tf32 by the tensor core) x W_hi
 #pragma unroll
-                        for (int k = 0; k < CG_BK / 8; ++k) {
-                            const uint64_t adv = (uint64_t)(k * 2);
-                            mma_tf32(tmem_main, a_hi + adv, b_hl + adv, IDESC_2N, ((kb - kb0) | k) ? 1u : 0u);
-                            mma_tf32(tmem_corr, a_lo + adv, b_hl + adv, IDESC_N, 1u);
+                            for (int k = 0; k < CG_BK / 8; ++k)
+                                mma_tf32(tmem_main, a_hi + (uint64_t)(k * 2), b_hl + (uint64_t)(k * 2), IDESC_N, ((kb - kb0) | k) ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < CG_BK / 8; ++k) {
+                                const uint64_t adv = (uint64_t)(k * 2);
+                                mma_tf32(tmem_main, a_hi + adv, b_hl + adv, IDESC_2N, ((kb - kb0) | k) ? 1u : 0u);
+                                mma_tf32(tmem_corr, a_lo + adv, b_hl + adv, IDESC_N, 1u);
+                            }
                         }
                         mma_commit(bar_empty + 8 * stage);
                         if (tile == blockIdx.x && kb < 16) CG_STAMP(48 + kb);
@@ -388,14 +395,16 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 if (t == 0 && tile == blockIdx.x && kb < 16) CG_STAMP(32 + kb);
-                const uint32_t a_hi = tiles_base + stage * Cfg::kStageBytes + t * 16, a_lo = a_hi + CG_A_BYTES;
-                float4 v[CG_A_BYTES / 16 / 128];                        // 8 chunks of 16 bytes per thread
+                if (P.passes != 1) {                                   // (single-pass mode: nothing to split, just hand the stage on)
+                    const uint32_t a_hi = tiles_base + stage * Cfg::kStageBytes + t * 16, a_lo = a_hi + CG_A_BYTES;
+                    float4 v[CG_A_BYTES / 16 / 128];                        // 8 chunks of 16 bytes per thread
 #pragma unroll
-                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i) v[i] = lds_v4(a_hi + i * 2048);
+                    for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i) v[i] = lds_v4(a_hi + i * 2048);
 #pragma unroll
-                for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i)
-                    sts_v4(a_lo + i * 2048, make_float4(cg_lo_part(v[i].x), cg_lo_part(v[i].y), cg_lo_part(v[i].z), cg_lo_part(v[i].w)));
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to UMMA
+                    for (int i = 0; i < CG_A_BYTES / 16 / 128; ++i)
+                        sts_v4(a_lo + i * 2048, make_float4(cg_lo_part(v[i].x), cg_lo_part(v[i].y), cg_lo_part(v[i].z), cg_lo_part(v[i].w)));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to UMMA
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_conv + 8 * stage);              // one arrival per converter warp
                 if (t == 0 && tile == blockIdx.x && kb < 16) CG_STAMP(64 + kb);
@@ -430,9 +439,11 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 #pragma unroll
                 for (int c = 0; c < CW / 32; ++c) {
                     float v[32];
-                    tmem_ld32(lane_base + acc * 2 * BN + BN + c * 32, v);           // corrections first (small)
+                    if (P.passes != 1) {
+                        tmem_ld32(lane_base + acc * 2 * BN + BN + c * 32, v);       // corrections first (small)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
+                        for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
+                    }
                     tmem_ld32(lane_base + acc * 2 * BN + c * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sum[c * 32 + j] += v[j];
@@ -605,7 +616,8 @@ extern "C" int camli_conv_gemm_strided(const float* x, int B, int Hin, int Win, 
     // (measured, M = 128), so a narrow tile does not shorten a CTA's k-loop -- it only multiplies the CTAs (and the
     // activation splits).  Few, wide CTAs also leave SMs free for the kernels of the other branch's stream: the
     // C_out <= 128 convolutions of the update block occupy 68 SMs instead of 136, a point-branch linear 16 instead of 64.
-    int bn = tile_n;
+    P.passes = (tile_n & CAMLI_CONV_SINGLE_PASS) ? 1 : 3;
+    int bn = tile_n & 0xff;
     if (bn == 0) bn = Cout > 64 ? 128 : (Cout > 32 ? 64 : 32);
     if (bn != 32 && bn != 64 && bn != 128) return CAMLI_EINVAL;
     P.tiles_n = camli_div_up(Cout, bn);

@@ -50,6 +50,7 @@ struct WgParams {
     int kblocks;                 // B * H * wblocks
     int splits, kb_per_split;
     int tiles_m, tiles_n;
+    int passes;                  // 3: 3xTF32 (fp32-accurate), 1: hi x hi only (tf32 operands)
     float* dw;                   // [Cout, kh*kw*Cin], zeroed by the caller
     long long ldw;
 };
@@ -110,11 +111,13 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t dst = tiles_base + stage * WG_STAGE_BYTES;
-                        mbar_expect_tx(full, WG_STAGE_BYTES);
+                        mbar_expect_tx(full, P.passes == 1 ? 2 * WG_TILE_BYTES : WG_STAGE_BYTES);
                         tma_load_5d(dst + 0 * WG_TILE_BYTES, &map_g_hi, full, xb * WG_BK, y, b, mt * WG_BM, 0);
-                        tma_load_5d(dst + 1 * WG_TILE_BYTES, &map_g_lo, full, xb * WG_BK, y, b, mt * WG_BM, 0);
                         tma_load_5d(dst + 2 * WG_TILE_BYTES, &map_x_hi, full, xb * WG_BK, y + dy, b, nt * WG_BN, sx);
-                        tma_load_5d(dst + 3 * WG_TILE_BYTES, &map_x_lo, full, xb * WG_BK, y + dy, b, nt * WG_BN, sx);
+                        if (P.passes != 1) {
+                            tma_load_5d(dst + 1 * WG_TILE_BYTES, &map_g_lo, full, xb * WG_BK, y, b, mt * WG_BM, 0);
+                            tma_load_5d(dst + 3 * WG_TILE_BYTES, &map_x_lo, full, xb * WG_BK, y + dy, b, nt * WG_BN, sx);
+                        }
                         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                     }
                     if (++xb == P.wblocks) { xb = 0; if (++y == P.H) { y = 0; ++b; } }
@@ -149,8 +152,10 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
                         for (int k = 0; k < WG_BK / 8; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);
                             mma_tf32(tmem_d, a_hi + adv, b_hi + adv, WG_IDESC, started | (uint32_t)k);
-                            mma_tf32(tmem_d, a_hi + adv, b_lo + adv, WG_IDESC, 1u);
-                            mma_tf32(tmem_d, a_lo + adv, b_hi + adv, WG_IDESC, 1u);
+                            if (P.passes != 1) {
+                                mma_tf32(tmem_d, a_hi + adv, b_lo + adv, WG_IDESC, 1u);
+                                mma_tf32(tmem_d, a_lo + adv, b_hi + adv, WG_IDESC, 1u);
+                            }
                         }
                         started = 1u;
                         mma_commit(bar_empty + 8 * stage);
@@ -273,7 +278,7 @@ transpose_split_kernel(const float* __restrict__ x, long long ld, long long P, i
                 float h, l;
                 split_tf32(s_t[tx][ty + 8 * i], h, l);
                 hj[(long long)c * ldt + p] = h;
-                lj[(long long)c * ldt + p] = l;
+                if (lo_t) lj[(long long)c * ldt + p] = l;
             }
         }
         __syncthreads();
@@ -303,7 +308,7 @@ extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, i
     if (n_shift > 1 && (y_rows || g_rows || colsum || P % W)) return CAMLI_EINVAL;   // shifted copies: plain activations only
     if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EUNSUPPORTED;
     if (P == 0) return CAMLI_OK;
-    if (!rows || !hi_t || !lo_t) return CAMLI_EINVAL;
+    if (!rows || !hi_t) return CAMLI_EINVAL;                                          // lo_t == NULL: hi parts only
     if (camli_div_up_ll(P, 32) > 2147483647LL) return CAMLI_EUNSUPPORTED;
     const dim3 grid((unsigned)camli_div_up_ll(P, 32), (unsigned)camli_div_up(C, 32));
     transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
@@ -312,12 +317,15 @@ extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, i
 }
 
 extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
-                                int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation,
+                                int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int passes,
                                 float* dw, void* stream) {
+    if (passes != 1 && passes != 3) return CAMLI_EINVAL;
     if (B < 0 || H < 1 || W < 1 || Cout < 1 || Cin < 1 || kh < 1 || kw < 1 || dilation < 1) return CAMLI_EINVAL;
     if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (W & 3) || (Cin & 3) || dilation > 64) return CAMLI_EUNSUPPORTED;
     if (B == 0) return CAMLI_OK;
-    if (!g_hi_t || !g_lo_t || !x_hi_t || !x_lo_t || !dw) return CAMLI_EINVAL;
+    if (!g_hi_t || !x_hi_t || !dw) return CAMLI_EINVAL;
+    if (passes == 1) { g_lo_t = g_hi_t; x_lo_t = x_hi_t; }                          // (never read)
+    if (!g_lo_t || !x_lo_t) return CAMLI_EINVAL;
     if ((reinterpret_cast<uintptr_t>(g_hi_t) | reinterpret_cast<uintptr_t>(g_lo_t) | reinterpret_cast<uintptr_t>(x_hi_t) |
          reinterpret_cast<uintptr_t>(x_lo_t) | reinterpret_cast<uintptr_t>(dw)) & 15)
         return CAMLI_EINVAL;
@@ -336,6 +344,7 @@ extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const 
     if (splits < 1) splits = 1;
     P.splits = (int)splits;
     P.kb_per_split = (int)((kblocks + splits - 1) / splits);
+    P.passes = passes;
     P.dw = dw; P.ldw = (long long)kh * kw * Cin;
     const long long total = base_tiles * splits;
     if (total > 2147483647LL) return CAMLI_EUNSUPPORTED;

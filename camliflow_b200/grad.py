@@ -240,18 +240,21 @@ class DenseFn(torch.autograd.Function):
     the hand-written tensor-core kernels: forward = camli_conv_gemm; backward = camli_transpose_split (activation derivative,
     bias gradient, K-major operands), camli_conv_gemm on the mirrored weights (data gradient), camli_conv_wgrad (weight
     gradient).  Replaces, for training, what autograd does with cuDNN / cuBLAS in the reference (train.py:143-171).
-    x_rows [B,H,W,Cin] contiguous fp32, weight [O,I,kh,kw], bias [O] or None -> [B,H,W,O]."""
+    x_rows [B,H,W,Cin] contiguous fp32, weight [O,I,kh,kw], bias [O] or None -> [B,H,W,O].
+    passes = 3: every product is 3xTF32 (fp32-accurate; the parity mode).  passes = 1: one tf32 product per element in all
+    three GEMMs -- the mode tc picks under bf16 / fp16 autocast, where the caller asked for reduced-precision dense layers
+    (a tf32 operand keeps 10 mantissa bits, a bf16 one 7); accumulation, bias, activations and gradients stay fp32."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x_rows, weight, bias, act, slope, dilation):
+    def forward(ctx, x_rows, weight, bias, act, slope, dilation, passes=3):
         from . import ops
         kh, kw = weight.shape[2:]
         w_hi, w_lo = _dense_weight(weight, False)
         x_rows = x_rows.contiguous()
         y = ops.conv_gemm(x_rows, w_hi, w_lo, kh, kw, None if bias is None else bias.detach().float().contiguous(), act, slope,
-                          dilation=dilation)
-        ctx.act, ctx.slope, ctx.dilation = act, slope, dilation
+                          dilation=dilation, single_pass=passes == 1)
+        ctx.act, ctx.slope, ctx.dilation, ctx.passes = act, slope, dilation, passes
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x_rows, weight, y if act is not None else None)
         return y
@@ -265,20 +268,22 @@ class DenseFn(torch.autograd.Function):
         B, H, W, Cin = x_rows.shape
         O, _, kh, kw = weight.shape
         gy = gy.float().contiguous()
-        g_hi, g_lo, g_rows, db = ops.transpose_split(gy, y, ctx.act, ctx.slope, want_rows=need_x, want_colsum=need_b)
+        fast = ctx.passes == 1
+        g_hi, g_lo, g_rows, db = ops.transpose_split(gy, y, ctx.act, ctx.slope, want_rows=need_x, want_colsum=need_b,
+                                                     want_lo=not fast)
         if y is None:
             g_rows = gy
         dx = dw = None
         if need_x:
             if O % 4 == 0:
                 wt_hi, wt_lo = _dense_weight(weight, True)
-                dx = ops.conv_gemm(g_rows, wt_hi, wt_lo, kh, kw, dilation=ctx.dilation)
+                dx = ops.conv_gemm(g_rows, wt_hi, wt_lo, kh, kw, dilation=ctx.dilation, single_pass=fast)
             else:                                    # TMA rows are 16-byte granular: ragged gradient rows (C_out = 2, 125, 126)
                 pad = (ctx.dilation * (kh // 2), ctx.dilation * (kw // 2))
                 dx = torch.nn.grad.conv2d_input((B, Cin, H, W), weight.float(), g_rows.permute(0, 3, 1, 2), padding=pad,
                                                 dilation=ctx.dilation).permute(0, 2, 3, 1)
         if need_w:
-            x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation)
-            dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation)
+            x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation, want_lo=not fast)
+            dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation, ctx.passes)
             dw = dw2d.view(O, kh, kw, Cin).permute(0, 3, 1, 2).to(weight.dtype)
-        return dx, dw, (db.to(weight.dtype) if need_b else None), None, None, None
+        return dx, dw, (db.to(weight.dtype) if need_b else None), None, None, None, None

@@ -281,13 +281,14 @@ def conv_gemm_ok(x_bhwc, kh=1, kw=1):
 
 
 def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residual=None, out=None, tile_n=0,
-              aux1=None, aux2=None, split=0, out2=None, stride=1, dilation=1):
+              aux1=None, aux2=None, split=0, out2=None, stride=1, dilation=1, single_pass=False):
     """Linear layer / stride-1 "same" convolution + bias + residual + activation in one tcgen05 kernel
     (include/camli_b200.h: camli_conv_gemm).  x_bhwc [B,H,W,Cin] channel-last view (a linear layer over rows
     is [1,1,R,K]); w_hi/w_lo [Cout, kh*kw*Cin] from tc_weight(); residual / out [B,H,W,Cout] channel-last views
     (out may be a channel slice of a wider buffer).  act "gru_gate" / "gru_update[_fix]" fuse the ConvGRU
     arithmetic (camli_conv_gemm_fused): aux1 / aux2 [B,H,W,*] channel-last side inputs, columns >= split of a gate
     convolution go to out2.  stride 2 (padding k/2): the output grid is ceil(H/2) x ceil(W/2) (camli_conv_gemm_strided).
+    single_pass: ONE tf32 product instead of three (CAMLI_CONV_SINGLE_PASS; training under bf16 autocast only).
     Returns out."""
     _need_cuda(x_bhwc, w_hi, w_lo)
     _no_grad("conv_gemm", x_bhwc, w_hi)
@@ -316,7 +317,7 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
                     ctypes.c_float(slope), ptr(out), i64(ldo),
                     ptr(aux1), i64(_pixel_layout(aux1)[0] if aux1 is not None else 0),
                     ptr(aux2), i64(_pixel_layout(aux2)[0] if aux2 is not None else 0), i32(split),
-                    ptr(out2), i64(_pixel_layout(out2)[0] if out2 is not None else 0), i32(tile_n), stream(),
+                    ptr(out2), i64(_pixel_layout(out2)[0] if out2 is not None else 0), i32(tile_n | (0x100 if single_pass else 0)), stream(),
                     algo_bytes=B * (H * W * Cin + Ho * Wo * Cout) * 4 + Cout * kh * kw * Cin * 4,
                     flops=2 * B * Ho * Wo * Cout * kh * kw * Cin, shape=(B * Ho * Wo, Cout, kh * kw * Cin))   # GEMM M, N, K
     return out
@@ -401,7 +402,7 @@ def split_tf32(w2d):
     return hi, lo
 
 
-def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_colsum=False, n_shift=1, shift_step=1):
+def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_colsum=False, n_shift=1, shift_step=1, want_lo=True):
     """rows [B,H,W,C] channel-last view -> (hi_t, lo_t [C, B*H*W], g_rows, colsum): the transposed tf32 parts the
     weight-gradient GEMM reads (camli_transpose_split).  With `y` (the layer output, same shape) rows is dL/dy: it is
     multiplied by act'(y) first; g_rows [B,H,W,C] = that product (operand of the data-gradient convolution), colsum [C] =
@@ -413,7 +414,7 @@ def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_col
         raise RuntimeError("transpose_split: channel-last rows expected")
     P = B * H * W
     hi_t = torch.empty((n_shift, C, P) if n_shift > 1 else (C, P), dtype=torch.float32, device=rows.device)
-    lo_t = torch.empty_like(hi_t)
+    lo_t = torch.empty_like(hi_t) if want_lo else None
     g_rows = torch.empty((B, H, W, C), dtype=torch.float32, device=rows.device) if (want_rows and y is not None) else None
     colsum = torch.zeros((C,), dtype=torch.float32, device=rows.device) if want_colsum else None
     ldy = _pixel_layout(y)[0] if y is not None else 0
@@ -424,13 +425,13 @@ def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_col
     return hi_t, lo_t, g_rows, colsum
 
 
-def conv_wgrad(g_t, x_t, B, H, W, Cout, Cin, kh, kw, dilation=1):
+def conv_wgrad(g_t, x_t, B, H, W, Cout, Cin, kh, kw, dilation=1, passes=3):
     """dW [Cout, kh*kw*Cin] (OHWI) of the stride-1 "same" convolution from the transposed hi / lo operand pairs of
-    transpose_split (camli_conv_wgrad: 3xTF32 on tcgen05, K split over the SMs)."""
+    transpose_split (camli_conv_wgrad: 3xTF32 on tcgen05, K split over the SMs; passes = 1: one tf32 product, lo parts unused)."""
     dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=g_t[0].device)
     with torch.cuda.device(dw.device):
         native.call("camli_conv_wgrad", ptr(g_t[0]), ptr(g_t[1]), ptr(x_t[0]), ptr(x_t[1]), i32(B), i32(H), i32(W), i32(Cout),
-                    i32(Cin), i32(kh), i32(kw), i32(dilation), ptr(dw), stream(),
+                    i32(Cin), i32(kh), i32(kw), i32(dilation), i32(passes), ptr(dw), stream(),
                     algo_bytes=2 * B * H * W * (Cout + Cin) * 4 + Cout * kh * kw * Cin * 4,
                     flops=2 * B * H * W * Cout * kh * kw * Cin, shape=(Cout, kh * kw * Cin, B * H * W))
     return dw

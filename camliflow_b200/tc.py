@@ -21,6 +21,11 @@ TRAIN_DENSE = os.environ.get("CAMLI_TRAIN_DENSE", "tcgen05")
 _DENSE_ACTS = (None, "relu", "leaky_relu", "tanh", "sigmoid")
 
 
+def _train_passes():
+    """3xTF32 (fp32-accurate) unless the caller runs the step under reduced-precision autocast: then one tf32 product."""
+    return 1 if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") in (torch.bfloat16, torch.float16) else 3
+
+
 def _train_route(x):
     return (ENABLED and TRAIN_DENSE == "tcgen05" and x.is_cuda and torch.is_grad_enabled()
             and x.dtype in (torch.float32, torch.bfloat16, torch.float16))
@@ -40,7 +45,7 @@ def conv_train(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), 
     B, _, H, W = x.shape
     if not ops.conv_wgrad_ok(B, H, W, I) or B * H * W < 128:
         return None
-    return grad.DenseFn.apply(x.permute(0, 2, 3, 1), weight, bias, act, slope, d).permute(0, 3, 1, 2)
+    return grad.DenseFn.apply(x.permute(0, 2, 3, 1), weight, bias, act, slope, d, _train_passes()).permute(0, 3, 1, 2)
 
 
 def linear_train(x, weight2d, bias, act=None, slope=0.1):
@@ -53,7 +58,7 @@ def linear_train(x, weight2d, bias, act=None, slope=0.1):
     R = rows.shape[2]
     if x.shape[-1] != K or not ops.conv_wgrad_ok(1, 1, R, K) or R < 128:
         return None
-    y = grad.DenseFn.apply(rows, weight2d.view(N, K, 1, 1), bias, act, slope, 1)
+    y = grad.DenseFn.apply(rows, weight2d.view(N, K, 1, 1), bias, act, slope, 1, _train_passes())
     return y.view(*x.shape[:-1], N)
 
 

@@ -268,14 +268,15 @@ int camli_allpairs_correlation(const float* a_rows, const float* b_rows, float* 
  * camli_conv_wgrad: dw[n, tap*Cin + c] = sum over pixels of g[p, n] * x[p (+) tap, c] for the stride-1 "same" convolution /
  * linear layer of camli_conv_gemm (OHWI layout, [Cout, kh*kw*Cin]); operands are the [C, B, H, W] hi / lo tensors of
  * camli_transpose_split, x with n_shift = kw, shift_step = dilation.  3xTF32 on tcgen05, K split over the SMs, partial tiles added with 128-bit atomics (dw is zeroed
- * inside).  W % 4 == 0, Cin % 4 == 0, odd windows.  The data gradient needs no kernel of its own: it is camli_conv_gemm of
+ * inside).  W % 4 == 0, Cin % 4 == 0, odd windows.  passes = 3: 3xTF32; passes = 1: the hi parts only (one tf32 product, the
+ * reduced-precision mode of the bf16-autocast training step; the lo tensors may then be NULL, also in camli_transpose_split).  The data gradient needs no kernel of its own: it is camli_conv_gemm of
  * g_rows with the spatially flipped, in/out-transposed weights.
  */
 int camli_transpose_split(const float* rows, int64_t ld, int64_t P, int C, const float* y_rows, int64_t ldy,
                           int act, float slope, int W, int n_shift, int shift_step,
                           float* hi_t, float* lo_t, float* g_rows, float* colsum, void* stream);
 int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
-                     int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, float* dw, void* stream);
+                     int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int passes, float* dw, void* stream);
 
 /*
  * SK fusion tail (SKFusion.forward after the align layers, models/clfm.py:199-214):
@@ -318,6 +319,7 @@ int camli_gru_update(int64_t n, const float* z, const float* h, const float* q, 
 /* OR-ed onto NONE / RELU / LEAKY / TANH / SIGMOID: torch.nan_to_num of the activated value (nan -> 0, +-inf -> +-FLT_MAX),
  * the guard the reference puts behind its motion encoder and flow heads (models/raft_core.py:164,180) */
 #define CAMLI_ACT_FIX_NONFINITE  16
+#define CAMLI_CONV_SINGLE_PASS   0x100   /* flag in the tile_n argument of camli_conv_gemm* (see there) */
 
 /* x -> (hi, lo) with hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand split of the 3xTF32
  * tensor-core kernels; used once per weight tensor. */
@@ -334,7 +336,9 @@ int camli_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stre
  * w_hi/lo  [Cout, kh*kw*Cin] f32 = camli_split_tf32 of the OHWI (channels_last) weight; kh, kw odd.
  * bias     [Cout] or NULL; residual [B*H*W, ldr] or NULL; act = CAMLI_ACT_*.
  * out      [B*H*W, ldo] f32: ldo >= Cout lets the layer write a channel slice of a wider tensor.
- * tile_n   0 = automatic; else 32 / 64 / 128 (accumulator tile width).
+ * tile_n   0 = automatic; else 32 / 64 / 128 (accumulator tile width).  | CAMLI_CONV_SINGLE_PASS: ONE tf32 product per
+ *          element instead of three (operands cut to 10-bit mantissas, fp32 accumulation) -- the reduced-precision mode the
+ *          training step uses under bf16 autocast (a tf32 operand is more accurate than a bf16 one); parity paths never set it.
  */
 int camli_conv_gemm(const float* x, int B, int H, int W, int Cin, int64_t ldx,
                     const float* w_hi, const float* w_lo, int Cout, int kh, int kw,

@@ -86,6 +86,38 @@ def test_dense_layer_backward_kernels(dev, B, H, W, Cin, Cout, kh, kw, dil, act,
         assert _rel(a.double(), r) <= 2e-5, n            # fp32-level: 3xTF32 products, fp32 accumulation
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw,act", [(1, 68, 120, 256, 192, 3, 3, "relu"), (1, 1, 2048, 384, 256, 1, 1, None)])
+def test_dense_layer_single_pass_mode(dev, B, H, W, Cin, Cout, kh, kw, act):
+    """passes = 1 (the mode picked under bf16 autocast): one tf32 product per element in forward, data gradient and weight
+    gradient -- tf32-operand accuracy (10-bit mantissas, fp32 accumulation), far inside what bf16 layers deliver."""
+    import torch.nn.functional as F
+    from camliflow_b200 import grad
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).to(dev).requires_grad_(True)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev).requires_grad_(True)
+    gy = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    grad.clear_dense_cache()
+    y = grad.DenseFn.apply(x, w, b, act, 0.1, 1, 1)
+    got = torch.autograd.grad(y, [x, w, b], gy)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yd = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=(kh // 2, kw // 2))
+    yd = (torch.relu(yd) if act == "relu" else yd).permute(0, 2, 3, 1)
+    # gradients against the reference with the kernel's OWN ReLU decisions (an output within rounding of zero may land on the
+    # other side in any reduced-precision forward; that flips whole gradient entries and says nothing about the GEMMs)
+    ylin = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=(kh // 2, kw // 2)).permute(0, 2, 3, 1)
+    gmask = gy.double() * (y.detach() > 0).double() if act == "relu" else gy.double()
+    ref = torch.autograd.grad(ylin, [xd, wd, bd], gmask)
+    errs = [_rel(y.double(), yd)] + [_rel(a.double(), r) for a, r in zip(got, ref)]
+    xb, wb = x.detach().bfloat16().float().double(), w.detach().bfloat16().float().double()       # what bf16 operands would give
+    yb = F.conv2d(xb.permute(0, 3, 1, 2), wb, bd.detach(), padding=(kh // 2, kw // 2))
+    yb = (torch.relu(yb) if act == "relu" else yb).permute(0, 2, 3, 1)
+    print("single pass %s: y %.2e dx %.2e dw %.2e db %.2e (bf16-rounded operands: y %.2e)" %
+          ((B, H, W, Cin, Cout, kh, kw, act), errs[0], errs[1], errs[2], errs[3], _rel(yb, yd)))
+    assert max(errs[:3]) <= 2e-3 and errs[3] <= 2e-5
+    assert errs[0] <= _rel(yb, yd)
+
+
 def test_dense_layers_route_through_the_kernels_under_autograd(dev):
     """nn.Conv2d / nn.Conv1d / nn.Linear applied through the tc doorways under autograd give the gradients of the library
     route (cuDNN / cuBLAS, strict fp32) -- and really take the kernel route (launch counter)."""
