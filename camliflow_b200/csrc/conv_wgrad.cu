@@ -228,57 +228,88 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
 // gradient: it is first multiplied by the derivative of the layer's activation at its OUTPUT y (relu / leaky: sign of y;
 // tanh: 1 - y^2; sigmoid: y (1 - y)) and -- with `g_rows` -- also written back row-major (the operand of the
 // data-gradient convolution); `colsum` [C] accumulates the bias gradient (atomics, zeroed by the caller).
+// Tile: 32 pixels x 128 channels per CTA (256 threads).  Load: a thread reads one float4 (4 channels) of 4 pixels -- a warp
+// covers whole 512-byte rows; store: a warp writes 32 consecutive pixels (128 bytes) of one channel, 16 channels per thread.
+constexpr int TS_PX = 32, TS_CH = 128;
+
 __global__ void __launch_bounds__(256)
-transpose_split_kernel(const float* __restrict__ x, long long ld, long long P, int C, const float* __restrict__ y, long long ldy,
+transpose_split_kernel(const float* __restrict__ x, long long ld, int P, int C, const float* __restrict__ y, long long ldy,
                        int act, float slope, float* __restrict__ hi_t, float* __restrict__ lo_t, long long ldt,
                        float* __restrict__ g_rows, float* __restrict__ colsum, int W, int n_shift, int shift_step) {
-    __shared__ float s_t[32][33];
-    __shared__ float s_sum[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                          // 32 x 8
-    const long long p0 = (long long)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
+    __shared__ float s_t[TS_PX][TS_CH + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p0 = blockIdx.x * TS_PX, c0 = blockIdx.y * TS_CH;
+    const int cq = (tid & 31) * 4, pr = tid >> 5;                                    // load side: 4 channels, pixel rows pr + 8 i
+    const bool vec = ((ld | ldy) & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                     (C & 3) == 0;
     for (int j = 0; j < n_shift; ++j) {
         const int shift = (j - n_shift / 2) * shift_step;                            // copy j holds the rows shifted by `shift` pixels
-        float part = 0.f;
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long p = p0 + ty + 8 * i;
-            const int c = c0 + tx;
-            float v = 0.f;
+        for (int i = 0; i < TS_PX / 8; ++i) {
+            const int p = p0 + pr + 8 * i, c = c0 + cq;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (p < P && c < C) {
-                const int xs = (int)(p % W) + shift;                                 // stays inside its image row, or reads zero
-                if ((unsigned)xs < (unsigned)W) v = __ldg(x + (p + shift) * ld + c);
+                const int xs = p % W + shift;                                        // stays inside its image row, or reads zero
+                const bool inside = (unsigned)xs < (unsigned)W;
+                const float* src = x + (long long)(p + shift) * ld + c;
+                float o[4] = {1.f, 1.f, 1.f, 1.f};
+                if (vec) {
+                    if (inside) { const float4 t = __ldg(reinterpret_cast<const float4*>(src)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+                    if (y) { const float4 t = __ldg(reinterpret_cast<const float4*>(y + (long long)p * ldy + c)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (c + e < C) {
+                            if (inside) v[e] = __ldg(src + e);
+                            if (y) o[e] = __ldg(y + (long long)p * ldy + c + e);
+                        }
+                    }
+                }
                 if (y) {
-                    const float o = __ldg(y + p * ldy + c);
-                    if (act == CAMLI_ACT_RELU) v = o > 0.f ? v : 0.f;
-                    else if (act == CAMLI_ACT_LEAKY) v = o > 0.f ? v : v * slope;
-                    else if (act == CAMLI_ACT_TANH) v = v * (1.f - o * o);
-                    else if (act == CAMLI_ACT_SIGMOID) v = v * o * (1.f - o);
-                    if (g_rows) g_rows[p * C + c] = v;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (act == CAMLI_ACT_RELU) v[e] = o[e] > 0.f ? v[e] : 0.f;
+                        else if (act == CAMLI_ACT_LEAKY) v[e] = o[e] > 0.f ? v[e] : v[e] * slope;
+                        else if (act == CAMLI_ACT_TANH) v[e] = v[e] * (1.f - o[e] * o[e]);
+                        else if (act == CAMLI_ACT_SIGMOID) v[e] = v[e] * o[e] * (1.f - o[e]);
+                    }
+                    if (g_rows) {
+                        float* d = g_rows + (long long)p * C + c;
+                        if (vec) *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (c + e < C) d[e] = v[e];
+                        }
+                    }
                 }
             }
-            part += v;
-            s_t[ty + 8 * i][tx] = v;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { part[e] += v[e]; s_t[pr + 8 * i][cq + e] = v[e]; }
         }
-        if (colsum) s_sum[ty][tx] = part;
         __syncthreads();
-        if (colsum && ty == 0 && c0 + tx < C) {                                      // bias gradient: column sums of this block
-            float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t += s_sum[i][tx];
-            atomicAdd(colsum + c0 + tx, t);
+        if (colsum) {                                                                // bias gradient: column sums of this tile
+            for (int c = tid; c < TS_CH; c += 256) {
+                if (c0 + c < C) {
+                    float t = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < TS_PX; ++r) t += s_t[r][c];
+                    atomicAdd(colsum + c0 + c, t);
+                }
+            }
         }
+        (void)part;
         float* __restrict__ hj = hi_t + (long long)j * C * ldt;
-        float* __restrict__ lj = lo_t + (long long)j * C * ldt;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = c0 + ty + 8 * i;
-            const long long p = p0 + tx;
+        float* __restrict__ lj = lo_t ? lo_t + (long long)j * C * ldt : nullptr;
+        const int p = p0 + lane;
+#pragma unroll 4
+        for (int i = 0; i < TS_CH / 8; ++i) {
+            const int c = c0 + warp + 8 * i;
             if (c < C && p < P) {
                 float h, l;
-                split_tf32(s_t[tx][ty + 8 * i], h, l);
+                split_tf32(s_t[lane][warp + 8 * i], h, l);
                 hj[(long long)c * ldt + p] = h;
-                if (lo_t) lj[(long long)c * ldt + p] = l;
+                if (lj) lj[(long long)c * ldt + p] = l;
             }
         }
         __syncthreads();
@@ -309,9 +340,9 @@ extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, i
     if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EUNSUPPORTED;
     if (P == 0) return CAMLI_OK;
     if (!rows || !hi_t) return CAMLI_EINVAL;                                          // lo_t == NULL: hi parts only
-    if (camli_div_up_ll(P, 32) > 2147483647LL) return CAMLI_EUNSUPPORTED;
-    const dim3 grid((unsigned)camli_div_up_ll(P, 32), (unsigned)camli_div_up(C, 32));
-    transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
+    if (P > 2147483647LL - 64) return CAMLI_EUNSUPPORTED;
+    const dim3 grid((unsigned)camli_div_up_ll(P, TS_PX), (unsigned)camli_div_up(C, TS_CH));
+    transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, (int)P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
                                                                    g_rows, colsum, W, n_shift, shift_step);
     CAMLI_RETURN_LAUNCH_STATUS();
 }

@@ -147,8 +147,15 @@ class GRU2D(nn.Module):
 
     def _half(self, h, x, convz, convr, convq):
         hx = torch.cat([h, x], dim=1)
-        z = tc.conv2d(hx, convz, "sigmoid")              # (under autograd: grad.DenseFn, activation in the epilogue)
-        r = tc.conv2d(hx, convr, "sigmoid")
+        if tc._train_route(hx):
+            # training on the GPU: z and r read the same input -- ONE 256-output convolution (the concatenation of the two
+            # weights is differentiable), forward and backward on the tensor-core kernels, sigmoid in the epilogue
+            zr = tc.conv2d_weights(hx, torch.cat([convz.weight, convr.weight], 0), torch.cat([convz.bias, convr.bias], 0),
+                                   convz.padding, "sigmoid")
+            z, r = torch.split(zr, [h.shape[1], h.shape[1]], dim=1)
+        else:
+            z = tc.conv2d(hx, convz, "sigmoid")
+            r = tc.conv2d(hx, convr, "sigmoid")
         q = tc.conv2d(torch.cat([r * h, x], dim=1), convq, "tanh")
         return (1 - z) * h + z * q
 

@@ -20,11 +20,12 @@ g = torch.Generator().manual_seed(1)
 inp["flow_2d"] = torch.randn(B, 2, H, W, generator=g) * 5
 inp["flow_3d"] = torch.randn(B, 3, N, generator=g) * 0.1
 inp = {k: v.to(dev) for k, v in inp.items()}
+amp = torch.bfloat16 if os.environ.get("TRACE_AMP", "1") == "1" else None
 for _ in range(2):
-    trainer.train_step(model, opt, inp)
+    trainer.train_step(model, opt, inp, autocast_dtype=amp)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=False) as prof:
-    trainer.train_step(model, opt, inp)
+    trainer.train_step(model, opt, inp, autocast_dtype=amp)
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in prof.events():
@@ -33,7 +34,8 @@ for e in prof.events():
         agg[e.name[:100]][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
 tot = sum(v[1] for v in agg.values())
 print("total kernel time %.1f ms over %d kernels" % (tot / 1e3, sum(v[0] for v in agg.values())))
-for n, (c, u) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+for n, (c, u) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print("%6d %9.1f us %5.1f%%  %s" % (c, u, 100 * u / tot, n))
 # CPU-side op totals (which autograd nodes dominate)
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60)[:6000])
+if os.environ.get("TRACE_OPS"):
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60)[:6000])
