@@ -275,13 +275,8 @@ class DenseFn(torch.autograd.Function):
             g_rows = gy
         dx = dw = None
         if need_x:
-            if O % 4 == 0:
-                wt_hi, wt_lo = _dense_weight(weight, True)
-                dx = ops.conv_gemm(g_rows, wt_hi, wt_lo, kh, kw, dilation=ctx.dilation, single_pass=fast)
-            else:                                    # TMA rows are 16-byte granular: ragged gradient rows (C_out = 2, 125, 126)
-                pad = (ctx.dilation * (kh // 2), ctx.dilation * (kw // 2))
-                dx = torch.nn.grad.conv2d_input((B, Cin, H, W), weight.float(), g_rows.permute(0, 3, 1, 2), padding=pad,
-                                                dilation=ctx.dilation).permute(0, 2, 3, 1)
+            wt_hi, wt_lo = _dense_weight(weight, True)          # (callers pad C_out to a multiple of 4: tc._pad_dense)
+            dx = ops.conv_gemm(g_rows, wt_hi, wt_lo, kh, kw, dilation=ctx.dilation, single_pass=fast)
         if need_w:
             x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation, want_lo=not fast)
             dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation, ctx.passes)

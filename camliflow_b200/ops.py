@@ -270,6 +270,10 @@ def _pixel_layout(t):
 # graphs in flight.  "latency": layers of <= 74 pixel tiles with 64 < C_out <= 128 and a long k-loop use 64-wide tiles (twice
 # the CTAs, ~15-30 % shorter).  A property of the graph being captured: FlowEngine(tile_policy=...) sets it around its capture.
 TILE_POLICY = os.environ.get("CAMLI_TILE_POLICY", "throughput")
+# Inference-side precision switch of the dense kernel (NOT a parity mode): True = one tf32 product per element instead of
+# three, what torch's default `cudnn.allow_tf32 = True` gives the reference's own convolutions on an Ampere+ GPU.  The parity
+# tests, smoke() and the default bench line run with False.
+SINGLE_PASS_INFERENCE = os.environ.get("CAMLI_CONV_PRECISION", "fp32") == "tf32"
 
 
 def conv_gemm_ok(x_bhwc, kh=1, kw=1):
@@ -317,7 +321,8 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
                     ctypes.c_float(slope), ptr(out), i64(ldo),
                     ptr(aux1), i64(_pixel_layout(aux1)[0] if aux1 is not None else 0),
                     ptr(aux2), i64(_pixel_layout(aux2)[0] if aux2 is not None else 0), i32(split),
-                    ptr(out2), i64(_pixel_layout(out2)[0] if out2 is not None else 0), i32(tile_n | (0x100 if single_pass else 0)), stream(),
+                    ptr(out2), i64(_pixel_layout(out2)[0] if out2 is not None else 0),
+                    i32(tile_n | (0x100 if (single_pass or (SINGLE_PASS_INFERENCE and not torch.is_grad_enabled())) else 0)), stream(),
                     algo_bytes=B * (H * W * Cin + Ho * Wo * Cout) * 4 + Cout * kh * kw * Cin * 4,
                     flops=2 * B * Ho * Wo * Cout * kh * kw * Cin, shape=(B * Ho * Wo, Cout, kh * kw * Cin))   # GEMM M, N, K
     return out

@@ -31,6 +31,20 @@ def _train_route(x):
             and x.dtype in (torch.float32, torch.bfloat16, torch.float16))
 
 
+def _pad_dense(x_rows, weight4d, bias):
+    """Zero-pad the channel dimensions the kernels need 16-byte granular (TMA rows): input channels of x and weight, output
+    channels of weight and bias.  Plain differentiable pads: autograd slices the gradients back."""
+    O, I = weight4d.shape[:2]
+    pi, po = (-I) % 4, (-O) % 4
+    if pi:
+        x_rows = F.pad(x_rows, (0, pi))
+        weight4d = F.pad(weight4d, (0, 0, 0, 0, 0, pi))
+    if po:
+        weight4d = F.pad(weight4d, (0, 0, 0, 0, 0, 0, 0, po))
+        bias = None if bias is None else F.pad(bias, (0, po))
+    return x_rows, weight4d, bias, O
+
+
 def conv_train(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1, act=None, slope=0.1):
     """Training route of a convolution on a logical [B,C,H,W] tensor: act(conv(x) + bias) through grad.DenseFn, or None when
     the layer is outside what the kernels cover (the caller then runs torch)."""
@@ -40,12 +54,14 @@ def conv_train(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), 
     O, I, kh, kw = weight.shape
     d = dilation[0]
     if (tuple(stride) != (1, 1) or groups != 1 or tuple(dilation) != (d, d) or kh % 2 == 0 or kw % 2 == 0
-            or tuple(padding) != (d * (kh // 2), d * (kw // 2)) or x.dim() != 4 or x.shape[1] != I):
+            or tuple(padding) != (d * (kh // 2), d * (kw // 2)) or x.dim() != 4 or x.shape[1] != I or I <= 4):
         return None
     B, _, H, W = x.shape
-    if not ops.conv_wgrad_ok(B, H, W, I) or B * H * W < 128:
+    if W % 4 or B * H * W < 128:
         return None
-    return grad.DenseFn.apply(x.permute(0, 2, 3, 1), weight, bias, act, slope, d, _train_passes()).permute(0, 3, 1, 2)
+    rows, w4, b, O = _pad_dense(x.permute(0, 2, 3, 1), weight, bias)
+    y = grad.DenseFn.apply(rows, w4, b, act, slope, d, _train_passes())
+    return (y if y.shape[-1] == O else y[..., :O]).permute(0, 3, 1, 2)
 
 
 def linear_train(x, weight2d, bias, act=None, slope=0.1):
@@ -54,12 +70,16 @@ def linear_train(x, weight2d, bias, act=None, slope=0.1):
     if not _train_route(x) or act not in _DENSE_ACTS:
         return None
     N, K = weight2d.shape
+    if x.shape[-1] != K or K <= 4:
+        return None
     rows = x.reshape(1, 1, -1, K)
     R = rows.shape[2]
-    if x.shape[-1] != K or not ops.conv_wgrad_ok(1, 1, R, K) or R < 128:
+    if R % 4 or R < 128:
         return None
-    y = grad.DenseFn.apply(rows, weight2d.view(N, K, 1, 1), bias, act, slope, 1, _train_passes())
-    return y.view(*x.shape[:-1], N)
+    rows, w4, b, N = _pad_dense(rows, weight2d.reshape(N, K, 1, 1), bias)
+    y = grad.DenseFn.apply(rows, w4, b, act, slope, 1, _train_passes())
+    y = y if y.shape[-1] == N else y[..., :N]
+    return y.reshape(*x.shape[:-1], N)
 
 
 def module_train(module, x, act=None, slope=0.1):

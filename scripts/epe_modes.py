@@ -24,9 +24,9 @@ def main():
     G = np.load(os.path.join(ROOT, "tests", "golden", "model_camliraft.npz"))
     inputs = {k: v.cuda() for k, v in co.synthetic_inputs(1, 540, 960, 8192, seed=0).items()}
     model = seed_module_(CamLiRAFT(camliraft_config(n_iters_eval=12)), seed=0).cuda().eval()
-    for allpairs, tf32, cl in [("tcgen05", False, False), ("cublas", False, False), ("tcgen05", False, True),
-                               ("tcgen05", True, True)]:
+    for allpairs, tf32, cl in [("tcgen05", False, True), ("cublas", False, True), ("tcgen05", True, True)]:
         ops.ALLPAIRS_IMPL = allpairs
+        ops.SINGLE_PASS_INFERENCE = tf32          # one tf32 product per element in the dense kernel instead of three
         torch.backends.cudnn.allow_tf32 = tf32
         torch.backends.cuda.matmul.allow_tf32 = False
         m = model.to(memory_format=torch.channels_last if cl else torch.contiguous_format)
@@ -37,7 +37,7 @@ def main():
         d3 = np.sqrt(((out["flow_3d"][0, :, ::4].cpu().numpy() - G["c2_kernel_flow3d"]) ** 2).sum(0)).ravel()
         dist = lambda d: {"mean": float(d.mean()), "median": float(np.median(d)), "p99": float(np.percentile(d, 99)),   # noqa: E731
                           "max": float(d.max()), "share_of_sum_in_top_1pct": float(np.sort(d)[-max(1, d.size // 100):].sum() / d.sum())}
-        print(json.dumps({"allpairs": allpairs, "cudnn_tf32": tf32, "channels_last": cl, "epe2d": dist(d2), "epe3d": dist(d3)}))
+        print(json.dumps({"allpairs": allpairs, "dense_single_pass_tf32": tf32, "channels_last": cl, "epe2d": dist(d2), "epe3d": dist(d3)}))
 
 
 if __name__ == "__main__":

@@ -1,12 +1,29 @@
 #!/bin/bash
-# Final round evidence (cheap): bench line + quick ncu of the kernels changed since the r1_v3 captures.
-mkdir -p gpurun_out; rm -f gpurun_out/*.ncu-rep
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks.csv &
-SMI=$!
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-kill $SMI
-tail -c 400 gpurun_out/bench.json
-timeout 600 ncu --set full --clock-control none -k regex:'knn_warp_kernel|backwarp3d_kernel|dw_gather_max|corr2d_lookup_kernel' -c 12 -f -o /tmp/prof_final python scripts/profile_kernels.py --iters 1 > gpurun_out/ncu_kernels.log 2>&1
-ncu -i /tmp/prof_final.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw.csv 2>/dev/null
-rm -f gpurun_out/launches.csv gpurun_out/prof_kernels_details.csv gpurun_out/prof_source_*.csv
-ls -la gpurun_out | head -20
+# Final evidence run of the round: gpu_profile.sh (bench line + ncu launch list + ncu --set full of the hot kernels), then the
+# bench lines of the other workloads, the training A/B (hand-written vs library dense layers) and the L0 microbench against the
+# reference's own kernels.  Everything lands in gpurun_out/ as text; scripts/summarise_profiles.py turns it into profiles/.
+bash scripts/gpu_profile.sh
+for w in c3 c4; do
+  timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --pairs-per-step 4 --no-cpu-baseline --no-training-block > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; tail -2 gpurun_out/bench_$w.err | cut -c1-200
+done
+timeout 600 python bench.py --workload c5 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
+timeout 600 python bench.py --workload c5 --train-dense library --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5_library.json 2> gpurun_out/bench_c5_library.err
+timeout 600 python bench.py --workload c5 --train-precision fp32 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5_fp32.json 2> gpurun_out/bench_c5_fp32.err
+timeout 600 python bench.py --workload c5 --train-precision fp32 --train-dense library --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5_fp32_library.json 2> gpurun_out/bench_c5_fp32_library.err
+timeout 300 python scripts/microbench_l0.py > gpurun_out/microbench_l0.log 2>&1; tail -3 gpurun_out/microbench_l0.log | cut -c1-200
+timeout 300 python scripts/cg_time.py --header > gpurun_out/cg_time.txt 2>&1; cat gpurun_out/cg_time.txt
+python - <<'PY'
+import json
+for f in ("bench", "bench_c3", "bench_c4", "bench_c5", "bench_c5_library", "bench_c5_fp32", "bench_c5_fp32_library"):
+    try:
+        b = json.loads(open("gpurun_out/%s.json" % f).read().strip().splitlines()[-1])
+        extra = ""
+        if "latency" in b: extra = " e2e %.1f latency %.2f ms" % (b["e2e"]["value"], b["latency"]["ms_per_pair"])
+        if b.get("roofline"): extra += " | %s frac %.3f" % (b["roofline"]["kernel"], b["roofline"]["frac"])
+        if b.get("training"): extra += " | training %.2f pairs/s" % b["training"]["value"]
+        if b.get("cpu_baseline"): extra += " | cpu %.3f" % b["cpu_baseline"]["value"]
+        print("%-24s value %.2f %s%s" % (f, b["value"], b["unit"], extra))
+    except Exception as e:
+        print(f, "ERR", e)
+PY
+ls gpurun_out | wc -l; du -sh gpurun_out

@@ -51,7 +51,8 @@ def test_dw_gather_max_backward(dev):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,kh,kw,dil,act,bias", [
     (1, 68, 120, 256, 192, 3, 3, 1, "relu", True),        # motion encoder conv_c2 at C2 size
-    (2, 20, 36, 64, 126, 3, 3, 1, "relu", True),          # ragged rows (W % 32 != 0), C_out % 4 != 0 (library data gradient)
+    (2, 20, 36, 64, 126, 3, 3, 1, "relu", True),          # ragged rows (W % 32 != 0), C_out % 4 != 0 (padded by the doorway)
+    (1, 24, 32, 147, 128, 3, 3, 1, "leaky_relu", True),   # C_in % 4 != 0 (PWC dense estimator): zero-padded channels
     (1, 17, 40, 128, 128, 1, 5, 1, "sigmoid", True),      # ConvGRU gate
     (1, 17, 40, 128, 128, 5, 1, 1, "tanh", True),
     (2, 24, 32, 32, 64, 3, 3, 2, "leaky_relu", False),    # dilated (PWC context network)
@@ -59,17 +60,19 @@ def test_dw_gather_max_backward(dev):
     (1, 1, 520, 128, 64, 1, 1, 1, "leaky_relu", True),
 ])
 def test_dense_layer_backward_kernels(dev, B, H, W, Cin, Cout, kh, kw, dil, act, bias):
-    """grad.DenseFn (forward conv_gemm; backward transpose_split + conv_gemm on mirrored weights + conv_wgrad) against fp64
-    autograd through F.conv2d: output, data gradient, weight gradient, bias gradient."""
+    """The training doorway tc.conv_train -> grad.DenseFn (forward conv_gemm; backward transpose_split + conv_gemm on mirrored
+    weights + conv_wgrad) against fp64 autograd through F.conv2d: output, data gradient, weight gradient, bias gradient."""
     import torch.nn.functional as F
-    from camliflow_b200 import grad
+    from camliflow_b200 import grad, tc
     g = torch.Generator().manual_seed(77)
     x = torch.randn(B, H, W, Cin, generator=g).to(dev).requires_grad_(True)
     w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).to(dev).requires_grad_(True)
     b = (torch.randn(Cout, generator=g) * 0.1).to(dev).requires_grad_(True) if bias else None
     gy = torch.randn(B, H, W, Cout, generator=g).to(dev)
     grad.clear_dense_cache()
-    y = grad.DenseFn.apply(x, w, b, act, 0.1, dil)
+    y = tc.conv_train(x.permute(0, 3, 1, 2), w, b, (1, 1), (dil * (kh // 2), dil * (kw // 2)), (dil, dil), 1, act, 0.1)
+    assert y is not None
+    y = y.permute(0, 2, 3, 1)
     got = torch.autograd.grad(y, [x, w] + ([b] if bias else []), gy)
     xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
     bd = b.detach().double().requires_grad_(True) if bias else None
