@@ -67,3 +67,51 @@ def test_new_entry_points_validate_arguments_without_launching():
     assert h.camli_corr2d_lookup_backward(None, None, None, 4, None, None, 1, 4, 4, 3, None) == -2      # radius != 4
     assert h.camli_pointconv_dw_gather_max_backward(1, 8, 4, 3, 4, 16, None, None, None, None, None, None, None) == -1   # K < k
     assert h.camli_split_tf32(None, None, None, i64(0), None) == 0
+
+
+def test_training_entry_points_validate_arguments_without_launching():
+    """camli_transpose_split / camli_conv_wgrad / the single-pass flag of camli_conv_gemm: CAMLI_E* for bad arguments, CAMLI_OK
+    for empty work, before any CUDA call (no GPU needed)."""
+    import ctypes
+    h = native.lib()
+    f32, i64 = ctypes.c_float, ctypes.c_int64
+    # camli_transpose_split(rows, ld, P, C, y_rows, ldy, act, slope, W, n_shift, shift_step, hi_t, lo_t, g_rows, colsum, stream)
+    ts = lambda ld, P, C, act, W, n_shift, step=1: h.camli_transpose_split(                 # noqa: E731
+        None, i64(ld), i64(P), C, None, i64(0), act, f32(0.1), W, n_shift, step, None, None, None, None, None)
+    assert ts(32, 0, 32, 0, 8, 1) == 0                 # no rows
+    assert ts(16, 64, 32, 0, 8, 1) == -1               # pitch smaller than C
+    assert ts(32, 64, 32, 0, 8, 2) == -1               # even number of shifted copies
+    assert ts(32, 64, 32, 5, 8, 1) == -2               # GRU epilogue codes have no derivative here
+    assert ts(32, 64, 32, 0, 8, 3) == -1               # null pointers with rows to move (and P % W == 0)
+    assert ts(32, 60, 32, 0, 8, 3) == -1               # shifted copies need whole image rows
+    # camli_conv_wgrad(g_hi, g_lo, x_hi, x_lo, B, H, W, Cout, Cin, kh, kw, dilation, passes, dw, stream)
+    wg = lambda B, H, W, Cout, Cin, kh, kw, dil, passes: h.camli_conv_wgrad(                # noqa: E731
+        None, None, None, None, B, H, W, Cout, Cin, kh, kw, dil, passes, None, None)
+    assert wg(0, 4, 8, 16, 32, 3, 3, 1, 3) == 0        # empty batch
+    assert wg(1, 4, 8, 16, 32, 3, 3, 1, 2) == -1       # passes is 1 or 3
+    assert wg(1, 4, 6, 16, 32, 3, 3, 1, 3) == -2       # W % 4 != 0: rows not 16-byte granular
+    assert wg(1, 4, 8, 16, 30, 3, 3, 1, 3) == -2       # Cin % 4 != 0
+    assert wg(1, 4, 8, 16, 32, 2, 3, 1, 3) == -2       # even window
+    assert wg(1, 4, 8, 16, 32, 3, 3, 1, 1) == -1       # null pointers with work to do
+    # the single-pass flag travels in tile_n: 0x100 | width
+    cg = lambda tile: h.camli_conv_gemm(None, 0, 4, 4, 32, i64(32), None, None, 16, 3, 3, None, None, i64(0), 1, f32(0.1), None,   # noqa: E731
+                                        i64(16), tile, None)
+    assert cg(0x100) == 0 and cg(0x100 | 64) == 0
+    bad = h.camli_conv_gemm(None, 1, 4, 4, 32, i64(32), None, None, 16, 3, 3, None, None, i64(0), 1, f32(0.1), None, i64(16), 0x100 | 48, None)
+    assert bad == -1                                   # 48 is not a tile width
+
+
+def test_training_doorway_pads_ragged_channel_counts():
+    """tc._pad_dense: input / output channel counts are padded to multiples of 4 with zeros (TMA rows are 16-byte granular),
+    differentiably, and the caller slices the result back."""
+    from camliflow_b200 import tc
+    x = torch.randn(1, 2, 8, 147, requires_grad=True)
+    w = torch.randn(126, 147, 3, 3, requires_grad=True)
+    b = torch.randn(126, requires_grad=True)
+    xr, w4, b4, O = tc._pad_dense(x, w, b)
+    assert xr.shape == (1, 2, 8, 148) and w4.shape == (128, 148, 3, 3) and b4.shape == (128,) and O == 126
+    assert float(xr[..., 147:].abs().sum()) == 0 and float(w4[126:].abs().sum()) == 0 and float(w4[:, 147:].abs().sum()) == 0
+    (xr.sum() + w4.sum() + b4.sum()).backward()
+    assert x.grad.shape == x.shape and w.grad.shape == w.shape and b.grad.shape == b.shape
+    xr2, w42, b42, _ = tc._pad_dense(torch.randn(1, 1, 4, 64), torch.randn(32, 64, 1, 1), None)
+    assert xr2.shape[-1] == 64 and w42.shape == (32, 64, 1, 1) and b42 is None
