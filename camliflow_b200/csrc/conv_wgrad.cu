@@ -45,7 +45,8 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 }
 
 struct WgParams {
-    int B, H, W, Cout, Cin, kh, kw, dil;
+    int B, H, W, Cout, Cin, kh, kw, dil;   // H, W: the OUTPUT grid (rows of G); the input grid has Hin rows
+    int Hin, stride;             // X row of output row y and vertical tap offset dy: y * stride + dy (must lie in [0, Hin))
     int wblocks;                 // k-blocks per image row = ceil(W / 32)
     int kblocks;                 // B * H * wblocks
     int splits, kb_per_split;
@@ -107,16 +108,16 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
                 int xb = kb_lo % P.wblocks, ry = kb_lo / P.wblocks;
                 int y = ry % P.H, b = ry / P.H;
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
-                    if ((unsigned)(y + dy) < (unsigned)P.H) {                         // (rows above / below the image: zero padding)
+                    if ((unsigned)(y * P.stride + dy) < (unsigned)P.Hin) {            // (rows above / below the image: zero padding)
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t dst = tiles_base + stage * WG_STAGE_BYTES;
                         mbar_expect_tx(full, P.passes == 1 ? 2 * WG_TILE_BYTES : WG_STAGE_BYTES);
                         tma_load_5d(dst + 0 * WG_TILE_BYTES, &map_g_hi, full, xb * WG_BK, y, b, mt * WG_BM, 0);
-                        tma_load_5d(dst + 2 * WG_TILE_BYTES, &map_x_hi, full, xb * WG_BK, y + dy, b, nt * WG_BN, sx);
+                        tma_load_5d(dst + 2 * WG_TILE_BYTES, &map_x_hi, full, xb * WG_BK, y * P.stride + dy, b, nt * WG_BN, sx);
                         if (P.passes != 1) {
                             tma_load_5d(dst + 1 * WG_TILE_BYTES, &map_g_lo, full, xb * WG_BK, y, b, mt * WG_BM, 0);
-                            tma_load_5d(dst + 3 * WG_TILE_BYTES, &map_x_lo, full, xb * WG_BK, y + dy, b, nt * WG_BN, sx);
+                            tma_load_5d(dst + 3 * WG_TILE_BYTES, &map_x_lo, full, xb * WG_BK, y * P.stride + dy, b, nt * WG_BN, sx);
                         }
                         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -141,7 +142,7 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
                 int xb = kb_lo % P.wblocks, y = (kb_lo / P.wblocks) % P.H;
                 uint32_t started = 0u;
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
-                    if ((unsigned)(y + dy) < (unsigned)P.H) {
+                    if ((unsigned)(y * P.stride + dy) < (unsigned)P.Hin) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
                         const uint32_t src = tiles_base + stage * WG_STAGE_BYTES;
@@ -184,12 +185,12 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
                 const int dy = (tap / P.kw - P.kh / 2) * P.dil;
                 int y = kb_lo < kb_hi ? (kb_lo / P.wblocks) % P.H : 0;
                 for (int kb = kb_lo; kb < kb_hi && empty; kb += P.wblocks) {          // one probe per image row touched
-                    if ((unsigned)(y + dy) < (unsigned)P.H) empty = false;
+                    if ((unsigned)(y * P.stride + dy) < (unsigned)P.Hin) empty = false;
                     if (++y == P.H) y = 0;
                 }
                 if (empty && kb_lo < kb_hi) {                                        // the last (partial) row of the range
                     const int yl = ((kb_hi - 1) / P.wblocks) % P.H;
-                    if ((unsigned)(yl + dy) < (unsigned)P.H) empty = false;
+                    if ((unsigned)(yl * P.stride + dy) < (unsigned)P.Hin) empty = false;
                 }
             }
 #pragma unroll 1
@@ -235,7 +236,8 @@ constexpr int TS_PX = 32, TS_CH = 128;
 __global__ void __launch_bounds__(256)
 transpose_split_kernel(const float* __restrict__ x, long long ld, int P, int C, const float* __restrict__ y, long long ldy,
                        int act, float slope, float* __restrict__ hi_t, float* __restrict__ lo_t, long long ldt,
-                       float* __restrict__ g_rows, float* __restrict__ colsum, int W, int n_shift, int shift_step) {
+                       float* __restrict__ g_rows, float* __restrict__ colsum, int W, int n_shift, int shift_step,
+                       int W_out, int xstride) {                                     // P counts OUTPUT pixels: rows of W_out
     __shared__ float s_t[TS_PX][TS_CH + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p0 = blockIdx.x * TS_PX, c0 = blockIdx.y * TS_CH;
@@ -250,9 +252,10 @@ transpose_split_kernel(const float* __restrict__ x, long long ld, int P, int C, 
             const int p = p0 + pr + 8 * i, c = c0 + cq;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (p < P && c < C) {
-                const int xs = p % W + shift;                                        // stays inside its image row, or reads zero
+                const int row = p / W_out, xo = p - row * W_out;
+                const int xs = xo * xstride + shift;                                 // stays inside its image row, or reads zero
                 const bool inside = (unsigned)xs < (unsigned)W;
-                const float* src = x + (long long)(p + shift) * ld + c;
+                const float* src = x + ((long long)row * W + xs) * ld + c;
                 float o[4] = {1.f, 1.f, 1.f, 1.f};
                 if (vec) {
                     if (inside) { const float4 t = __ldg(reinterpret_cast<const float4*>(src)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
@@ -332,25 +335,31 @@ int wg_encode_map(CUtensorMap* map, const float* base, int B, int H, int W, int 
 }  // namespace
 
 extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, int C, const float* y_rows, int64_t ldy,
-                                     int act, float slope, int W, int n_shift, int shift_step,
+                                     int act, float slope, int W, int n_shift, int shift_step, int xstride,
                                      float* hi_t, float* lo_t, float* g_rows, float* colsum, void* stream) {
-    if (P < 0 || C < 1 || ld < C || (y_rows && ldy < C) || W < 1 || n_shift < 1 || (n_shift & 1) == 0 || shift_step < 1)
+    if (P < 0 || C < 1 || ld < C || (y_rows && ldy < C) || W < 1 || n_shift < 1 || (n_shift & 1) == 0 || shift_step < 1 ||
+        (xstride != 1 && xstride != 2))
         return CAMLI_EINVAL;
-    if (n_shift > 1 && (y_rows || g_rows || colsum || P % W)) return CAMLI_EINVAL;   // shifted copies: plain activations only
+    if ((n_shift > 1 || xstride > 1) && (y_rows || g_rows || colsum || P % W)) return CAMLI_EINVAL;   // plain activations only
+    const int W_out = (W - 1) / xstride + 1;
+    const int64_t P_in = P;
+    P = P / W * W_out + (xstride == 1 ? P % W : 0);                                 // output pixels (x subsampled by xstride)
+    (void)P_in;
     if (act < CAMLI_ACT_NONE || act > CAMLI_ACT_SIGMOID) return CAMLI_EUNSUPPORTED;
     if (P == 0) return CAMLI_OK;
     if (!rows || !hi_t) return CAMLI_EINVAL;                                          // lo_t == NULL: hi parts only
     if (P > 2147483647LL - 64) return CAMLI_EUNSUPPORTED;
     const dim3 grid((unsigned)camli_div_up_ll(P, TS_PX), (unsigned)camli_div_up(C, TS_CH));
     transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, (int)P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
-                                                                   g_rows, colsum, W, n_shift, shift_step);
+                                                                   g_rows, colsum, W, n_shift, shift_step, W_out, xstride);
     CAMLI_RETURN_LAUNCH_STATUS();
 }
 
 extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
-                                int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int passes,
-                                float* dw, void* stream) {
+                                int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int stride, int Hin,
+                                int passes, float* dw, void* stream) {
     if (passes != 1 && passes != 3) return CAMLI_EINVAL;
+    if ((stride != 1 && stride != 2) || Hin < 1 || (Hin - 1) / stride + 1 != H) return CAMLI_EINVAL;
     if (B < 0 || H < 1 || W < 1 || Cout < 1 || Cin < 1 || kh < 1 || kw < 1 || dilation < 1) return CAMLI_EINVAL;
     if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (W & 3) || (Cin & 3) || dilation > 64) return CAMLI_EUNSUPPORTED;
     if (B == 0) return CAMLI_OK;
@@ -362,6 +371,7 @@ extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const 
         return CAMLI_EINVAL;
     WgParams P;
     P.B = B; P.H = H; P.W = W; P.Cout = Cout; P.Cin = Cin; P.kh = kh; P.kw = kw; P.dil = dilation;
+    P.Hin = Hin; P.stride = stride;
     P.wblocks = camli_div_up(W, WG_BK);
     const long long kblocks = (long long)B * H * P.wblocks;
     if (kblocks > 2147483647LL) return CAMLI_EUNSUPPORTED;
@@ -384,8 +394,8 @@ extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const 
     int rc;
     if ((rc = wg_encode_map(&m_ghi, g_hi_t, B, H, W, Cout, 1))) return rc;
     if ((rc = wg_encode_map(&m_glo, g_lo_t, B, H, W, Cout, 1))) return rc;
-    if ((rc = wg_encode_map(&m_xhi, x_hi_t, B, H, W, Cin, kw))) return rc;          // kw horizontally pre-shifted copies
-    if ((rc = wg_encode_map(&m_xlo, x_lo_t, B, H, W, Cin, kw))) return rc;
+    if ((rc = wg_encode_map(&m_xhi, x_hi_t, B, Hin, W, Cin, kw))) return rc;        // kw horizontally pre-shifted (and, for stride 2,
+    if ((rc = wg_encode_map(&m_xlo, x_lo_t, B, Hin, W, Cin, kw))) return rc;        // horizontally subsampled) copies, all Hin rows
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;

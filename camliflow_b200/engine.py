@@ -71,6 +71,30 @@ class FlowEngine:
                     self._forward_static()
                 self.graph = g
         torch.cuda.synchronize(self.device)
+        self._use_graph, self._warmup = use_graph, warmup
+        self._weights_key = self._weights_fingerprint()
+
+    # ------------------------------------------------------------------ weights are part of the captured graph
+    def _weights_fingerprint(self):
+        """(storage address, version counter) of every parameter and buffer: the captured graph reads the split / folded
+        copies made from these values, so any in-place update, load_state_dict or .to() invalidates it."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.model.parameters()) + list(self.model.buffers()))
+
+    def check_weights(self):
+        """Raise if the model's weights changed since the graph was captured (an optimizer step, load_state_dict, ...):
+        replaying would silently keep computing with the old ones.  Called by the public entry points `__call__` and
+        `pipelined`; `step()` itself stays check-free (it is the inner loop of the throughput paths)."""
+        if self.graph is not None and self._weights_fingerprint() != self._weights_key:
+            raise RuntimeError("FlowEngine: the model's weights changed after the CUDA graph was captured; call "
+                               "engine.recapture() (the graph holds split / folded copies of the old values)")
+
+    def recapture(self):
+        """Drop the captured graph and the cached split weights, and capture again from the model's current weights."""
+        from . import ops, tc
+        self.graph = None
+        ops._TC_WEIGHTS.clear()
+        tc._PLAIN.clear()
+        self._prepare(self._use_graph, self._warmup)
 
     # ------------------------------------------------------------------ execution
     def load(self, inputs):
@@ -101,6 +125,7 @@ class FlowEngine:
         return self.host_out
 
     def __call__(self, inputs):
+        self.check_weights()
         self.load(inputs)
         self.step()
         return self.fetch()
@@ -113,6 +138,7 @@ class FlowEngine:
         overlapped, not skipped.  Double-buffered staging on both sides; the compute stream only ever waits on
         events.  The yielded dict is reused two batches later: consume (or clone) it before advancing twice."""
         dev = self.device
+        self.check_weights()
         if not hasattr(self, "_pipe"):
             with torch.cuda.device(dev):
                 self._pipe = {
@@ -209,6 +235,8 @@ class EnginePool:
 
     def pipelined(self, batches):
         n = len(self.engines)
+        for eng in self.engines:
+            eng.check_weights()
         pending = [None] * n
         for i, inputs in enumerate(batches):
             eng = self.engines[i % n]

@@ -247,14 +247,14 @@ class DenseFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x_rows, weight, bias, act, slope, dilation, passes=3):
+    def forward(ctx, x_rows, weight, bias, act, slope, dilation, passes=3, stride=1):
         from . import ops
         kh, kw = weight.shape[2:]
         w_hi, w_lo = _dense_weight(weight, False)
         x_rows = x_rows.contiguous()
         y = ops.conv_gemm(x_rows, w_hi, w_lo, kh, kw, None if bias is None else bias.detach().float().contiguous(), act, slope,
-                          dilation=dilation, single_pass=passes == 1)
-        ctx.act, ctx.slope, ctx.dilation, ctx.passes = act, slope, dilation, passes
+                          dilation=dilation, single_pass=passes == 1, stride=stride)
+        ctx.act, ctx.slope, ctx.dilation, ctx.passes, ctx.stride = act, slope, dilation, passes, stride
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x_rows, weight, y if act is not None else None)
         return y
@@ -265,10 +265,11 @@ class DenseFn(torch.autograd.Function):
         from . import ops
         x_rows, weight, y = ctx.saved_tensors
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        B, H, W, Cin = x_rows.shape
+        B, Hin, Win, Cin = x_rows.shape
         O, _, kh, kw = weight.shape
         gy = gy.float().contiguous()
-        fast = ctx.passes == 1
+        H, W = gy.shape[1:3]                                     # output grid (= input grid for stride 1)
+        fast, st = ctx.passes == 1, ctx.stride
         g_hi, g_lo, g_rows, db = ops.transpose_split(gy, y, ctx.act, ctx.slope, want_rows=need_x, want_colsum=need_b,
                                                      want_lo=not fast)
         if y is None:
@@ -276,9 +277,15 @@ class DenseFn(torch.autograd.Function):
         dx = dw = None
         if need_x:
             wt_hi, wt_lo = _dense_weight(weight, True)          # (callers pad C_out to a multiple of 4: tc._pad_dense)
+            if st == 2:
+                # data gradient of a stride-2 layer = the stride-1 convolution of the zero-upsampled gradient with the mirrored
+                # weights (3/4 of the products multiply zeros; two such layers per encoder pass)
+                up = torch.zeros((B, Hin, Win, O), dtype=torch.float32, device=gy.device)
+                up[:, ::2, ::2] = g_rows
+                g_rows = up
             dx = ops.conv_gemm(g_rows, wt_hi, wt_lo, kh, kw, dilation=ctx.dilation, single_pass=fast)
         if need_w:
-            x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation, want_lo=not fast)
-            dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation, ctx.passes)
+            x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation, want_lo=not fast, xstride=st)
+            dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation, ctx.passes, st, Hin)
             dw = dw2d.view(O, kh, kw, Cin).permute(0, 3, 1, 2).to(weight.dtype)
-        return dx, dw, (db.to(weight.dtype) if need_b else None), None, None, None, None
+        return dx, dw, (db.to(weight.dtype) if need_b else None), None, None, None, None, None

@@ -407,36 +407,40 @@ def split_tf32(w2d):
     return hi, lo
 
 
-def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_colsum=False, n_shift=1, shift_step=1, want_lo=True):
+def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_colsum=False, n_shift=1, shift_step=1, want_lo=True,
+                    xstride=1):
     """rows [B,H,W,C] channel-last view -> (hi_t, lo_t [C, B*H*W], g_rows, colsum): the transposed tf32 parts the
     weight-gradient GEMM reads (camli_transpose_split).  With `y` (the layer output, same shape) rows is dL/dy: it is
     multiplied by act'(y) first; g_rows [B,H,W,C] = that product (operand of the data-gradient convolution), colsum [C] =
     its sum over the pixels (the bias gradient).  n_shift = kw > 1: [kw, C, B*H*W] horizontally pre-shifted copies (the x
-    operand of a kw-wide window, shift_step = dilation)."""
+    operand of a kw-wide window, shift_step = dilation); xstride = 2: the copies keep every second pixel of a row (the x
+    operand of a stride-2 layer), [kw, C, B*H*ceil(W/2)]."""
     B, H, W, C = rows.shape
     ld, ok = _pixel_layout(rows)
     if not ok and rows.stride(-1) != 1:
         raise RuntimeError("transpose_split: channel-last rows expected")
     P = B * H * W
-    hi_t = torch.empty((n_shift, C, P) if n_shift > 1 else (C, P), dtype=torch.float32, device=rows.device)
+    P_out = B * H * ((W - 1) // xstride + 1)
+    hi_t = torch.empty((n_shift, C, P_out) if (n_shift > 1 or xstride > 1) else (C, P_out), dtype=torch.float32, device=rows.device)
     lo_t = torch.empty_like(hi_t) if want_lo else None
     g_rows = torch.empty((B, H, W, C), dtype=torch.float32, device=rows.device) if (want_rows and y is not None) else None
     colsum = torch.zeros((C,), dtype=torch.float32, device=rows.device) if want_colsum else None
     ldy = _pixel_layout(y)[0] if y is not None else 0
     with torch.cuda.device(rows.device):
         native.call("camli_transpose_split", ptr(rows), i64(ld), i64(P), i32(C), ptr(y), i64(ldy), i32(ACT_CODES[act]),
-                    ctypes.c_float(slope), i32(W), i32(n_shift), i32(shift_step), ptr(hi_t), ptr(lo_t), ptr(g_rows), ptr(colsum),
+                    ctypes.c_float(slope), i32(W), i32(n_shift), i32(shift_step), i32(xstride), ptr(hi_t), ptr(lo_t), ptr(g_rows), ptr(colsum),
                     stream(), algo_bytes=P * C * 4 * (1 + 2 * n_shift + (2 if y is not None else 0)))
     return hi_t, lo_t, g_rows, colsum
 
 
-def conv_wgrad(g_t, x_t, B, H, W, Cout, Cin, kh, kw, dilation=1, passes=3):
+def conv_wgrad(g_t, x_t, B, H, W, Cout, Cin, kh, kw, dilation=1, passes=3, stride=1, Hin=None):
     """dW [Cout, kh*kw*Cin] (OHWI) of the stride-1 "same" convolution from the transposed hi / lo operand pairs of
-    transpose_split (camli_conv_wgrad: 3xTF32 on tcgen05, K split over the SMs; passes = 1: one tf32 product, lo parts unused)."""
+    transpose_split (camli_conv_wgrad: 3xTF32 on tcgen05, K split over the SMs; passes = 1: one tf32 product, lo parts unused).
+    H, W: the OUTPUT grid (= the grid of g); stride 2: Hin input rows, x_t prepared with xstride = 2."""
     dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=g_t[0].device)
     with torch.cuda.device(dw.device):
         native.call("camli_conv_wgrad", ptr(g_t[0]), ptr(g_t[1]), ptr(x_t[0]), ptr(x_t[1]), i32(B), i32(H), i32(W), i32(Cout),
-                    i32(Cin), i32(kh), i32(kw), i32(dilation), i32(passes), ptr(dw), stream(),
+                    i32(Cin), i32(kh), i32(kw), i32(dilation), i32(stride), i32(H if Hin is None else Hin), i32(passes), ptr(dw), stream(),
                     algo_bytes=2 * B * H * W * (Cout + Cin) * 4 + Cout * kh * kw * Cin * 4,
                     flops=2 * B * H * W * Cout * kh * kw * Cin, shape=(Cout, kh * kw * Cin, B * H * W))
     return dw

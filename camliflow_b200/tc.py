@@ -53,14 +53,15 @@ def conv_train(x, weight, bias, stride=(1, 1), padding=(0, 0), dilation=(1, 1), 
         return None
     O, I, kh, kw = weight.shape
     d = dilation[0]
-    if (tuple(stride) != (1, 1) or groups != 1 or tuple(dilation) != (d, d) or kh % 2 == 0 or kw % 2 == 0
-            or tuple(padding) != (d * (kh // 2), d * (kw // 2)) or x.dim() != 4 or x.shape[1] != I or I <= 4):
+    st = stride[0]
+    if (tuple(stride) not in ((1, 1), (2, 2)) or groups != 1 or tuple(dilation) != (d, d) or kh % 2 == 0 or kw % 2 == 0
+            or tuple(padding) != (d * (kh // 2), d * (kw // 2)) or x.dim() != 4 or x.shape[1] != I or I <= 4 or (st == 2 and d != 1)):
         return None
     B, _, H, W = x.shape
-    if W % 4 or B * H * W < 128:
+    if ((W - 1) // st + 1) % 4 or W % 4 or B * H * W < 128:
         return None
     rows, w4, b, O = _pad_dense(x.permute(0, 2, 3, 1), weight, bias)
-    y = grad.DenseFn.apply(rows, w4, b, act, slope, d, _train_passes())
+    y = grad.DenseFn.apply(rows, w4, b, act, slope, d, _train_passes(), st)
     return (y if y.shape[-1] == O else y[..., :O]).permute(0, 3, 1, 2)
 
 
@@ -77,7 +78,7 @@ def linear_train(x, weight2d, bias, act=None, slope=0.1):
     if R % 4 or R < 128:
         return None
     rows, w4, b, N = _pad_dense(rows, weight2d.reshape(N, K, 1, 1), bias)
-    y = grad.DenseFn.apply(rows, w4, b, act, slope, 1, _train_passes())
+    y = grad.DenseFn.apply(rows, w4, b, act, slope, 1, _train_passes(), 1)
     y = y if y.shape[-1] == N else y[..., :N]
     return y.reshape(*x.shape[:-1], N)
 

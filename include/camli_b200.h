@@ -264,19 +264,22 @@ int camli_allpairs_correlation(const float* a_rows, const float* b_rows, float* 
  * zeroed by the caller) its column sums = the bias gradient.  n_shift (odd) > 1: hi_t / lo_t are [n_shift, C, P], copy j
  * holding the rows shifted by (j - n_shift/2) * shift_step pixels inside their image row of W pixels (zero outside) -- the
  * x operand of a kw-wide window, because a TMA box cannot start at a 4-byte pixel offset of the contiguous dimension.
+ * xstride = 2 (stride-2 convolution): the copies keep every second pixel of a row, [n_shift, C, P / W * ceil(W/2)].
  *
  * camli_conv_wgrad: dw[n, tap*Cin + c] = sum over pixels of g[p, n] * x[p (+) tap, c] for the stride-1 "same" convolution /
  * linear layer of camli_conv_gemm (OHWI layout, [Cout, kh*kw*Cin]); operands are the [C, B, H, W] hi / lo tensors of
- * camli_transpose_split, x with n_shift = kw, shift_step = dilation.  3xTF32 on tcgen05, K split over the SMs, partial tiles added with 128-bit atomics (dw is zeroed
+ * camli_transpose_split, x with n_shift = kw, shift_step = dilation.  H, W are the OUTPUT grid; a stride-2 layer (stride = 2,
+ * Hin = input rows, x prepared with xstride = 2) reads input row y * 2 + dy for output row y.  3xTF32 on tcgen05, K split over the SMs, partial tiles added with 128-bit atomics (dw is zeroed
  * inside).  W % 4 == 0, Cin % 4 == 0, odd windows.  passes = 3: 3xTF32; passes = 1: the hi parts only (one tf32 product, the
  * reduced-precision mode of the bf16-autocast training step; the lo tensors may then be NULL, also in camli_transpose_split).  The data gradient needs no kernel of its own: it is camli_conv_gemm of
  * g_rows with the spatially flipped, in/out-transposed weights.
  */
 int camli_transpose_split(const float* rows, int64_t ld, int64_t P, int C, const float* y_rows, int64_t ldy,
-                          int act, float slope, int W, int n_shift, int shift_step,
+                          int act, float slope, int W, int n_shift, int shift_step, int xstride,
                           float* hi_t, float* lo_t, float* g_rows, float* colsum, void* stream);
 int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
-                     int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int passes, float* dw, void* stream);
+                     int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int stride, int Hin, int passes,
+                     float* dw, void* stream);
 
 /*
  * SK fusion tail (SKFusion.forward after the align layers, models/clfm.py:199-214):

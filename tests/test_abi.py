@@ -75,18 +75,21 @@ def test_training_entry_points_validate_arguments_without_launching():
     import ctypes
     h = native.lib()
     f32, i64 = ctypes.c_float, ctypes.c_int64
-    # camli_transpose_split(rows, ld, P, C, y_rows, ldy, act, slope, W, n_shift, shift_step, hi_t, lo_t, g_rows, colsum, stream)
-    ts = lambda ld, P, C, act, W, n_shift, step=1: h.camli_transpose_split(                 # noqa: E731
-        None, i64(ld), i64(P), C, None, i64(0), act, f32(0.1), W, n_shift, step, None, None, None, None, None)
+    # camli_transpose_split(rows, ld, P, C, y_rows, ldy, act, slope, W, n_shift, shift_step, xstride, hi_t, lo_t, g_rows, colsum, stream)
+    ts = lambda ld, P, C, act, W, n_shift, step=1, xs=1: h.camli_transpose_split(           # noqa: E731
+        None, i64(ld), i64(P), C, None, i64(0), act, f32(0.1), W, n_shift, step, xs, None, None, None, None, None)
+    assert ts(32, 64, 32, 0, 8, 1, 1, 3) == -1         # xstride is 1 or 2
     assert ts(32, 0, 32, 0, 8, 1) == 0                 # no rows
     assert ts(16, 64, 32, 0, 8, 1) == -1               # pitch smaller than C
     assert ts(32, 64, 32, 0, 8, 2) == -1               # even number of shifted copies
     assert ts(32, 64, 32, 5, 8, 1) == -2               # GRU epilogue codes have no derivative here
     assert ts(32, 64, 32, 0, 8, 3) == -1               # null pointers with rows to move (and P % W == 0)
     assert ts(32, 60, 32, 0, 8, 3) == -1               # shifted copies need whole image rows
-    # camli_conv_wgrad(g_hi, g_lo, x_hi, x_lo, B, H, W, Cout, Cin, kh, kw, dilation, passes, dw, stream)
-    wg = lambda B, H, W, Cout, Cin, kh, kw, dil, passes: h.camli_conv_wgrad(                # noqa: E731
-        None, None, None, None, B, H, W, Cout, Cin, kh, kw, dil, passes, None, None)
+    # camli_conv_wgrad(g_hi, g_lo, x_hi, x_lo, B, H, W, Cout, Cin, kh, kw, dilation, stride, Hin, passes, dw, stream)
+    wg = lambda B, H, W, Cout, Cin, kh, kw, dil, passes, stride=1, Hin=None: h.camli_conv_wgrad(   # noqa: E731
+        None, None, None, None, B, H, W, Cout, Cin, kh, kw, dil, stride, H if Hin is None else Hin, passes, None, None)
+    assert wg(1, 4, 8, 16, 32, 3, 3, 1, 3, stride=2, Hin=4) == -1      # 4 input rows give 2 output rows at stride 2, not 4
+    assert wg(0, 4, 8, 16, 32, 3, 3, 1, 3, stride=2, Hin=8) == 0
     assert wg(0, 4, 8, 16, 32, 3, 3, 1, 3) == 0        # empty batch
     assert wg(1, 4, 8, 16, 32, 3, 3, 1, 2) == -1       # passes is 1 or 3
     assert wg(1, 4, 6, 16, 32, 3, 3, 1, 3) == -2       # W % 4 != 0: rows not 16-byte granular

@@ -33,6 +33,21 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
+def _own_decisions(gy, y_kernel, y_ref_lin, act, slope=0.1):
+    """(reference output to differentiate, upstream gradient) such that a piecewise-linear activation uses the KERNEL's
+    decisions: an fp32 output within rounding of zero may land on the other side of the kink than the fp64 reference's,
+    which flips whole gradient entries (the more outputs, the likelier) and says nothing about the GEMMs under test."""
+    if act == "relu":
+        return y_ref_lin, gy * (y_kernel > 0).double()
+    if act == "leaky_relu":
+        return y_ref_lin, gy * torch.where(y_kernel > 0, 1.0, slope).double()
+    if act == "tanh":
+        return torch.tanh(y_ref_lin), gy
+    if act == "sigmoid":
+        return torch.sigmoid(y_ref_lin), gy
+    return y_ref_lin, gy
+
+
 def test_dw_gather_max_backward(dev):
     g = torch.Generator().manual_seed(41)
     B, N, S, K, k, O = 2, 600, 500, 32, 16, 125
@@ -77,9 +92,11 @@ def test_dense_layer_backward_kernels(dev, B, H, W, Cin, Cout, kh, kw, dil, act,
     xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
     bd = b.detach().double().requires_grad_(True) if bias else None
     yd = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, padding=(dil * (kh // 2), dil * (kw // 2)), dilation=dil)
+    ylin = yd.permute(0, 2, 3, 1)
     yd = {None: lambda v: v, "relu": torch.relu, "leaky_relu": lambda v: F.leaky_relu(v, 0.1), "tanh": torch.tanh,
-          "sigmoid": torch.sigmoid}[act](yd).permute(0, 2, 3, 1)
-    ref = torch.autograd.grad(yd, [xd, wd] + ([bd] if bias else []), gy.double())
+          "sigmoid": torch.sigmoid}[act](ylin)
+    out, up = _own_decisions(gy.double(), y.detach(), ylin, act)
+    ref = torch.autograd.grad(out, [xd, wd] + ([bd] if bias else []), up)
     names = ["dx", "dw", "db"]
     print("dense %s: y %.2e %s" % ((B, H, W, Cin, Cout, kh, kw, dil, act), _rel(y.double(), yd),
                                     " ".join("%s %.2e" % (n, _rel(a.double(), r)) for n, a, r in zip(names, got, ref))))
@@ -119,6 +136,33 @@ def test_dense_layer_single_pass_mode(dev, B, H, W, Cin, Cout, kh, kw, act):
           ((B, H, W, Cin, Cout, kh, kw, act), errs[0], errs[1], errs[2], errs[3], _rel(yb, yd)))
     assert max(errs[:3]) <= 2e-3 and errs[3] <= 2e-5
     assert errs[0] <= _rel(yb, yd)
+
+
+@pytest.mark.parametrize("B,Hin,Win,Cin,Cout,k,bias", [(2, 68, 120, 128, 128, 3, False), (1, 135, 240, 256, 512, 1, False), (1, 34, 56, 64, 96, 3, True)])
+def test_dense_layer_stride2_backward(dev, B, Hin, Win, Cin, Cout, k, bias):
+    """Stride-2 layers of the encoders (raft_core.py:10-38) through the training doorway: strided forward, data gradient as the
+    stride-1 convolution of the zero-upsampled gradient, weight gradient over the x-subsampled transposed copies."""
+    import torch.nn.functional as F
+    from camliflow_b200 import grad, tc
+    g = torch.Generator().manual_seed(79)
+    x = torch.randn(B, Hin, Win, Cin, generator=g).to(dev).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev).requires_grad_(True)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev).requires_grad_(True) if bias else None
+    grad.clear_dense_cache()
+    y = tc.conv_train(x.permute(0, 3, 1, 2), w, b, (2, 2), (k // 2, k // 2), (1, 1), 1, "relu", 0.1)
+    assert y is not None
+    y = y.permute(0, 2, 3, 1)
+    gy = torch.randn(y.shape, generator=g).to(dev)
+    got = torch.autograd.grad(y, [x, w] + ([b] if bias else []), gy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    ylin = F.conv2d(xd.permute(0, 3, 1, 2), wd, bd, stride=2, padding=k // 2).permute(0, 2, 3, 1)
+    yd = torch.relu(ylin)
+    out, up = _own_decisions(gy.double(), y.detach(), ylin, "relu")
+    ref = torch.autograd.grad(out, [xd, wd] + ([bd] if bias else []), up)
+    errs = [_rel(y.double(), yd)] + [_rel(a.double(), r) for a, r in zip(got, ref)]
+    print("stride 2 %s:" % ((B, Hin, Win, Cin, Cout, k),), " ".join("%.2e" % e for e in errs))
+    assert y.shape == yd.shape and max(errs) <= 2e-5
 
 
 def test_dense_layers_route_through_the_kernels_under_autograd(dev):

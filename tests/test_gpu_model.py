@@ -149,6 +149,27 @@ def test_engine_graph_matches_eager():
     assert torch.equal(out2["flow_3d"], out["flow_3d"].clone())
 
 
+def test_engine_detects_changed_weights_and_recaptures():
+    """The captured graph holds split / folded copies of the weights: after an in-place update the public call refuses
+    to replay stale values, and recapture() brings the engine back in line with the eager module."""
+    from camliflow_b200.engine import FlowEngine
+    from oracle import camliraft_oracle as co
+    _strict_fp32()
+    inputs = co.synthetic_inputs(1, 160, 224, 8192, seed=6)
+    model = _model(2)
+    eng = FlowEngine(model, 1, 160, 224, 8192, use_graph=True)
+    before = {k: v.clone() for k, v in eng(inputs).items()}
+    with torch.no_grad():
+        model.core.branch_2d.flow_head.conv1.weight.mul_(1.5)
+    with pytest.raises(RuntimeError, match="weights changed"):
+        eng(inputs)
+    eng.recapture()
+    after = eng(inputs)
+    f2, f3 = _run(model, inputs)
+    assert epe(after["flow_2d"][0].numpy(), f2[0].numpy()) <= 1e-5
+    assert epe(after["flow_2d"][0].numpy(), before["flow_2d"][0].numpy()) > 1e-4       # the new weights really are in use
+
+
 def test_bench_inputs_equal_oracle_inputs():
     import bench
     from oracle import camliraft_oracle as co
