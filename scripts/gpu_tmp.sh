@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | cut -c1-200
+timeout 600 python scripts/trace_glue.py 2>&1 | grep -v Warning > gpurun_out/trace_glue.txt; head -60 gpurun_out/trace_glue.txt
