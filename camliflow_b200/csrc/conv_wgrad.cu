@@ -19,6 +19,7 @@
 //   * the pixel range is split over `splits` CTAs per tile so that every SM has work (a 128x128 tile of a 1x1 layer would
 //     otherwise be ONE CTA walking all pixels); partial tiles are added to the zeroed dW with 128-bit `red.global.add`.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,7 +37,7 @@ constexpr int WG_STAGE_BYTES = 4 * WG_TILE_BYTES;            // G_hi, G_lo, X_hi
 constexpr int WG_THREADS = 192;
 constexpr int WG_TMEM_COLS = 2 * WG_BN;
 constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
-constexpr uint32_t WG_IDESC = tf32_idesc(WG_BM, WG_BN);
+constexpr uint32_t WG_IDESC = tf32_idesc(WG_BM, WG_BN), WG_IDESC_BF16 = bf16_idesc(WG_BM, WG_BN);
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
     asm volatile(
@@ -52,6 +53,8 @@ struct WgParams {
     int splits, kb_per_split;
     int tiles_m, tiles_n;
     int passes;                  // 3: 3xTF32 (fp32-accurate), 1: hi x hi only (tf32 operands)
+    int bf16;                    // operands are bf16 (one product, 64 pixels per 128-byte k-block row instead of 32)
+    int bk_px;                   // pixels per k-block: 32 (fp32 operands) or 64 (bf16)
     float* dw;                   // [Cout, kh*kw*Cin], zeroed by the caller
     long long ldw;
 };
@@ -113,11 +116,11 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t dst = tiles_base + stage * WG_STAGE_BYTES;
                         mbar_expect_tx(full, P.passes == 1 ? 2 * WG_TILE_BYTES : WG_STAGE_BYTES);
-                        tma_load_5d(dst + 0 * WG_TILE_BYTES, &map_g_hi, full, xb * WG_BK, y, b, mt * WG_BM, 0);
-                        tma_load_5d(dst + 2 * WG_TILE_BYTES, &map_x_hi, full, xb * WG_BK, y * P.stride + dy, b, nt * WG_BN, sx);
+                        tma_load_5d(dst + 0 * WG_TILE_BYTES, &map_g_hi, full, xb * P.bk_px, y, b, mt * WG_BM, 0);
+                        tma_load_5d(dst + 2 * WG_TILE_BYTES, &map_x_hi, full, xb * P.bk_px, y * P.stride + dy, b, nt * WG_BN, sx);
                         if (P.passes != 1) {
-                            tma_load_5d(dst + 1 * WG_TILE_BYTES, &map_g_lo, full, xb * WG_BK, y, b, mt * WG_BM, 0);
-                            tma_load_5d(dst + 3 * WG_TILE_BYTES, &map_x_lo, full, xb * WG_BK, y * P.stride + dy, b, nt * WG_BN, sx);
+                            tma_load_5d(dst + 1 * WG_TILE_BYTES, &map_g_lo, full, xb * P.bk_px, y, b, mt * WG_BM, 0);
+                            tma_load_5d(dst + 3 * WG_TILE_BYTES, &map_x_lo, full, xb * P.bk_px, y * P.stride + dy, b, nt * WG_BN, sx);
                         }
                         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -152,7 +155,8 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
 #pragma unroll
                         for (int k = 0; k < WG_BK / 8; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);
-                            mma_tf32(tmem_d, a_hi + adv, b_hi + adv, WG_IDESC, started | (uint32_t)k);
+                            if (P.bf16) mma_f16(tmem_d, a_hi + adv, b_hi + adv, WG_IDESC_BF16, started | (uint32_t)k);
+                            else mma_tf32(tmem_d, a_hi + adv, b_hi + adv, WG_IDESC, started | (uint32_t)k);
                             if (P.passes != 1) {
                                 mma_tf32(tmem_d, a_hi + adv, b_lo + adv, WG_IDESC, 1u);
                                 mma_tf32(tmem_d, a_lo + adv, b_hi + adv, WG_IDESC, 1u);
@@ -231,8 +235,10 @@ conv_wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __g
 // data-gradient convolution); `colsum` [C] accumulates the bias gradient (atomics, zeroed by the caller).
 // Tile: 32 pixels x 128 channels per CTA (256 threads).  Load: a thread reads one float4 (4 channels) of 4 pixels -- a warp
 // covers whole 512-byte rows; store: a warp writes 32 consecutive pixels (128 bytes) of one channel, 16 channels per thread.
-constexpr int TS_PX = 32, TS_CH = 128;
+// (bf16 output: 64 pixels per tile, a lane writes two pixels as one bf16x2 -- 128-byte rows again.)
+constexpr int TS_CH = 128;
 
+template <int TS_PX>
 __global__ void __launch_bounds__(256)
 transpose_split_kernel(const float* __restrict__ x, long long ld, int P, int C, const float* __restrict__ y, long long ldy,
                        int act, float slope, float* __restrict__ hi_t, float* __restrict__ lo_t, long long ldt,
@@ -304,29 +310,45 @@ transpose_split_kernel(const float* __restrict__ x, long long ld, int P, int C, 
         (void)part;
         float* __restrict__ hj = hi_t + (long long)j * C * ldt;
         float* __restrict__ lj = lo_t ? lo_t + (long long)j * C * ldt : nullptr;
-        const int p = p0 + lane;
+        if (TS_PX == 64) {
+            // bf16 operands (hi_t is a bf16 tensor of the same shape; ldt and p0 are even): lane = pixel pair
+            const int p = p0 + 2 * lane;
+            __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(hi_t) + (long long)j * C * ldt;
 #pragma unroll 4
-        for (int i = 0; i < TS_CH / 8; ++i) {
-            const int c = c0 + warp + 8 * i;
-            if (c < C && p < P) {
-                float h, l;
-                split_tf32(s_t[lane][warp + 8 * i], h, l);
-                hj[(long long)c * ldt + p] = h;
-                if (lj) lj[(long long)c * ldt + p] = l;
+            for (int i = 0; i < TS_CH / 8; ++i) {
+                const int c = c0 + warp + 8 * i;
+                if (c < C && p < P) {
+                    const float a = s_t[(2 * lane) % TS_PX][warp + 8 * i], b2 = s_t[(2 * lane + 1) % TS_PX][warp + 8 * i];
+                    if (p + 1 < P) *reinterpret_cast<__nv_bfloat162*>(hb + (long long)c * ldt + p) = __floats2bfloat162_rn(a, b2);
+                    else hb[(long long)c * ldt + p] = __float2bfloat16_rn(a);
+                }
+            }
+        } else {
+            const int p = p0 + lane;
+#pragma unroll 4
+            for (int i = 0; i < TS_CH / 8; ++i) {
+                const int c = c0 + warp + 8 * i;
+                if (c < C && p < P) {
+                    float h, l;
+                    split_tf32(s_t[lane][warp + 8 * i], h, l);
+                    hj[(long long)c * ldt + p] = h;
+                    if (lj) lj[(long long)c * ldt + p] = l;
+                }
             }
         }
         __syncthreads();
     }
 }
 
-int wg_encode_map(CUtensorMap* map, const float* base, int B, int H, int W, int C, int S) {
+int wg_encode_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int S, bool bf16) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     const cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)C, (cuuint64_t)S};
-    const cuuint64_t strides[4] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * B * 4, (cuuint64_t)W * H * B * C * 4};
-    const cuuint32_t box[5] = {WG_BK, 1, 1, WG_BM, 1};
+    const cuuint64_t es = bf16 ? 2 : 4;
+    const cuuint64_t strides[4] = {(cuuint64_t)W * es, (cuuint64_t)W * H * es, (cuuint64_t)W * H * B * es, (cuuint64_t)W * H * B * C * es};
+    const cuuint32_t box[5] = {(cuuint32_t)(bf16 ? 2 * WG_BK : WG_BK), 1, 1, WG_BM, 1};          // one 128-byte row of pixels
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+    const CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
@@ -337,6 +359,8 @@ int wg_encode_map(CUtensorMap* map, const float* base, int B, int H, int W, int 
 extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, int C, const float* y_rows, int64_t ldy,
                                      int act, float slope, int W, int n_shift, int shift_step, int xstride,
                                      float* hi_t, float* lo_t, float* g_rows, float* colsum, void* stream) {
+    const int out_bf16 = (xstride & CAMLI_TRANSPOSE_BF16) ? 1 : 0;                   // flag bit: hi_t is bf16, lo_t unused
+    xstride &= ~CAMLI_TRANSPOSE_BF16;
     if (P < 0 || C < 1 || ld < C || (y_rows && ldy < C) || W < 1 || n_shift < 1 || (n_shift & 1) == 0 || shift_step < 1 ||
         (xstride != 1 && xstride != 2))
         return CAMLI_EINVAL;
@@ -349,19 +373,28 @@ extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, i
     if (P == 0) return CAMLI_OK;
     if (!rows || !hi_t) return CAMLI_EINVAL;                                          // lo_t == NULL: hi parts only
     if (P > 2147483647LL - 64) return CAMLI_EUNSUPPORTED;
-    const dim3 grid((unsigned)camli_div_up_ll(P, TS_PX), (unsigned)camli_div_up(C, TS_CH));
-    transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, (int)P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
-                                                                   g_rows, colsum, W, n_shift, shift_step, W_out, xstride);
+    if (out_bf16) {
+        if (P & 1) return CAMLI_EUNSUPPORTED;                                        // bf16x2 stores: even row pitch
+        const dim3 grid((unsigned)camli_div_up_ll(P, 64), (unsigned)camli_div_up(C, TS_CH));
+        transpose_split_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, (int)P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
+                                                                           g_rows, colsum, W, n_shift, shift_step, W_out, xstride);
+        CAMLI_RETURN_LAUNCH_STATUS();
+    }
+    const dim3 grid((unsigned)camli_div_up_ll(P, 32), (unsigned)camli_div_up(C, TS_CH));
+    transpose_split_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(rows, ld, (int)P, C, y_rows, ldy, act, slope, hi_t, lo_t, P,
+                                                                       g_rows, colsum, W, n_shift, shift_step, W_out, xstride);
     CAMLI_RETURN_LAUNCH_STATUS();
 }
 
 extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
                                 int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int stride, int Hin,
                                 int passes, float* dw, void* stream) {
+    const bool bf16 = passes == CAMLI_WGRAD_BF16;
+    if (bf16) passes = 1;
     if (passes != 1 && passes != 3) return CAMLI_EINVAL;
     if ((stride != 1 && stride != 2) || Hin < 1 || (Hin - 1) / stride + 1 != H) return CAMLI_EINVAL;
     if (B < 0 || H < 1 || W < 1 || Cout < 1 || Cin < 1 || kh < 1 || kw < 1 || dilation < 1) return CAMLI_EINVAL;
-    if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (W & 3) || (Cin & 3) || dilation > 64) return CAMLI_EUNSUPPORTED;
+    if ((kh & 1) == 0 || (kw & 1) == 0 || kh > 15 || kw > 15 || (W & (bf16 ? 7 : 3)) || (Cin & 3) || dilation > 64) return CAMLI_EUNSUPPORTED;
     if (B == 0) return CAMLI_OK;
     if (!g_hi_t || !x_hi_t || !dw) return CAMLI_EINVAL;
     if (passes == 1) { g_lo_t = g_hi_t; x_lo_t = x_hi_t; }                          // (never read)
@@ -372,7 +405,8 @@ extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const 
     WgParams P;
     P.B = B; P.H = H; P.W = W; P.Cout = Cout; P.Cin = Cin; P.kh = kh; P.kw = kw; P.dil = dilation;
     P.Hin = Hin; P.stride = stride;
-    P.wblocks = camli_div_up(W, WG_BK);
+    P.bf16 = bf16 ? 1 : 0; P.bk_px = bf16 ? 2 * WG_BK : WG_BK;
+    P.wblocks = camli_div_up(W, P.bk_px);
     const long long kblocks = (long long)B * H * P.wblocks;
     if (kblocks > 2147483647LL) return CAMLI_EUNSUPPORTED;
     P.kblocks = (int)kblocks;
@@ -392,10 +426,10 @@ extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const 
 
     CUtensorMap m_ghi, m_glo, m_xhi, m_xlo;
     int rc;
-    if ((rc = wg_encode_map(&m_ghi, g_hi_t, B, H, W, Cout, 1))) return rc;
-    if ((rc = wg_encode_map(&m_glo, g_lo_t, B, H, W, Cout, 1))) return rc;
-    if ((rc = wg_encode_map(&m_xhi, x_hi_t, B, Hin, W, Cin, kw))) return rc;        // kw horizontally pre-shifted (and, for stride 2,
-    if ((rc = wg_encode_map(&m_xlo, x_lo_t, B, Hin, W, Cin, kw))) return rc;        // horizontally subsampled) copies, all Hin rows
+    if ((rc = wg_encode_map(&m_ghi, g_hi_t, B, H, W, Cout, 1, bf16))) return rc;
+    if ((rc = wg_encode_map(&m_glo, g_lo_t, B, H, W, Cout, 1, bf16))) return rc;
+    if ((rc = wg_encode_map(&m_xhi, x_hi_t, B, Hin, W, Cin, kw, bf16))) return rc;  // kw horizontally pre-shifted (and, for stride 2,
+    if ((rc = wg_encode_map(&m_xlo, x_lo_t, B, Hin, W, Cin, kw, bf16))) return rc;  // horizontally subsampled) copies, all Hin rows
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;

@@ -206,6 +206,7 @@ def recompute(kernel, formula, *args):
 
 
 # --------------------------------------------------------------------------------------- dense layers
+BF16_WGRAD = True  # under autocast (passes = 1): bf16 operands in the weight-gradient GEMM (A/B switch)
 _DENSE_W = {}      # (data_ptr, version, shape, flipped) -> (weak ref, hi, lo): lives for ONE training step (clear_dense_cache)
 
 
@@ -270,8 +271,11 @@ class DenseFn(torch.autograd.Function):
         gy = gy.float().contiguous()
         H, W = gy.shape[1:3]                                     # output grid (= input grid for stride 1)
         fast, st = ctx.passes == 1, ctx.stride
+        # reduced-precision mode: the weight gradient multiplies bf16 operands (kind::f16, fp32 accumulation) -- half the bytes
+        # through the transposed copies and L2, twice the MMA rate; what the reference's autocast does in this GEMM anyway
+        wg_bf16 = fast and need_w and W % 8 == 0 and BF16_WGRAD
         g_hi, g_lo, g_rows, db = ops.transpose_split(gy, y, ctx.act, ctx.slope, want_rows=need_x, want_colsum=need_b,
-                                                     want_lo=not fast)
+                                                     want_lo=not fast, bf16=wg_bf16)
         if y is None:
             g_rows = gy
         dx = dw = None
@@ -285,7 +289,9 @@ class DenseFn(torch.autograd.Function):
                 g_rows = up
             dx = ops.conv_gemm(g_rows, wt_hi, wt_lo, kh, kw, dilation=ctx.dilation, single_pass=fast)
         if need_w:
-            x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation, want_lo=not fast, xstride=st)
-            dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation, ctx.passes, st, Hin)
+            x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation, want_lo=not fast, xstride=st,
+                                                   bf16=wg_bf16)
+            dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation, 16 if wg_bf16 else ctx.passes,
+                                  st, Hin)
             dw = dw2d.view(O, kh, kw, Cin).permute(0, 3, 1, 2).to(weight.dtype)
         return dx, dw, (db.to(weight.dtype) if need_b else None), None, None, None, None, None

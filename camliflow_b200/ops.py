@@ -408,7 +408,7 @@ def split_tf32(w2d):
 
 
 def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_colsum=False, n_shift=1, shift_step=1, want_lo=True,
-                    xstride=1):
+                    xstride=1, bf16=False):
     """rows [B,H,W,C] channel-last view -> (hi_t, lo_t [C, B*H*W], g_rows, colsum): the transposed tf32 parts the
     weight-gradient GEMM reads (camli_transpose_split).  With `y` (the layer output, same shape) rows is dL/dy: it is
     multiplied by act'(y) first; g_rows [B,H,W,C] = that product (operand of the data-gradient convolution), colsum [C] =
@@ -421,14 +421,16 @@ def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_col
         raise RuntimeError("transpose_split: channel-last rows expected")
     P = B * H * W
     P_out = B * H * ((W - 1) // xstride + 1)
-    hi_t = torch.empty((n_shift, C, P_out) if (n_shift > 1 or xstride > 1) else (C, P_out), dtype=torch.float32, device=rows.device)
-    lo_t = torch.empty_like(hi_t) if want_lo else None
+    hi_t = torch.empty((n_shift, C, P_out) if (n_shift > 1 or xstride > 1) else (C, P_out),
+                       dtype=torch.bfloat16 if bf16 else torch.float32, device=rows.device)      # bf16: operands of the kind::f16 product
+    lo_t = torch.empty_like(hi_t) if (want_lo and not bf16) else None
     g_rows = torch.empty((B, H, W, C), dtype=torch.float32, device=rows.device) if (want_rows and y is not None) else None
     colsum = torch.zeros((C,), dtype=torch.float32, device=rows.device) if want_colsum else None
     ldy = _pixel_layout(y)[0] if y is not None else 0
     with torch.cuda.device(rows.device):
         native.call("camli_transpose_split", ptr(rows), i64(ld), i64(P), i32(C), ptr(y), i64(ldy), i32(ACT_CODES[act]),
-                    ctypes.c_float(slope), i32(W), i32(n_shift), i32(shift_step), i32(xstride), ptr(hi_t), ptr(lo_t), ptr(g_rows), ptr(colsum),
+                    ctypes.c_float(slope), i32(W), i32(n_shift), i32(shift_step), i32(xstride | (0x100 if bf16 else 0)), ptr(hi_t), ptr(lo_t),
+                    ptr(g_rows), ptr(colsum),
                     stream(), algo_bytes=P * C * 4 * (1 + 2 * n_shift + (2 if y is not None else 0)))
     return hi_t, lo_t, g_rows, colsum
 

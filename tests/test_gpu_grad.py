@@ -134,8 +134,17 @@ def test_dense_layer_single_pass_mode(dev, B, H, W, Cin, Cout, kh, kw, act):
     yb = (torch.relu(yb) if act == "relu" else yb).permute(0, 2, 3, 1)
     print("single pass %s: y %.2e dx %.2e dw %.2e db %.2e (bf16-rounded operands: y %.2e)" %
           ((B, H, W, Cin, Cout, kh, kw, act), errs[0], errs[1], errs[2], errs[3], _rel(yb, yd)))
-    assert max(errs[:3]) <= 2e-3 and errs[3] <= 2e-5
+    # forward and data gradient: one tf32 product; weight gradient: bf16 operands (grad.BF16_WGRAD), fp32 accumulation
+    assert max(errs[:2]) <= 2e-3 and errs[2] <= 8e-3 and errs[3] <= 2e-5
     assert errs[0] <= _rel(yb, yd)
+    grad.BF16_WGRAD = False                              # the same with tf32 operands in the weight gradient
+    try:
+        grad.clear_dense_cache()
+        y2 = grad.DenseFn.apply(x, w, b, act, 0.1, 1, 1)
+        dw2 = torch.autograd.grad(y2, [w], gy)[0]
+        assert _rel(dw2.double(), ref[1]) <= 2e-3
+    finally:
+        grad.BF16_WGRAD = True
 
 
 @pytest.mark.parametrize("B,Hin,Win,Cin,Cout,k,bias", [(2, 68, 120, 128, 128, 3, False), (1, 135, 240, 256, 512, 1, False), (1, 34, 56, 64, 96, 3, True)])
