@@ -236,7 +236,8 @@ class EnginePool:
     def pipelined(self, batches):
         n = len(self.engines)
         for eng in self.engines:
-            eng.check_weights()
+            if hasattr(eng, "check_weights"):
+                eng.check_weights()
         pending = [None] * n
         for i, inputs in enumerate(batches):
             eng = self.engines[i % n]
