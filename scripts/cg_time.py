@@ -11,6 +11,9 @@ from camliflow_b200 import ops  # noqa: E402
 SHAPES = [(1, 1, 2048, 128, 128, 1, 1, 0), (1, 1, 2048, 384, 128, 1, 1, 0), (1, 68, 120, 128, 128, 1, 1, 0),
           (1, 68, 120, 256, 192, 3, 3, 0), (1, 68, 120, 256, 256, 1, 5, 0), (1, 68, 120, 256, 128, 1, 5, 64),
           (4, 68, 120, 256, 192, 3, 3, 0), (4, 68, 120, 128, 128, 1, 1, 0), (2, 136, 240, 64, 64, 3, 3, 0)]
+if os.environ.get("CG_TIME_SMALL"):       # small layers at the three tile widths (latency policy study)
+    SHAPES = [(1, 1, 2048, 128, 128, 1, 1, t) for t in (128, 64, 32)] + [(1, 68, 120, 128, 128, 1, 1, t) for t in (128, 64, 32)] + \
+             [(1, 1, 2048, 384, 256, 1, 1, t) for t in (128, 64, 32)] + [(1, 68, 120, 324, 256, 1, 1, t) for t in (128, 64)]
 
 
 def main():
@@ -48,4 +51,5 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--header":
         print(" ".join("%7s" % ("%dx%d.%d>%d" % (s[0], s[5] * s[6], s[3], s[4]))[:7] for s in SHAPES))
+        print(" ".join("%7s" % ("r%d t%d" % (s[1] * s[2], s[7])) for s in SHAPES))
     main()

@@ -2,6 +2,8 @@
 # Final evidence run of the round: gpu_profile.sh (bench line + ncu launch list + ncu --set full of the hot kernels), then the
 # bench lines of the other workloads, the training A/B (hand-written vs library dense layers) and the L0 microbench against the
 # reference's own kernels.  Everything lands in gpurun_out/ as text; scripts/summarise_profiles.py turns it into profiles/.
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | cut -c1-200 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | cut -c1-200
 bash scripts/gpu_profile.sh
 for w in c3 c4; do
   timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --pairs-per-step 4 --no-cpu-baseline --no-training-block > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; tail -2 gpurun_out/bench_$w.err | cut -c1-200
@@ -11,6 +13,7 @@ timeout 600 python bench.py --workload c5 --train-dense library --steps 6 --warm
 timeout 600 python bench.py --workload c5 --train-precision fp32 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5_fp32.json 2> gpurun_out/bench_c5_fp32.err
 timeout 600 python bench.py --workload c5 --train-precision fp32 --train-dense library --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5_fp32_library.json 2> gpurun_out/bench_c5_fp32_library.err
 timeout 300 python scripts/microbench_l0.py > gpurun_out/microbench_l0.log 2>&1; tail -3 gpurun_out/microbench_l0.log | cut -c1-200
+timeout 600 python scripts/trace_train.py 2>&1 | grep -v Warning | tail -48 | cut -c1-150 > gpurun_out/trace_train.txt
 timeout 300 python scripts/cg_time.py --header > gpurun_out/cg_time.txt 2>&1; cat gpurun_out/cg_time.txt
 python - <<'PY'
 import json
