@@ -1,5 +1,7 @@
 """The fused 2-D/3-D recurrent core of CamLiRAFT (reference models/camliraft_core.py:33-145):
 schedules the two branches and the CLFM fusion sites around the hot loop."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -114,14 +116,13 @@ class CamLiRAFT_Core(nn.Module):
                 warped = warp_pyramid(xyz1, xyzs2, flow_3d) if it > 0 else xyzs2
                 return b3.correlation.forward_rows(xyz1, warped)
 
-            def corr_2d_fn():
-                # + the flow half of the motion encoder, which only needs flow_2d: fills the image stream while
-                # the point stream is still in its (longer) correlation lookup
-                return b2.correlation(grid + flow_2d), (b2.motion_encoder.flow_features(flow_2d) if tc.fused(flow_2d) else None)
-
-            (corr_2d, cf_2d), corr_3d = par.run(corr_2d_fn, corr_3d_fn)
+            # the flow half of the motion encoder only needs flow_2d: on a stream of its own it runs beside the
+            # lookups and the correlation fusion instead of in front of them (2 of the ~25 launches of the image chain)
+            cf_fork = par.fork(lambda: b2.motion_encoder.flow_features(flow_2d)) if tc.fused(flow_2d) else None
+            corr_2d, corr_3d = par.run(lambda: b2.correlation(grid + flow_2d), corr_3d_fn)
             if cfgs.fuse_corr:
                 corr_2d, corr_3d = self.clfm_corr.forward_rows(uv1, corr_2d, corr_3d, nn1, par)
+            cf_2d = cf_fork.join() if cf_fork is not None else None
 
             motion_2d, motion_3d = par.run(
                 lambda: b2.motion_encoder(flow_2d, corr_2d, cf_2d),
@@ -168,6 +169,7 @@ class _TwoStreams:
     the point branch is worth more than any single-kernel optimisation.  Tensors that cross streams
     are kept referenced by the caller until after the join, which is what the caching allocator needs."""
     _side = {}
+    _aux = {}
 
     def __init__(self, enabled):
         self.enabled = enabled
@@ -177,6 +179,21 @@ class _TwoStreams:
                 # the point branch is a chain of short kernels: give its CTAs precedence whenever SMs free up
                 _TwoStreams._side[dev] = torch.cuda.Stream(dev, priority=-1)
             self.side = _TwoStreams._side[dev]
+
+    def fork(self, fn, key="aux"):
+        """Starts `fn` on a further side stream (one per key) and returns a handle whose .join() makes the current
+        stream wait for it and hands back fn's result.  For work off the critical chain of a branch: the flow half
+        of the motion encoder, the 2-D alignment layer of a fusion site."""
+        if not self.enabled or os.environ.get("CAMLI_AUX_STREAMS", "1") == "0":     # (A/B switch: inline, in program order)
+            return _Joined(fn())
+        dev = torch.cuda.current_device()
+        if (dev, key) not in _TwoStreams._aux:
+            _TwoStreams._aux[(dev, key)] = torch.cuda.Stream(dev)
+        s = _TwoStreams._aux[(dev, key)]
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            out = fn()
+        return _Joined(out, s)
 
     def run(self, fn_main, fn_side):
         if not self.enabled:
@@ -188,3 +205,17 @@ class _TwoStreams:
         a = fn_main()
         main.wait_stream(self.side)
         return a, b
+
+
+class _Joined:
+    """Result of _TwoStreams.fork: .join() orders the current stream after the forked work (fork / join on streams is
+    graph-capturable; the result stays referenced by the caller past the join, as the caching allocator needs)."""
+
+    def __init__(self, out, stream=None):
+        self.out, self.stream = out, stream
+
+    def join(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.stream = None
+        return self.out

@@ -57,8 +57,10 @@ class SKFusion(nn.Module):
     def _fused_tail_ok(self, a):
         return a.is_cuda and not (torch.is_grad_enabled() and (a.requires_grad or self.fc_mid[0].weight.requires_grad))
 
-    def forward(self, feat_2d, feat_3d):
-        a, b = self.align1(feat_2d), self.align2(feat_3d)
+    def forward(self, feat_2d, feat_3d, aligned_2d=None):
+        """aligned_2d: align1(feat_2d) if the caller already started it (a handle with .join())."""
+        b = self.align2(feat_3d)
+        a = self.align1(feat_2d) if aligned_2d is None else aligned_2d.join()
         B, C = a.shape[:2]
         if a.dim() == 4 and self._fused_tail_ok(a):        # pool + FCs + softmax + blend in 3 launches
             H, W = a.shape[-2:]
@@ -101,8 +103,10 @@ class CLFM(nn.Module):
         feat_2d = feat_2d.float()
 
         def to_2d():
+            # align1 of the selective-kernel fusion does not depend on the interpolation: beside it, not behind it
+            early = par.fork(lambda: self.fuse2d.align1(feat_2d), "clfm") if par is not None and hasattr(par, "fork") else None
             interp = self.interp.forward_rows(uv, feat_2d.shape[-2:], feat3d_rows.detach(), nn_idx)
-            return self.fuse2d(feat_2d, interp)
+            return self.fuse2d(feat_2d, interp, early)
 
         def to_3d():
             sampled = ops.bilinear_sample_rows(feat_2d.detach(), uv)

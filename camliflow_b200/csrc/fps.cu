@@ -15,6 +15,7 @@
 // Tie rule (bit-exact with the reference tree, which takes the right operand
 // on `<=`): winner = max over points of (dist, bitrev10(i & 1023), -i).
 #include <cooperative_groups.h>
+#include <cub/block/block_radix_sort.cuh>
 #include "common.cuh"
 
 namespace {
@@ -130,6 +131,173 @@ fps_streaming_kernel(const float* __restrict__ xyz_all, float* __restrict__ dist
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pruned single-CTA path (2048 < N <= 8192, default).  A round of the kernels above touches every point
+// although a new sample can only lower the running distance of points closer to it than that distance:
+// late in the sampling that is a handful of points around the sample.  Here the cloud is first sorted along a
+// Morton curve inside the kernel (cub block radix sort of 21-bit cell codes), so every warp owns a compact
+// bucket of 32*PPT points with a bounding box and a cached (max distance, tie key) record.  Per round a warp
+// compares the sample with its box: if even the box is no closer than the bucket's largest running distance,
+// none of its distances can change and the cached record stands -- the warp goes straight to the barrier.
+// The test is exact, not approximate: rounding is monotonic, so for a point inside the box every term of
+// camli_sqdist3 is >= the same term of the box distance computed by the same function, hence d >= lb >= pd and
+// fminf(pd, d) == pd bit for bit.  Typically 1..4 of the 32 warps do arithmetic in a round; the others only
+// take part in the one barrier and the 32-record pick.  No cross-SM exchange at all: ~2x the round rate of the
+// 8-CTA cluster on 1/8 of the SMs.
+// Winner and tie rule are carried by the same explicit 64-bit key as in the cluster kernels below
+// (distance bits, then fps_key_lo(original index)), so the order of the points inside the kernel is irrelevant.
+__device__ __forceinline__ unsigned fps_key_lo(int i) {
+    return ((__brev((unsigned)i & 1023u) >> 22) << 22) | (0x3FFFFFu - (unsigned)i);
+}
+
+__device__ __forceinline__ unsigned fps_spread7(unsigned v) {      // 7 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__device__ __forceinline__ float fps_warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(CAMLI_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ float fps_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(CAMLI_FULL_MASK, v, o));
+    return v;
+}
+
+template <int PPT>
+struct FpsPruned {
+    using Sort = cub::BlockRadixSort<unsigned, FPS_THREADS, PPT, unsigned>;
+    static constexpr int kMaxN = FPS_THREADS * PPT;
+    static constexpr size_t kXyzBytes = (size_t)3 * kMaxN * sizeof(float);
+    static constexpr size_t kLoBytes = (size_t)kMaxN * sizeof(unsigned);
+    static constexpr size_t kSmem = kXyzBytes + kLoBytes + sizeof(typename Sort::TempStorage) + 16;
+};
+
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_pruned_kernel(const float* __restrict__ xyz_all, int N, int S, int64_t* __restrict__ out_all) {
+    using K = FpsPruned<PPT>;
+    extern __shared__ __align__(16) uint8_t fpsp_smem[];
+    float* sx = reinterpret_cast<float*>(fpsp_smem);              // the cloud by ORIGINAL index (the sample's coordinates)
+    float* sy = sx + K::kMaxN;
+    float* sz = sy + K::kMaxN;
+    unsigned* s_lo = reinterpret_cast<unsigned*>(fpsp_smem + K::kXyzBytes);     // tie key of register point j of thread t: [j][t]
+    typename K::Sort::TempStorage& sort_tmp =
+        *reinterpret_cast<typename K::Sort::TempStorage*>(fpsp_smem + K::kXyzBytes + K::kLoBytes);
+    __shared__ uint2 s_slots[2][FPS_WARPS];
+    __shared__ float s_box[6][FPS_WARPS];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float* __restrict__ xyz = xyz_all + (size_t)blockIdx.x * N * 3;
+    int64_t* __restrict__ out = out_all + (size_t)blockIdx.x * S;
+
+    // ---- the cloud -> shared memory, its bounding box
+    const float INF = __int_as_float(0x7f800000);
+    float lo_x = INF, lo_y = INF, lo_z = INF, hi_x = -INF, hi_y = -INF, hi_z = -INF;
+    for (int i = t; i < N; i += FPS_THREADS) {
+        const float x = __ldg(xyz + i * 3 + 0), y = __ldg(xyz + i * 3 + 1), z = __ldg(xyz + i * 3 + 2);
+        sx[i] = x; sy[i] = y; sz[i] = z;
+        lo_x = fminf(lo_x, x); hi_x = fmaxf(hi_x, x);
+        lo_y = fminf(lo_y, y); hi_y = fmaxf(hi_y, y);
+        lo_z = fminf(lo_z, z); hi_z = fmaxf(hi_z, z);
+    }
+    lo_x = fps_warp_min(lo_x); lo_y = fps_warp_min(lo_y); lo_z = fps_warp_min(lo_z);
+    hi_x = fps_warp_max(hi_x); hi_y = fps_warp_max(hi_y); hi_z = fps_warp_max(hi_z);
+    if (lane == 0) {
+        s_box[0][warp] = lo_x; s_box[1][warp] = lo_y; s_box[2][warp] = lo_z;
+        s_box[3][warp] = hi_x; s_box[4][warp] = hi_y; s_box[5][warp] = hi_z;
+    }
+    __syncthreads();
+    lo_x = fps_warp_min(s_box[0][lane]); lo_y = fps_warp_min(s_box[1][lane]); lo_z = fps_warp_min(s_box[2][lane]);
+    hi_x = fps_warp_max(s_box[3][lane]); hi_y = fps_warp_max(s_box[4][lane]); hi_z = fps_warp_max(s_box[5][lane]);
+    const float extent = fmaxf(fmaxf(hi_x - lo_x, hi_y - lo_y), hi_z - lo_z);
+    const float cell = (extent > 0.f && extent < INF) ? 127.999f / extent : 0.f;     // cubic cells; only the bucket quality depends on it
+
+    // ---- Morton order: sorted position p = t * PPT + j lives in register j of thread t
+    unsigned key[PPT], val[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int i = t + j * FPS_THREADS;
+        val[j] = (unsigned)i;
+        key[j] = 0x1FFFFFu;                                        // padding sorts last
+        if (i < N) {
+            const unsigned qx = (unsigned)min(127, max(0, (int)((sx[i] - lo_x) * cell)));
+            const unsigned qy = (unsigned)min(127, max(0, (int)((sy[i] - lo_y) * cell)));
+            const unsigned qz = (unsigned)min(127, max(0, (int)((sz[i] - lo_z) * cell)));
+            key[j] = fps_spread7(qx) | (fps_spread7(qy) << 1) | (fps_spread7(qz) << 2);
+        }
+    }
+    typename K::Sort(sort_tmp).Sort(key, val, 0, 21);
+
+    float px[PPT], py[PPT], pz[PPT], pd[PPT];
+    float b_lo_x = INF, b_lo_y = INF, b_lo_z = INF, b_hi_x = -INF, b_hi_y = -INF, b_hi_z = -INF;    // this warp's bucket
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int i = (int)val[j];
+        if (i < N) {
+            px[j] = sx[i]; py[j] = sy[i]; pz[j] = sz[i];
+            pd[j] = 1e10f;                                        // furthest_point_sampling.cpp:12
+            s_lo[j * FPS_THREADS + t] = fps_key_lo(i);
+            b_lo_x = fminf(b_lo_x, px[j]); b_hi_x = fmaxf(b_hi_x, px[j]);
+            b_lo_y = fminf(b_lo_y, py[j]); b_hi_y = fmaxf(b_hi_y, py[j]);
+            b_lo_z = fminf(b_lo_z, pz[j]); b_hi_z = fmaxf(b_hi_z, pz[j]);
+        } else {
+            px[j] = py[j] = pz[j] = 0.f;
+            pd[j] = -2.f;                                         // never beats a real point
+            s_lo[j * FPS_THREADS + t] = 0u;
+        }
+    }
+    b_lo_x = fps_warp_min(b_lo_x); b_lo_y = fps_warp_min(b_lo_y); b_lo_z = fps_warp_min(b_lo_z);
+    b_hi_x = fps_warp_max(b_hi_x); b_hi_y = fps_warp_max(b_hi_y); b_hi_z = fps_warp_max(b_hi_z);
+
+    // cached record of this warp's bucket: (max running distance, tie key); the initial value forces the first update.
+    // A warp that only holds padding never competes.
+    int w_hi = b_lo_x <= b_hi_x ? __float_as_int(1e10f) : __float_as_int(-3.f);
+    unsigned w_lo = 0u;
+    int cur = 0;
+    for (int s = 0; s < S; ++s) {
+        if (t == 0) out[s] = (int64_t)cur;
+        if (s == S - 1) break;
+        const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+        // distance from the sample to the bucket's box, by the same function and therefore <= every point's distance
+        const float ex = fmaxf(fmaxf(b_lo_x - cx, cx - b_hi_x), 0.f);
+        const float ey = fmaxf(fmaxf(b_lo_y - cy, cy - b_hi_y), 0.f);
+        const float ez = fmaxf(fmaxf(b_lo_z - cz, cz - b_hi_z), 0.f);
+        const float lb = camli_sqdist3(ex, ey, ez);
+        if (!(lb >= __int_as_float(w_hi))) {                      // (warp-uniform) some running distance may drop
+            float best_d = -3.f;
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                const float d = camli_sqdist3(px[j] - cx, py[j] - cy, pz[j] - cz);
+                const float nd = fminf(pd[j], d);
+                pd[j] = nd;
+                best_d = fmaxf(best_d, nd);
+            }
+            const int hi = __float_as_int(best_d);
+            w_hi = __reduce_max_sync(CAMLI_FULL_MASK, hi);
+            unsigned best_lo = 0u;
+            if (hi == w_hi) {
+#pragma unroll
+                for (int j = 0; j < PPT; ++j)
+                    if (pd[j] == best_d) best_lo = max(best_lo, s_lo[j * FPS_THREADS + t]);
+            }
+            w_lo = __reduce_max_sync(CAMLI_FULL_MASK, best_lo);
+        }
+        const int par = s & 1;
+        if (lane == 0) s_slots[par][warp] = make_uint2((unsigned)w_hi, w_lo);
+        __syncthreads();
+        const uint2 r = s_slots[par][lane];
+        const int gh = __reduce_max_sync(CAMLI_FULL_MASK, (int)r.x);
+        const unsigned gl = __reduce_max_sync(CAMLI_FULL_MASK, (int)r.x == gh ? r.y : 0u);
+        cur = (int)(0x3FFFFFu - (gl & 0x3FFFFFu));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cluster path (2048 < N <= 16384): the rounds of ONE cloud are spread over a thread-block cluster
 // of 8 CTAs (8 SMs).  A single 1024-thread CTA is issue-bound at ~1 kcycle per round (N*10
 // instructions through 4 schedulers); splitting the points 8 ways leaves ~100 cycles of math per
@@ -149,10 +317,6 @@ constexpr int FPSC_WARPS = FPSC_THREADS / 32;
 constexpr int FPSC_MAX_N = FPSC_CTAS * FPSC_THREADS * 8;   // 16384
 
 struct __align__(16) FpsRecord { int hi; unsigned lo; float x, y, z; int pad0, pad1, pad2; };
-
-__device__ __forceinline__ unsigned fps_key_lo(int i) {
-    return ((__brev((unsigned)i & 1023u) >> 22) << 22) | (0x3FFFFFu - (unsigned)i);
-}
 
 template <int PPT>
 __global__ void __cluster_dims__(FPSC_CTAS, 1, 1) __launch_bounds__(FPSC_THREADS, 1)
@@ -391,6 +555,15 @@ int fps_launch_cluster_async(const float* xyz, int B, int N, int S, int64_t* out
 }
 
 template <int PPT>
+int fps_launch_pruned(const float* xyz, int B, int N, int S, int64_t* out, cudaStream_t st) {
+    const size_t smem = FpsPruned<PPT>::kSmem;
+    cudaError_t e = cudaFuncSetAttribute(fps_pruned_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fps_pruned_kernel<PPT><<<B, FPS_THREADS, smem, st>>>(xyz, N, S, out);
+    CAMLI_RETURN_LAUNCH_STATUS();
+}
+
+template <int PPT>
 int fps_launch_cluster(const float* xyz, int B, int N, int S, int64_t* out, cudaStream_t st) {
     fps_cluster_kernel<PPT><<<B * FPSC_CTAS, FPSC_THREADS, 0, st>>>(xyz, N, S, out);
     CAMLI_RETURN_LAUNCH_STATUS();
@@ -409,11 +582,12 @@ int fps_launch_register(const float* xyz, int B, int N, int S, int64_t* out, cud
 }  // namespace
 
 // Tuning switch (tests exercise every path) for 2048 < N <= 16384: 0 = single-CTA register kernel,
-// 1 = cluster kernel with a cluster barrier per round, 2 = cluster kernel with the st.async exchange (default).
-static int camli_fps_use_cluster = 2;
+// 1 = cluster kernel with a cluster barrier per round, 2 = cluster kernel with the st.async exchange (the default
+// above 8192 points), 3 = Morton-bucketed single CTA with exact pruning (default; N <= 8192, else falls to 2).
+static int camli_fps_use_cluster = 3;
 extern "C" int camli_fps_set_cluster_path(int mode) {
     const int old = camli_fps_use_cluster;
-    camli_fps_use_cluster = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+    camli_fps_use_cluster = mode < 0 ? 0 : (mode > 3 ? 3 : mode);
     return old;
 }
 
@@ -429,7 +603,11 @@ extern "C" int camli_furthest_point_sampling(const float* xyz, float* dists_tmp,
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 1 * FPS_THREADS) return fps_launch_register<1>(xyz, B, N, S, out, st);
     if (N <= 2 * FPS_THREADS) return fps_launch_register<2>(xyz, B, N, S, out, st);
-    if (camli_fps_use_cluster == 2) {
+    if (camli_fps_use_cluster == 3) {
+        if (N <= 4 * FPS_THREADS) return fps_launch_pruned<4>(xyz, B, N, S, out, st);
+        if (N <= 8 * FPS_THREADS) return fps_launch_pruned<8>(xyz, B, N, S, out, st);
+    }
+    if (camli_fps_use_cluster >= 2) {
         const int per = FPSA_CTAS * FPSA_THREADS;
         if (N <= 2 * per) return fps_launch_cluster_async<2>(xyz, B, N, S, out, st);
         if (N <= 4 * per) return fps_launch_cluster_async<4>(xyz, B, N, S, out, st);

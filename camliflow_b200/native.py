@@ -41,6 +41,8 @@ def lib():
                                % (handle.camli_abi_version(), ABI_VERSION))
         if os.environ.get("CAMLI_PDL") is not None:         # A/B switch for the benchmarks (default: on)
             handle.camli_conv_gemm_set_pdl(int(os.environ["CAMLI_PDL"]))
+        if os.environ.get("CAMLI_FPS_PATH") is not None:    # 3 pruned single CTA (default) / 2 cluster + st.async / 1 / 0
+            handle.camli_fps_set_cluster_path(int(os.environ["CAMLI_FPS_PATH"]))
         if os.environ.get("CAMLI_LOOKUP_KEEP_L2") is not None:
             handle.camli_corr2d_lookup_set_l2_keep(int(os.environ["CAMLI_LOOKUP_KEEP_L2"]))
         _lib = handle

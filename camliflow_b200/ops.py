@@ -276,6 +276,30 @@ TILE_POLICY = os.environ.get("CAMLI_TILE_POLICY", "throughput")
 SINGLE_PASS_INFERENCE = os.environ.get("CAMLI_CONV_PRECISION", "fp32") == "tf32"
 
 
+# CTAs a layer may spread over under the "latency" policy: one wave of the 148 SMs
+LATENCY_WAVE = int(os.environ.get("CAMLI_LATENCY_WAVE", "148"))
+
+
+def _latency_tile(B, Ho, Wo, Cout):
+    """Tile width of a layer when ONE graph runs at a time (TILE_POLICY "latency"): the narrowest of 32 / 64 / 128
+    output columns that still keeps the layer within one wave of CTAs.  The library's default (the widest tile Cout
+    fills) minimises SM-time, which is what counts with several graphs in flight; alone on the GPU a 2048-point linear
+    layer would sit on 16 SMs and an 8160-pixel C_out = 128 convolution on 68, with a 64 KB tile store at the end of
+    each CTA (scripts/cg_time.py, CG_TIME_SMALL: 2048 x 128->128: 9.1 / 7.0 / 6.6 us at 128 / 64 / 32 columns; 8160
+    pixels: 9.2 / 7.3 / 9.3 -- the 32-wide tiling would need two waves there)."""
+    m_tiles = None
+    th = 1
+    while th <= 16:                                     # the library's pixel tile: th x (128 / th) with the least padding
+        tiles = B * (-(-Ho // th)) * (-(-Wo // (128 // th)))
+        m_tiles = tiles if m_tiles is None else min(m_tiles, tiles)
+        th *= 2
+    widest = 128 if Cout > 64 else (64 if Cout > 32 else 32)
+    for bn in (32, 64, 128):
+        if bn <= widest and m_tiles * (-(-Cout // bn)) <= LATENCY_WAVE:
+            return bn if bn != widest else 0
+    return 0
+
+
 def conv_gemm_ok(x_bhwc, kh=1, kw=1):
     """Whether conv_gemm can take this input directly (else callers keep the cuDNN / cuBLAS route)."""
     if not (x_bhwc.is_cuda and x_bhwc.dtype == torch.float32 and x_bhwc.dim() == 4):
@@ -304,9 +328,8 @@ def conv_gemm(x_bhwc, w_hi, w_lo, kh, kw, bias=None, act=None, slope=0.1, residu
         raise RuntimeError("conv_gemm: input must be a 16-byte aligned channel-last view with Cin % 4 == 0")
     n_out = split if out2 is not None else Cout
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
-    if tile_n == 0 and TILE_POLICY == "latency" and 64 < Cout <= 128 and B * Ho * Wo <= 74 * 128 and kh * kw * Cin >= 512:
-        # one graph at a time: a 128-wide tile would leave half of the SMs idle -- two 64-wide tiles per pixel tile
-        tile_n = 64
+    if tile_n == 0 and TILE_POLICY == "latency":
+        tile_n = _latency_tile(B, Ho, Wo, Cout)
     if out is None:
         out = torch.empty((B, Ho, Wo, n_out), dtype=torch.float32, device=x_bhwc.device)
     assert tuple(out.shape) == (B, Ho, Wo, n_out)

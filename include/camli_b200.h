@@ -50,9 +50,10 @@ const char* camli_strerror(int code);
 int camli_furthest_point_sampling(const float* xyz, float* dists_tmp,
                                   int B, int N, int S, int64_t* out, void* stream);
 
-/* Selects the FPS kernel for 2048 < N <= 16384: 2 = 8-CTA thread-block cluster exchanging the per-round
- * records with st.async + mbarrier (default), 1 = 8-CTA cluster with a cluster barrier per round,
- * 0 = single-CTA register kernel.  Returns the previous setting.  Results are identical. */
+/* Selects the FPS kernel for 2048 < N <= 16384: 3 = one CTA per cloud over Morton-ordered buckets with an exact
+ * bounding-box pruning test per warp and round (default; N <= 8192, larger clouds take 2), 2 = 8-CTA thread-block
+ * cluster exchanging the per-round records with st.async + mbarrier, 1 = 8-CTA cluster with a cluster barrier per
+ * round, 0 = single-CTA register kernel.  Returns the previous setting.  Results are identical. */
 int camli_fps_set_cluster_path(int mode);
 
 /* Diagnostics: a device buffer of >= 20 int64 that thread 0 of CTA 0 of the async-cluster FPS kernel stamps with

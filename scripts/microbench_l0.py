@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tests import _util  # noqa: E402
-from camliflow_b200 import csrc  # noqa: E402
+from camliflow_b200 import csrc, native  # noqa: E402
 from camliflow_b200.csrc import wrapper  # noqa: E402
 
 
@@ -40,6 +40,14 @@ def main():
     for B in (2, 8):
         pc = _util.synthetic_pc(B, 8192, seed=0).to(dev)
         row("fps_%dx8192_s4096" % B, lambda: csrc.furthest_point_sampling(pc, 4096), lambda: _util.ref_fps(pc, 4096))
+        for mode, tag in ((2, "cluster_async"), (0, "single_cta_unpruned")):      # the other kernels behind the same entry point
+            old = native.lib().camli_fps_set_cluster_path(mode)
+            try:
+                row("fps_%dx8192_s4096_%s" % (B, tag), lambda: csrc.furthest_point_sampling(pc, 4096))
+            finally:
+                native.lib().camli_fps_set_cluster_path(old)
+    pc = _util.synthetic_pc(2, 4096, seed=0).to(dev)
+    row("fps_2x4096_s2048", lambda: csrc.furthest_point_sampling(pc, 2048), lambda: _util.ref_fps(pc, 2048))
     for (n, m, k, D) in [(2048, 2048, 32, 3), (2048, 2048, 16, 3), (4096, 8192, 16, 3), (2048, 4096, 16, 3),
                          (8192, 2048, 3, 3), (1024, 2048, 3, 3), (2048, 256, 16, 3), (8160, 2048, 1, 2),
                          (34560, 4096, 1, 2)]:

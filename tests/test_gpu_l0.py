@@ -48,11 +48,11 @@ FPS_CASES = [
 ]
 
 
-@pytest.mark.parametrize("cluster", [2, 1, 0], ids=["cluster_async", "cluster_barrier", "single_cta"])
+@pytest.mark.parametrize("cluster", [3, 2, 1, 0], ids=["pruned_single_cta", "cluster_async", "cluster_barrier", "single_cta"])
 @pytest.mark.parametrize("name,make,S", FPS_CASES, ids=[c[0] for c in FPS_CASES])
 def test_fps_bit_exact(dev, name, make, S, cluster):
-    """Every kernel behind camli_furthest_point_sampling (8-CTA cluster with st.async exchange / with a
-    cluster barrier per round / single CTA)."""
+    """Every kernel behind camli_furthest_point_sampling (Morton-bucketed single CTA with exact pruning / 8-CTA
+    cluster with st.async exchange / with a cluster barrier per round / plain single CTA)."""
     from camliflow_b200 import native
     xyz = make().contiguous()
     old = native.lib().camli_fps_set_cluster_path(cluster)
