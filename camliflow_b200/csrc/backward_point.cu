@@ -454,3 +454,195 @@ extern "C" int camli_clfm_interp_backward(int B, int H, int W, int N, int C, con
         H, W, N, C, uv, nn_idx, feat3d_rows, ld_feat, W1, b1, W2, b2, grad_out_rows, grad_W1, grad_b1, grad_W2, grad_b2);
     CAMLI_RETURN_LAUNCH_STATUS();
 }
+
+// =============================================================================================
+// PointConv grouping stage, backward (forward: pointconv.cu; reference models/point_conv.py:56-66 under autograd).
+//   out[s, o*C + c] = sum_j w_j[o] * rows[idx_j, c],   w_j = WeightNet(rows[idx_j, 0:3] - centre[s])   (3 -> 8 -> 16, leaky)
+// Same mapping as the forward: one warp owns a centroid, lane j re-evaluates the WeightNet of neighbour j, the
+// lanes sweep the channels of the neighbours' rows.  With G[o][c] = grad_out[s, o*C + c] in registers:
+//   d rows[idx_j, c] += sum_o w_j[o] G[o][c]                       (atomics: a point is a neighbour of many centroids)
+//   d w_j[o]          = sum_c G[o][c] rows[idx_j, c]               (warp sums; lane j keeps its 16)
+// then lane j walks back through its WeightNet: the offset gradient goes to the neighbour's xyz columns (+) and the
+// centroid (-), and the outer products that make up the WeightNet's parameter gradients are staged in shared memory,
+// summed over the CTA's 8 centroids x k neighbours by one thread per parameter, kept in a register across the CTA's
+// grid-stride loop and added to global memory once per CTA.
+namespace {
+
+constexpr int PCB_WARPS = 8;
+constexpr int PCB_NW = 16, PCB_H = 8;
+constexpr int PCB_REC = PCB_NW + PCB_H + PCB_H + 3;                       // d pre2 | h | d pre1 | offset  = 35 floats
+constexpr int PCB_PARAMS = PCB_H * 3 + PCB_H + PCB_NW * PCB_H + PCB_NW;   // W1 | b1 | W2 | b2 = 176
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(PCB_WARPS * 32)
+pointconv_group_backward_kernel(int N, int S, int K, int k, int C,
+                                const float* __restrict__ rows, long long ldr,
+                                const float* __restrict__ centre, long long c_sb, long long c_sp, long long c_sd,
+                                const int64_t* __restrict__ idx,
+                                const float* __restrict__ W1, const float* __restrict__ b1,
+                                const float* __restrict__ W2, const float* __restrict__ b2, float slope,
+                                const float* __restrict__ g_out,                                   // [B,S,16*C]
+                                float* __restrict__ g_rows,                                        // [B,N,C] zero-initialised
+                                float* __restrict__ g_centre,                                      // [B,3,S] contiguous, every element written
+                                float* __restrict__ g_params) {                                    // [176] zero-initialised
+    __shared__ float s_rec[PCB_WARPS][32][PCB_REC + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const float* rb = rows + (size_t)b * N * ldr;
+    float* grb = g_rows + (size_t)b * N * C;
+    float param_acc = 0.f;                                                  // thread t < 176 owns parameter t
+    const int groups = (S + PCB_WARPS - 1) / PCB_WARPS;
+    for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+        const int s = grp * PCB_WARPS + warp;
+        const bool live = s < S;
+        float rec[PCB_REC];
+#pragma unroll
+        for (int i = 0; i < PCB_REC; ++i) rec[i] = 0.f;
+        if (live) {
+            const float* cp = centre + b * c_sb + s * c_sp;
+            const float cx = __ldg(cp), cy = __ldg(cp + c_sd), cz = __ldg(cp + 2 * c_sd);
+            int my = 0;
+            float h[PCB_H], w[PCB_NW], off0 = 0.f, off1 = 0.f, off2 = 0.f;
+#pragma unroll
+            for (int a = 0; a < PCB_H; ++a) h[a] = 0.f;
+#pragma unroll
+            for (int o = 0; o < PCB_NW; ++o) w[o] = 0.f;
+            if (lane < k) {
+                my = (int)__ldg(idx + ((size_t)b * S + s) * K + lane);
+                const float* p = rb + (size_t)my * ldr;
+                off0 = __ldg(p) - cx; off1 = __ldg(p + 1) - cy; off2 = __ldg(p + 2) - cz;
+#pragma unroll
+                for (int a = 0; a < PCB_H; ++a)
+                    h[a] = camli_leaky(fmaf(__ldg(W1 + a * 3 + 2), off2, fmaf(__ldg(W1 + a * 3 + 1), off1,
+                                       fmaf(__ldg(W1 + a * 3), off0, __ldg(b1 + a)))), slope);
+#pragma unroll
+                for (int o = 0; o < PCB_NW; ++o) {
+                    float acc = __ldg(b2 + o);
+#pragma unroll
+                    for (int a = 0; a < PCB_H; ++a) acc = fmaf(__ldg(W2 + o * PCB_H + a), h[a], acc);
+                    w[o] = camli_leaky(acc, slope);
+                }
+            }
+            // this centroid's output gradient: G[t][o] = g_out[s, o*C + t*32 + lane]
+            float G[CHUNKS][PCB_NW];
+            const float* gs = g_out + ((size_t)b * S + s) * PCB_NW * C;
+#pragma unroll
+            for (int o = 0; o < PCB_NW; ++o)
+#pragma unroll
+                for (int t = 0; t < CHUNKS; ++t) {
+                    const int c = t * 32 + lane;
+                    G[t][o] = (c < C) ? __ldg(gs + (size_t)o * C + c) : 0.f;
+                }
+            float dw[PCB_NW];
+#pragma unroll
+            for (int o = 0; o < PCB_NW; ++o) dw[o] = 0.f;
+            for (int j = 0; j < k; ++j) {
+                const int ij = __shfl_sync(CAMLI_FULL_MASK, my, j);
+                const float* g = rb + (size_t)ij * ldr;
+                float gv[CHUNKS], dr[CHUNKS];
+#pragma unroll
+                for (int t = 0; t < CHUNKS; ++t) {
+                    const int c = t * 32 + lane;
+                    gv[t] = (c < C) ? __ldg(g + c) : 0.f;
+                    dr[t] = 0.f;
+                }
+#pragma unroll
+                for (int o = 0; o < PCB_NW; ++o) {
+                    const float wj = __shfl_sync(CAMLI_FULL_MASK, w[o], j);
+                    float part = 0.f;
+#pragma unroll
+                    for (int t = 0; t < CHUNKS; ++t) {
+                        dr[t] = fmaf(wj, G[t][o], dr[t]);
+                        part = fmaf(G[t][o], gv[t], part);
+                    }
+                    part = camli_warp_sum(part);
+                    if (lane == j) dw[o] = part;
+                }
+#pragma unroll
+                for (int t = 0; t < CHUNKS; ++t) {
+                    const int c = t * 32 + lane;
+                    if (c < C) atomicAdd(grb + (size_t)ij * C + c, dr[t]);
+                }
+            }
+            // lane j: back through its WeightNet (leaky': the sign of the activation is the sign of the pre-activation)
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            if (lane < k) {
+                float dh[PCB_H];
+#pragma unroll
+                for (int a = 0; a < PCB_H; ++a) dh[a] = 0.f;
+#pragma unroll
+                for (int o = 0; o < PCB_NW; ++o) {
+                    const float dp2 = dw[o] * (w[o] > 0.f ? 1.f : slope);
+                    rec[o] = dp2;
+#pragma unroll
+                    for (int a = 0; a < PCB_H; ++a) dh[a] = fmaf(__ldg(W2 + o * PCB_H + a), dp2, dh[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < PCB_H; ++a) {
+                    const float dp1 = dh[a] * (h[a] > 0.f ? 1.f : slope);
+                    rec[PCB_NW + a] = h[a];
+                    rec[PCB_NW + PCB_H + a] = dp1;
+                    d0 = fmaf(__ldg(W1 + a * 3), dp1, d0);
+                    d1 = fmaf(__ldg(W1 + a * 3 + 1), dp1, d1);
+                    d2 = fmaf(__ldg(W1 + a * 3 + 2), dp1, d2);
+                }
+                rec[PCB_NW + 2 * PCB_H] = off0; rec[PCB_NW + 2 * PCB_H + 1] = off1; rec[PCB_NW + 2 * PCB_H + 2] = off2;
+                float* gp = grb + (size_t)my * C;
+                atomicAdd(gp, d0); atomicAdd(gp + 1, d1); atomicAdd(gp + 2, d2);
+            }
+            const float c0 = camli_warp_sum(d0), c1 = camli_warp_sum(d1), c2 = camli_warp_sum(d2);
+            if (lane == 0) {
+                float* gc = g_centre + (size_t)b * 3 * S + s;
+                gc[0] = -c0; gc[S] = -c1; gc[2 * (size_t)S] = -c2;
+            }
+        }
+        // ---- parameter gradients of this group of centroids: one thread per parameter sums the staged records
+#pragma unroll
+        for (int i = 0; i < PCB_REC; ++i) s_rec[warp][lane][i] = rec[i];     // (lanes >= k and dead warps stage zeros)
+        __syncthreads();
+        const int t = threadIdx.x;
+        if (t < PCB_PARAMS) {
+            int ia, ib;                                                         // product of record fields ia * ib (ib < 0: ia alone)
+            if (t < PCB_H * 3) { ia = PCB_NW + PCB_H + t / 3; ib = PCB_NW + 2 * PCB_H + t % 3; }                 // dW1[a][d] = d pre1[a] * off[d]
+            else if (t < PCB_H * 4) { ia = PCB_NW + PCB_H + (t - PCB_H * 3); ib = -1; }                         // db1[a]
+            else if (t < PCB_H * 4 + PCB_NW * PCB_H) { const int u = t - PCB_H * 4; ia = u / PCB_H; ib = PCB_NW + u % PCB_H; }   // dW2[o][a] = d pre2[o] * h[a]
+            else { ia = t - (PCB_H * 4 + PCB_NW * PCB_H); ib = -1; }                                             // db2[o]
+            float acc = 0.f;
+            for (int wq = 0; wq < PCB_WARPS; ++wq)
+                for (int l = 0; l < k; ++l)
+                    acc += ib >= 0 ? s_rec[wq][l][ia] * s_rec[wq][l][ib] : s_rec[wq][l][ia];
+            param_acc += acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < PCB_PARAMS) atomicAdd(g_params + threadIdx.x, param_acc);
+}
+
+}  // namespace
+
+extern "C" int camli_pointconv_group_backward(int B, int N, int S, int K, int k, int C,
+                                              const float* rows, int64_t ld_rows,
+                                              const float* centre_xyz, int64_t c_sb, int64_t c_sp, int64_t c_sd,
+                                              const int64_t* knn_idx, const float* W1, const float* b1, const float* W2,
+                                              const float* b2, float negative_slope, const float* grad_out,
+                                              float* grad_rows, float* grad_centre, float* grad_params, void* stream) {
+    if (B < 0 || N < 1 || S < 0 || k < 1 || K < k || C < 3 || ld_rows < C) return CAMLI_EINVAL;
+    if (k > 32 || B > 65535 || C > 32 * 8) return CAMLI_EUNSUPPORTED;
+    if (B == 0 || S == 0) return CAMLI_OK;
+    if (!rows || !centre_xyz || !knn_idx || !W1 || !b1 || !W2 || !b2 || !grad_out || !grad_rows || !grad_centre || !grad_params)
+        return CAMLI_EINVAL;
+    const int groups = camli_div_up(S, PCB_WARPS);
+    dim3 grid(groups < 148 * 2 ? groups : 148 * 2, B), block(PCB_WARPS * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CAMLI_PCB_LAUNCH(CH)                                                                                                 \
+    pointconv_group_backward_kernel<CH><<<grid, block, 0, st>>>(N, S, K, k, C, rows, ld_rows, centre_xyz, c_sb, c_sp, c_sd, \
+                                                                knn_idx, W1, b1, W2, b2, negative_slope, grad_out, grad_rows, \
+                                                                grad_centre, grad_params)
+    const int chunks = camli_div_up(C, 32);
+    if (chunks <= 2) CAMLI_PCB_LAUNCH(2);
+    else if (chunks <= 4) CAMLI_PCB_LAUNCH(4);
+    else if (chunks <= 6) CAMLI_PCB_LAUNCH(6);
+    else CAMLI_PCB_LAUNCH(8);
+#undef CAMLI_PCB_LAUNCH
+    CAMLI_RETURN_LAUNCH_STATUS();
+}

@@ -167,15 +167,49 @@ def bilinear_sample(feat2d, uv):
     return cf_of(bilinear_sample_rows(feat2d, uv))
 
 
-def convex_upsample(flow, mask, s=8):
-    """models/utils.py:191-204 (once per forward at inference); fp32 like the reference's explicit casts."""
+class _ConvexUpsample(torch.autograd.Function):
+    """camli_convex_upsample / camli_convex_upsample_backward: softmax over the taps, the 3x3 unfold, the weighted sum
+    and the pixel shuffle in one kernel each way (the backward recomputes the softmax; the flow gradient is a gather
+    over per-pixel tap sums: deterministic)."""
+
+    @staticmethod
+    def forward(ctx, flow, mask, s, scale):
+        B, _, H, W = flow.shape
+        flow = flow.contiguous()
+        mask_rows = nhwc_rows(mask)
+        ctx.save_for_backward(flow, mask_rows)
+        ctx.s, ctx.scale = s, scale
+        up = torch.empty((B, 2, H * s, W * s), dtype=torch.float32, device=flow.device)
+        with torch.cuda.device(flow.device):
+            native.call("camli_convex_upsample", i32(B), i32(H), i32(W), i32(s), ptr(flow), ptr(mask_rows), ctypes.c_float(scale),
+                        ptr(up), stream(), algo_bytes=B * H * W * 11 * s * s * 4)
+        return up
+
+    @staticmethod
+    def backward(ctx, g):
+        flow, mask_rows = ctx.saved_tensors
+        B, _, H, W = flow.shape
+        g = g.float().contiguous()
+        g_mask_rows = torch.empty_like(mask_rows)
+        taps = torch.empty((B, H, W, 18), dtype=torch.float32, device=flow.device)
+        g_flow = torch.empty_like(flow)
+        with torch.cuda.device(flow.device):
+            native.call("camli_convex_upsample_backward", i32(B), i32(H), i32(W), i32(ctx.s), ptr(flow), ptr(mask_rows),
+                        ctypes.c_float(ctx.scale), ptr(g), ptr(g_mask_rows), ptr(taps), ptr(g_flow), stream(),
+                        algo_bytes=B * H * W * (20 * ctx.s * ctx.s + 18) * 4)
+        return g_flow, nchw_view(g_mask_rows), None, None
+
+
+def convex_upsample(flow, mask, s=8, scale=1.0):
+    """models/utils.py:191-204: flow [B,2,H,W], mask [B,9*s*s,H,W] -> [B,2,s*H,s*W]; the softmax runs on scale * mask
+    (RAFT's up-sampler passes 0.25, models/raft_core.py:197).  fp32 like the reference's explicit casts."""
     flow, mask = grad.f32(flow, mask)
     _need_cuda(flow, mask)
-    B, _, H, W = flow.shape
-    mask = torch.softmax(mask.float().reshape(B, 1, 9, s, s, H, W), 2)
-    up = F.unfold(flow.float() * s, [3, 3], padding=1).view(B, 2, 9, 1, 1, H, W)
-    up = torch.sum(mask * up, 2).permute(0, 1, 4, 2, 5, 3)
-    return up.reshape(B, 2, H * s, W * s)
+    B, two, H, W = flow.shape
+    if two != 2 or tuple(mask.shape) != (B, 9 * s * s, H, W) or s not in (4, 8):
+        raise RuntimeError("convex_upsample: flow [B,2,H,W] and mask [B,9*s*s,H,W] with s = 4 or 8 expected, got %s / %s / s = %d"
+                           % (tuple(flow.shape), tuple(mask.shape), s))
+    return _ConvexUpsample.apply(flow, mask, s, float(scale))
 
 
 # ---------------------------------------------------------------- all-pairs inner products
@@ -821,8 +855,40 @@ def pointconv_group(rows, sampled_xyz, knn_idx, k, weight_net, negative_slope):
     rows, sampled_xyz = grad.f32(rows, sampled_xyz)
     _need_cuda(rows, sampled_xyz, knn_idx)
     (w1, b1), (w2, b2) = weight_net.convs[0].folded(), weight_net.convs[1].folded()
-    return grad.recompute(_pointconv_group, grad.f_pointconv_group, rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2,
-                          negative_slope)
+    if not grad.needs_grad(rows, sampled_xyz, w1, b1, w2, b2):
+        return _pointconv_group(rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2, negative_slope)
+    return _PointConvGroup.apply(rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2, negative_slope)
+
+
+class _PointConvGroup(torch.autograd.Function):
+    """Backward by camli_pointconv_group_backward: the WeightNet is re-evaluated per neighbour, the row gradient is a
+    scatter-add over the neighbour tables, the WeightNet's parameter gradients are reduced per CTA (176 atomics each)."""
+
+    @staticmethod
+    def forward(ctx, rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2, slope):
+        rows, knn_idx = rows.contiguous(), knn_idx.contiguous()
+        ctx.save_for_backward(rows, sampled_xyz, knn_idx, w1, b1, w2, b2)
+        ctx.k, ctx.slope = k, slope
+        return _pointconv_group(rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2, slope)
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, sampled_xyz, knn_idx, w1, b1, w2, b2 = ctx.saved_tensors
+        B, N, C = rows.shape
+        S, K = knn_idx.shape[1], knn_idx.shape[2]
+        g = g.float().contiguous()
+        g_rows = torch.zeros_like(rows)
+        g_centre = torch.empty((B, 3, S), dtype=torch.float32, device=rows.device)
+        g_par = torch.zeros(176, dtype=torch.float32, device=rows.device)
+        cs = sampled_xyz.stride()
+        with torch.cuda.device(rows.device):
+            native.call("camli_pointconv_group_backward", i32(B), i32(N), i32(S), i32(K), i32(ctx.k), i32(C), ptr(rows), i64(C),
+                        ptr(sampled_xyz), i64(cs[0]), i64(cs[2]), i64(cs[1]), ptr(knn_idx),
+                        ptr(w1.contiguous()), ptr(b1.contiguous()), ptr(w2.contiguous()), ptr(b2.contiguous()),
+                        ctypes.c_float(ctx.slope), ptr(g), ptr(g_rows), ptr(g_centre), ptr(g_par), stream(),
+                        algo_bytes=B * S * (ctx.k * (2 * C * 4 + 8) + 16 * C * 4), flops=4 * B * S * 16 * ctx.k * C)
+        return (g_rows, g_centre, None, None, g_par[:24].view(8, 3), g_par[24:32], g_par[32:160].view(16, 8), g_par[160:],
+                None)
 
 
 def _pointconv_group(rows, sampled_xyz, knn_idx, k, w1, b1, w2, b2, negative_slope):

@@ -313,7 +313,7 @@ class ConvexUpsampler2D(nn.Module):
 
     def forward(self, h, flow):
         mask = tc.conv2d(tc.conv2d(h.float(), self.mask[0], "relu"), self.mask[2])
-        return convex_upsample(flow, 0.25 * mask)
+        return convex_upsample(flow, mask, mask_scale=0.25)
 
 
 class RAFTCore(nn.Module):

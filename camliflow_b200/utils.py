@@ -88,9 +88,10 @@ def backwarp_2d(x, flow12, padding_mode):
     return F.grid_sample(x, torch.stack([gx, gy], -1), padding_mode=padding_mode, align_corners=True)
 
 
-def convex_upsample(flow, mask, scale_factor=8):
-    """Convex-combination upsampling of a 1/s flow field (utils.py:191-204)."""
-    return ops.convex_upsample(flow, mask, scale_factor)
+def convex_upsample(flow, mask, scale_factor=8, mask_scale=1.0):
+    """Convex-combination upsampling of a 1/s flow field (utils.py:191-204); `mask_scale` multiplies the mask logits
+    first (the 0.25 of raft_core.py:197, folded into the kernel)."""
+    return ops.convex_upsample(flow, mask, scale_factor, mask_scale)
 
 
 def project_pc2image(pc, camera_info):

@@ -228,6 +228,37 @@ int camli_bilinear_sample_rows(int B, int H, int W, int N, int C, const float* f
                                float* out_rows, int64_t ld_out, void* stream);
 
 /*
+ * Backward of camli_pointconv_group (the reference differentiates models/point_conv.py:56-66 through autograd).
+ * grad_out [B,S,16*C] -> grad_rows [B,N,C] (ZERO-INITIALISED by the caller: scatter-add over the neighbour tables),
+ * grad_centre [B,3,S] contiguous (every element written) and grad_params[176] = dW1[8,3] | db1[8] | dW2[16,8] |
+ * db2[16] of the WeightNet (ZERO-INITIALISED by the caller).  Other arguments as in the forward.
+ */
+int camli_pointconv_group_backward(int B, int N, int S, int K, int k, int C,
+                                   const float* rows, int64_t ld_rows,
+                                   const float* centre_xyz, int64_t c_sb, int64_t c_sp, int64_t c_sd,
+                                   const int64_t* knn_idx, const float* W1, const float* b1, const float* W2,
+                                   const float* b2, float negative_slope, const float* grad_out,
+                                   float* grad_rows, float* grad_centre, float* grad_params, void* stream);
+
+/*
+ * Convex up-sampling of a coarse flow field (convex_upsample, models/utils.py:191-204; callers
+ * models/raft_core.py:184-197 with factor 8 and `0.25 * mask`, models/pwc_core.py:218-224 with factor 4):
+ *   up[b,c,S*h+i,S*w+j] = sum_k softmax_k(scale * mask[b,h,w, k*S*S + i*S + j]) * S * flow[b,c,h+dy_k,w+dx_k]
+ * k = 3*(dy+1)+(dx+1), zeros outside the map.  flow [B,2,H,W] contiguous, mask_rows NHWC [B,H,W,9*S*S],
+ * up [B,2,S*H,S*W] contiguous; factor S = 4 or 8.
+ */
+int camli_convex_upsample(int B, int H, int W, int factor, const float* flow, const float* mask_rows, float scale,
+                          float* up, void* stream);
+
+/*
+ * Its backward: grad_up [B,2,S*H,S*W] -> grad_mask_rows [B,H,W,9*S*S] (every element written) and grad_flow
+ * [B,2,H,W] (every element written; gathered from tap_scratch, B*H*W*18 floats of workspace).
+ */
+int camli_convex_upsample_backward(int B, int H, int W, int factor, const float* flow, const float* mask_rows, float scale,
+                                   const float* grad_up, float* grad_mask_rows, float* tap_scratch, float* grad_flow,
+                                   void* stream);
+
+/*
  * PointConv grouping stage (models/point_conv.py:56-66): rows [B,N,ld_rows] hold [xyz | features]
  * channel-last (xyz in columns 0..2, C columns used); out[b,s,w*C + c] =
  * sum_{j<k} WeightNet(xyz[idx[b,s,j]] - centre[b,s])[w] * rows[b, idx[b,s,j], c], w < 16, with

@@ -60,6 +60,7 @@ def cpu_kernels():
         (ops, "knn_interpolate"): knn_interpolate,
         (ops, "backwarp_3d"): backwarp_3d,
         (ops, "bilinear_sample_rows"): lambda f, uv: ops.rows_of(R.bilinear_sample(f, uv)),
+        (ops, "convex_upsample"): lambda flow, mask, s=8, scale=1.0: co.convex_upsample(flow.float(), (scale * mask.float()).contiguous(), s),
         (ops, "corr2d_build"): R.corr2d_build,
         (ops, "corr2d_lookup"): lambda pyr, c, r, channels_last=True: R.corr2d_lookup(pyr, c, r),
         (ops, "corr3d_build"): corr3d_build,

@@ -67,6 +67,15 @@ def test_new_entry_points_validate_arguments_without_launching():
     assert h.camli_corr2d_lookup_backward(None, None, None, 4, None, None, 1, 4, 4, 3, None) == -2      # radius != 4
     assert h.camli_pointconv_dw_gather_max_backward(1, 8, 4, 3, 4, 16, None, None, None, None, None, None, None) == -1   # K < k
     assert h.camli_split_tf32(None, None, None, i64(0), None) == 0
+    # camli_convex_upsample(B,H,W,factor, flow, mask_rows, scale, up, stream)
+    assert h.camli_convex_upsample(0, 4, 4, 8, None, None, f32(0.25), None, None) == 0            # empty batch
+    assert h.camli_convex_upsample(1, 4, 4, 3, None, None, f32(0.25), None, None) == -2           # factor is 4 or 8
+    assert h.camli_convex_upsample(1, 4, 4, 8, None, None, f32(0.25), None, None) == -1           # null pointers
+    assert h.camli_convex_upsample_backward(1, 4, 4, 4, None, None, f32(1), None, None, None, None, None) == -1
+    # camli_pointconv_group_backward(B,N,S,K,k,C, rows,ld, centre,sb,sp,sd, idx, W1,b1,W2,b2, slope, g_out, g_rows, g_centre, g_params, stream)
+    pgb = lambda S, K, k, C, ld: h.camli_pointconv_group_backward(                                                  # noqa: E731
+        1, 64, S, K, k, C, None, i64(ld), None, i64(0), i64(1), i64(S), None, None, None, None, None, f32(0.1), None, None, None, None, None)
+    assert pgb(0, 16, 16, 35, 35) == 0 and pgb(8, 8, 16, 35, 35) == -1 and pgb(8, 16, 16, 300, 300) == -2 and pgb(8, 16, 16, 35, 35) == -1
 
 
 def test_training_entry_points_validate_arguments_without_launching():

@@ -459,3 +459,51 @@ def test_captured_train_step_matches_eager(dev):
     assert out[True][0] != out[True][2]                          # the weights move
     for a, b in zip(out[True], out[False]):
         assert abs(a - b) <= 2e-4 * abs(b), (out[True], out[False])
+
+
+@pytest.mark.parametrize("B,H,W,s,scale", [(1, 68, 120, 8, 0.25), (2, 17, 23, 8, 0.25), (2, 33, 60, 4, 1.0), (1, 5, 3, 4, 1.0)])
+def test_convex_upsample_forward_backward(dev, B, H, W, s, scale):
+    """camli_convex_upsample{,_backward} against the reference formula (oracle.convex_upsample = models/utils.py:191-204)
+    and its autograd gradients; RAFT's factor 8 with the 0.25 mask scale and CamLiPWC's factor 4."""
+    from camliflow_b200 import ops
+    from oracle import camliraft_oracle as co
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    flow = (torch.randn(B, 2, H, W, generator=g) * 3).to(dev)
+    mask = (torch.randn(B, 9 * s * s, H, W, generator=g) * 4).to(dev).contiguous(memory_format=torch.channels_last)
+    gout = torch.randn(B, 2, H * s, W * s, generator=g).to(dev)
+    f1, m1 = flow.clone().requires_grad_(True), mask.clone().requires_grad_(True)
+    want = co.convex_upsample(f1, (scale * m1).contiguous(), s)
+    want.backward(gout)
+    f2, m2 = flow.clone().requires_grad_(True), mask.clone().requires_grad_(True)
+    got = ops.convex_upsample(f2, m2, s, scale)
+    got.backward(gout)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())      # fp32: summation order only
+    for a, b, name in ((f2.grad, f1.grad, "flow"), (m2.grad, m1.grad, "mask")):
+        assert (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item()), name
+    with torch.no_grad():                                                                  # the inference doorway
+        assert torch.equal(ops.convex_upsample(flow, mask, s, scale), got.detach())
+
+
+@pytest.mark.parametrize("B,N,S,C,k", [(2, 700, 300, 32, 16), (1, 2048, 1024, 96, 16), (2, 512, 203, 128, 9), (1, 300, 64, 250, 16)])
+def test_pointconv_group_backward_kernel(dev, B, N, S, C, k):
+    """camli_pointconv_group_backward against autograd through the reference formula (tests/torch_ref.pointconv_group =
+    models/point_conv.py:56-66): gradients of the feature AND coordinate columns, the centroids and the four WeightNet
+    parameters.  Scatter-adds are float atomics: 1e-4 relative."""
+    from camliflow_b200.mlp import MLP2d
+    ops = _ops()
+    g = torch.Generator().manual_seed(N + C)
+    xyz = ((torch.rand(B, 3, N, generator=g) - 0.5) * 6).to(dev).requires_grad_(True)
+    feat = torch.randn(B, C, N, generator=g).to(dev).requires_grad_(True)
+    centre = (xyz.detach()[:, :, :S] + 0.01).contiguous().requires_grad_(True)
+    idx = _knn(xyz.detach(), centre.detach(), k + 3)                    # a wider table than k, as the encoders pass
+    wn = MLP2d(3, [8, 16], act="leaky_relu").to(dev)
+    fp = [wn.convs[0].conv_fn.weight.flatten(1), wn.convs[0].conv_fn.bias, wn.convs[1].conv_fn.weight.flatten(1),
+          wn.convs[1].conv_fn.bias]
+    out = ops.pointconv_group(ops.rows_of(torch.cat([xyz, feat], 1)), centre, idx, k, wn, 0.1)
+    gg = torch.randn(out.shape, generator=g).to(dev)
+    leaves = [xyz, feat, centre] + list(wn.parameters())
+    got = torch.autograd.grad(out, leaves, gg)
+    want = torch.autograd.grad(R.pointconv_group(xyz, feat, centre, idx[:, :, :k], *fp, 0.1), leaves, gg)
+    for name, a, b in zip(["xyz", "feat", "centre", "w1", "b1", "w2", "b2"], got, want):
+        assert a.shape == b.shape and _rel(a, b) <= 1e-4, (name, _rel(a, b))
