@@ -108,18 +108,29 @@ class CamLiRAFT_Core(nn.Module):
         dw_cache = {}                  # iteration-invariant WeightNet outputs of the PointConvDW layers
         gru_cache = {}                 # iteration-invariant context contributions to the ConvGRU pre-activations
         preds_2d, preds_3d = [], []
+        # Software pipelining of the point branch (two-stream inference only): its back-warp + correlation lookup of
+        # iteration i+1 depend on flow_3d alone, and the point branch finishes an iteration well before the image branch
+        # (ConvGRU + flow head); issued right behind the point update they are done when the image chain comes round,
+        # instead of standing in front of the correlation fusion (~60 us of every iteration).
+        ahead = par.enabled and not cfgs.fuse_hidden and os.environ.get("CAMLI_PIPELINE_3D", "1") != "0"
+        corr_3d_next = None
         for it in range(n_iters):
             if it > 0:
                 flow_2d, flow_3d = flow_2d.detach(), flow_3d.detach()
 
-            def corr_3d_fn():
-                warped = warp_pyramid(xyz1, xyzs2, flow_3d) if it > 0 else xyzs2
+            def corr_3d_fn(flow=None):
+                flow = flow_3d if flow is None else flow
+                warped = warp_pyramid(xyz1, xyzs2, flow) if (it > 0 or flow is not flow_3d) else xyzs2
                 return b3.correlation.forward_rows(xyz1, warped)
 
             # the flow half of the motion encoder only needs flow_2d: on a stream of its own it runs beside the
             # lookups and the correlation fusion instead of in front of them (2 of the ~25 launches of the image chain)
+            if corr_3d_next is None:
+                corr_2d, corr_3d = par.run(lambda: b2.correlation(grid + flow_2d), corr_3d_fn)
+            else:
+                corr_2d, corr_3d = b2.correlation(grid + flow_2d), corr_3d_next
+            # (forked behind the lookup: its 7x7 convolution fills every SM and must not stand in front of the chain)
             cf_fork = par.fork(lambda: b2.motion_encoder.flow_features(flow_2d)) if tc.fused(flow_2d) else None
-            corr_2d, corr_3d = par.run(lambda: b2.correlation(grid + flow_2d), corr_3d_fn)
             if cfgs.fuse_corr:
                 corr_2d, corr_3d = self.clfm_corr.forward_rows(uv1, corr_2d, corr_3d, nn1, par)
             cf_2d = cf_fork.join() if cf_fork is not None else None
@@ -128,7 +139,9 @@ class CamLiRAFT_Core(nn.Module):
                 lambda: b2.motion_encoder(flow_2d, corr_2d, cf_2d),
                 lambda: b3.motion_encoder.forward_rows(xyz1, ops.rows_of(flow_3d), corr_3d, nbr, dw_cache))
             if cfgs.fuse_motion:
-                motion_2d, motion_3d = self.clfm_motion.forward_rows(uv1, motion_2d, motion_3d, nn1, par)
+                # the fused image features are the ConvGRU's x_dynamic: written straight into its state buffer
+                slot = b2.gru.dynamic_slot(gru_cache, h_2d, motion_2d.shape[1]) if tc.fused(h_2d) and not cfgs.fuse_hidden else None
+                motion_2d, motion_3d = self.clfm_motion.forward_rows(uv1, motion_2d, motion_3d, nn1, par, out_2d=slot)
 
             last = every or it == n_iters - 1
 
@@ -143,9 +156,10 @@ class CamLiRAFT_Core(nn.Module):
             def update_3d():
                 h = b3.gru.forward_rows(xyz1, h_3d, torch.cat([x_3d, motion_3d], dim=-1), nbr, dw_cache)
                 if cfgs.fuse_hidden:
-                    return h, None, None
+                    return h, None, None, None
                 flow = flow_3d + ops.cf_of(b3.flow_head.forward_rows(xyz1, h, nbr, dw_cache))
-                return h, flow, (knn_interpolation(xyz1, flow, pc1, k=3) if last else None)
+                nxt = corr_3d_fn(flow.detach()) if ahead and it < n_iters - 1 else None
+                return h, flow, (knn_interpolation(xyz1, flow, pc1, k=3) if last else None), nxt
 
             if cfgs.fuse_hidden:       # hidden-state fusion sits between the GRUs and the flow heads
                 h_2d, h_3d = b2.gru(h=h_2d, x=torch.cat([x_2d, motion_2d], dim=1)), update_3d()[0]
@@ -155,7 +169,7 @@ class CamLiRAFT_Core(nn.Module):
                 up_2d = b2.convex_upsampler(h_2d, flow_2d) if last else None
                 up_3d = knn_interpolation(xyz1, flow_3d, pc1, k=3) if last else None
             else:
-                (h_2d, flow_2d, up_2d), (h_3d, flow_3d, up_3d) = par.run(update_2d, update_3d)
+                (h_2d, flow_2d, up_2d), (h_3d, flow_3d, up_3d, corr_3d_next) = par.run(update_2d, update_3d)
             if last:
                 preds_2d.append(up_2d)
                 preds_3d.append(up_3d)
@@ -188,7 +202,7 @@ class _TwoStreams:
             return _Joined(fn())
         dev = torch.cuda.current_device()
         if (dev, key) not in _TwoStreams._aux:
-            _TwoStreams._aux[(dev, key)] = torch.cuda.Stream(dev)
+            _TwoStreams._aux[(dev, key)] = torch.cuda.Stream(dev, priority=0)      # below the two branch streams
         s = _TwoStreams._aux[(dev, key)]
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

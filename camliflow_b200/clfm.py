@@ -57,16 +57,20 @@ class SKFusion(nn.Module):
     def _fused_tail_ok(self, a):
         return a.is_cuda and not (torch.is_grad_enabled() and (a.requires_grad or self.fc_mid[0].weight.requires_grad))
 
-    def forward(self, feat_2d, feat_3d, aligned_2d=None):
-        """aligned_2d: align1(feat_2d) if the caller already started it (a handle with .join())."""
+    def forward(self, feat_2d, feat_3d, aligned_2d=None, out=None):
+        """aligned_2d: align1(feat_2d) if the caller already started it (a handle with .join()); out: a logical [B,C,H,W]
+        channel-last destination (a channel slice of a wider buffer) for the fused tail."""
         b = self.align2(feat_3d)
         a = self.align1(feat_2d) if aligned_2d is None else aligned_2d.join()
         B, C = a.shape[:2]
         if a.dim() == 4 and self._fused_tail_ok(a):        # pool + FCs + softmax + blend in 3 launches
             H, W = a.shape[-2:]
-            out = ops.sk_fusion_tail(ops.nhwc_rows(a).view(B, H * W, C), ops.nhwc_rows(b).view(B, H * W, C), 1.0,
-                                     self.fc_mid[0].weight, self.fc_out[0].weight)
-            return ops.nchw_view(out.view(B, H, W, C))
+            dst = None
+            if out is not None:
+                dst = out.permute(0, 2, 3, 1).view(B, H * W, C)           # (raises unless the slice is viewable as rows)
+            res = ops.sk_fusion_tail(ops.nhwc_rows(a).view(B, H * W, C), ops.nhwc_rows(b).view(B, H * W, C), 1.0,
+                                     self.fc_mid[0].weight, self.fc_out[0].weight, out=dst)
+            return out if out is not None else ops.nchw_view(res.view(B, H, W, C))
         w = self._blend_weights((a + b).flatten(2).mean(-1))
         shape = (B, C) + (1,) * (a.dim() - 2)
         return a * w[..., 0].reshape(shape) + b * w[..., 1].reshape(shape)
@@ -97,16 +101,20 @@ class CLFM(nn.Module):
         out2d, out3d_rows = self.forward_rows(uv, feat_2d, ops.rows_of(feat_3d.float()), nn_idx)
         return out2d, ops.cf_of(out3d_rows)
 
-    def forward_rows(self, uv, feat_2d, feat3d_rows, nn_idx=None, par=None):
+    def forward_rows(self, uv, feat_2d, feat3d_rows, nn_idx=None, par=None, out_2d=None):
         """Same with channel-last point features in and out.  The two directions only read the
-        inputs, so `par` (a fork/join helper with .run(fn_a, fn_b)) may execute them concurrently."""
+        inputs, so `par` (a fork/join helper with .run(fn_a, fn_b)) may execute them concurrently.
+        out_2d: where the fused image features go (SKFusion.forward's `out`), inference only."""
         feat_2d = feat_2d.float()
 
         def to_2d():
             # align1 of the selective-kernel fusion does not depend on the interpolation: beside it, not behind it
+            # (forked behind the interpolation kernel: a 324-channel alignment layer is more than one wave of CTAs)
+            H, W = feat_2d.shape[-2:]
+            nn = ops.nearest_point_2d(uv, H, W) if nn_idx is None else nn_idx
+            raw = ops.clfm_interp(uv, nn, feat3d_rows.detach(), self.interp.score_net, H, W)
             early = par.fork(lambda: self.fuse2d.align1(feat_2d), "clfm") if par is not None and hasattr(par, "fork") else None
-            interp = self.interp.forward_rows(uv, feat_2d.shape[-2:], feat3d_rows.detach(), nn_idx)
-            return self.fuse2d(feat_2d, interp, early)
+            return self.fuse2d(feat_2d, self.interp.out_conv(raw), early, out_2d)
 
         def to_3d():
             sampled = ops.bilinear_sample_rows(feat_2d.detach(), uv)

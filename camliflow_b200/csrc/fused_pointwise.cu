@@ -97,13 +97,15 @@ sk_out_kernel(const float* __restrict__ mid, int C, int Cm, const float* __restr
 template <int VEC>
 __global__ void __launch_bounds__(256)
 sk_blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ weights,
-                size_t PC, int C, float slope, float* __restrict__ out) {
+                size_t PC, int C, float slope, float* __restrict__ out, long long ldo) {   // out rows of pitch ldo (>= C); PC < 2^32
     const int bi = blockIdx.y;
     const float2* w = reinterpret_cast<const float2*>(weights) + (size_t)bi * C;
     const size_t nv = PC / VEC;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)((i * VEC) % C);
-        const size_t g = (size_t)bi * PC + i * VEC;
+        const unsigned e = (unsigned)(i * VEC), row = e / (unsigned)C;
+        const int c = (int)(e - row * (unsigned)C);
+        const size_t g = (size_t)bi * PC + e;
+        float* o_ptr = out + ((size_t)bi * (PC / C) + row) * ldo + c;
         if (VEC == 4) {
             const float4 av = __ldcs(reinterpret_cast<const float4*>(a + g)), bv = __ldcs(reinterpret_cast<const float4*>(b + g));
             const float2 w0 = __ldg(w + c), w1 = __ldg(w + c + 1), w2 = __ldg(w + c + 2), w3 = __ldg(w + c + 3);
@@ -112,10 +114,10 @@ sk_blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const 
             o.y = camli_leaky(av.y, slope) * w1.x + camli_leaky(bv.y, slope) * w1.y;
             o.z = camli_leaky(av.z, slope) * w2.x + camli_leaky(bv.z, slope) * w2.y;
             o.w = camli_leaky(av.w, slope) * w3.x + camli_leaky(bv.w, slope) * w3.y;
-            *reinterpret_cast<float4*>(out + g) = o;
+            *reinterpret_cast<float4*>(o_ptr) = o;
         } else {
             const float2 w0 = __ldg(w + c);
-            out[g] = camli_leaky(__ldg(a + g), slope) * w0.x + camli_leaky(__ldg(b + g), slope) * w0.y;
+            *o_ptr = camli_leaky(__ldg(a + g), slope) * w0.x + camli_leaky(__ldg(b + g), slope) * w0.y;
         }
     }
 }
@@ -166,7 +168,16 @@ inline unsigned grid_for(size_t n) {
 extern "C" int camli_sk_fusion_tail(int B, int P, int C, int C_mid, const float* a_rows, const float* b_rows,
                                     float negative_slope, const float* w_mid, const float* w_out,
                                     float* partial_scratch, float* weights_scratch, float* out_rows, void* stream) {
-    if (B < 0 || P < 1 || C < 1 || C_mid < 1) return CAMLI_EINVAL;
+    return camli_sk_fusion_tail_strided(B, P, C, C_mid, a_rows, b_rows, negative_slope, w_mid, w_out, partial_scratch,
+                                        weights_scratch, out_rows, C, stream);
+}
+
+extern "C" int camli_sk_fusion_tail_strided(int B, int P, int C, int C_mid, const float* a_rows, const float* b_rows,
+                                            float negative_slope, const float* w_mid, const float* w_out,
+                                            float* partial_scratch, float* weights_scratch, float* out_rows, int64_t ld_out,
+                                            void* stream) {
+    if (B < 0 || P < 1 || C < 1 || C_mid < 1 || ld_out < C) return CAMLI_EINVAL;
+    if ((long long)P * C > 4294967295LL) return CAMLI_EUNSUPPORTED;
     if (B > 65535 || (size_t)(C > C_mid ? C : C_mid) * sizeof(float) > 48 * 1024) return CAMLI_EUNSUPPORTED;
     if (B == 0) return CAMLI_OK;
     if (!a_rows || !b_rows || !w_mid || !w_out || !partial_scratch || !weights_scratch || !out_rows) return CAMLI_EINVAL;
@@ -178,10 +189,11 @@ extern "C" int camli_sk_fusion_tail(int B, int P, int C, int C_mid, const float*
     sk_mid_kernel<<<dim3(camli_div_up(C_mid, 8), B), 256, (size_t)C * sizeof(float), st>>>(partial_scratch, P, C, C_mid, w_mid, mid);
     sk_out_kernel<<<dim3(camli_div_up(C, 8), B), 256, (size_t)C_mid * sizeof(float), st>>>(mid, C, C_mid, w_out, weights_scratch);
     const size_t PC = (size_t)P * C;
-    const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(a_rows) | reinterpret_cast<uintptr_t>(b_rows) |
-                                       reinterpret_cast<uintptr_t>(out_rows)) % 16 == 0);
-    if (vec) sk_blend_kernel<4><<<dim3(grid_for(PC / 4), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows);
-    else     sk_blend_kernel<1><<<dim3(grid_for(PC), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows);
+    const bool vec = (C % 4 == 0) && (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(a_rows) | reinterpret_cast<uintptr_t>(b_rows) |
+                                                           reinterpret_cast<uintptr_t>(out_rows)) % 16 == 0);
+    // batch b's rows start at out_rows + b * P * ld_out: the kernel's row index runs over all B * P rows
+    if (vec) sk_blend_kernel<4><<<dim3(grid_for(PC / 4), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows, ld_out);
+    else     sk_blend_kernel<1><<<dim3(grid_for(PC), B), 256, 0, st>>>(a_rows, b_rows, weights_scratch, PC, C, negative_slope, out_rows, ld_out);
     CAMLI_RETURN_LAUNCH_STATUS();
 }
 

@@ -2,6 +2,8 @@
 whole forward captured in ONE CUDA graph, so a B=1 frame pair costs one graph launch instead
 of ~1.5 k eager launches.  `FlowEngine.__call__` is the public end-to-end
 call: host tensors in, host tensors out."""
+import os
+
 import torch
 
 from . import native
@@ -28,7 +30,8 @@ class FlowEngine:
         self.dev_out = None
         self.graph = None
         self.launches_per_step = 0
-        self.stream = torch.cuda.Stream(self.device)
+        # (a high-priority main stream was measured: it delays the FPS on the side stream and lengthens the pre-loop phase)
+        self.stream = torch.cuda.Stream(self.device, priority=int(os.environ.get("CAMLI_MAIN_PRIORITY", "0")))
         self._prepare(use_graph, warmup)
 
     # ------------------------------------------------------------------ setup

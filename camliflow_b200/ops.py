@@ -967,22 +967,28 @@ def _clfm_interp(uv, nn_idx, feat3d_rows, w1, b1, w2, b2, H, W):
 
 
 # ---------------------------------------------------------------- fused pointwise stages
-def sk_fusion_tail(a_rows, b_rows, negative_slope, w_mid, w_out):
+def sk_fusion_tail(a_rows, b_rows, negative_slope, w_mid, w_out, out=None):
     """SKFusion after the align layers (models/clfm.py:199-214) on rows [B,P,C]: activation of the two
-    inputs (leaky, slope 1 = already activated), pooled mean, two bias-free FCs, pair softmax, blend."""
+    inputs (leaky, slope 1 = already activated), pooled mean, two bias-free FCs, pair softmax, blend.
+    out: optional [B,P,C] destination view with unit channel stride and row pitch ld (batch pitch P * ld): a channel
+    slice of a wider channel-last buffer."""
     _need_cuda(a_rows, b_rows, w_mid, w_out)
     _no_grad("sk_fusion_tail", a_rows, b_rows, w_mid, w_out)
     assert a_rows.is_contiguous() and b_rows.is_contiguous() and a_rows.shape == b_rows.shape
     B, P, C = a_rows.shape
     Cm = w_mid.shape[0]
     assert w_mid.shape == (Cm, C) and w_out.shape == (2 * C, Cm)
-    out = torch.empty_like(a_rows)
+    if out is None:
+        out = torch.empty_like(a_rows)
+    ld = out.stride(1)
+    if tuple(out.shape) != (B, P, C) or out.stride(2) != 1 or ld < C or (B > 1 and out.stride(0) != P * ld) or out.dtype != torch.float32:
+        raise RuntimeError("sk_fusion_tail: out must be a [B,P,C] fp32 view with unit channel stride and batch pitch P * row pitch")
     partial = torch.empty((B, 32, C), dtype=torch.float32, device=out.device)
     weights = torch.empty((B * (2 * C + Cm),), dtype=torch.float32, device=out.device)
     with torch.cuda.device(out.device):
-        native.call("camli_sk_fusion_tail", i32(B), i32(P), i32(C), i32(Cm), ptr(a_rows), ptr(b_rows),
+        native.call("camli_sk_fusion_tail_strided", i32(B), i32(P), i32(C), i32(Cm), ptr(a_rows), ptr(b_rows),
                     ctypes.c_float(negative_slope), ptr(w_mid.contiguous()), ptr(w_out.contiguous()), ptr(partial),
-                    ptr(weights), ptr(out), stream(), algo_bytes=B * P * C * 4 * 5)
+                    ptr(weights), ptr(out), i64(ld), stream(), algo_bytes=B * P * C * 4 * 5)
     return out
 
 

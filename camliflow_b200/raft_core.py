@@ -202,6 +202,23 @@ class GRU2D(nn.Module):
             cache[id(convz)] = hit
         return hit[2], hit[3], hit[4]
 
+    @staticmethod
+    def _state_buffers(cache, h, X):
+        """[h | x_dynamic | r*h] and z, channel-last, one pair per forward pass (kept in the caller's cache)."""
+        bufs = cache.get("gru2d_buffers")
+        if bufs is None:
+            B, C, H, W = h.shape
+            bufs = (torch.empty((B, H, W, C + X + C), dtype=torch.float32, device=h.device),
+                    torch.empty((B, H, W, C), dtype=torch.float32, device=h.device))
+            cache["gru2d_buffers"] = bufs
+        return bufs
+
+    def dynamic_slot(self, cache, h, X):
+        """The x_dynamic group of the state buffer as a logical [B,X,H,W] map: the layer that produces the motion features
+        writes them here and forward_split() finds them in place (no copy kernel on the image chain)."""
+        C = h.shape[1]
+        return self._state_buffers(cache, h, X)[0][..., C:C + X].permute(0, 3, 1, 2)
+
     def forward_split(self, h, x_static, x_dynamic, cache):
         """forward(h, cat([x_static, x_dynamic])) as four tensor-core launches per call and nothing else:
         * the x_static contributions to the z, r and q pre-activations come from `cache` (a dict owned by the
@@ -212,16 +229,12 @@ class GRU2D(nn.Module):
           view of its first group and is recognised (no copy) when it comes back in the next iteration."""
         B, C, H, W = h.shape
         S, X = x_static.shape[1], x_dynamic.shape[1]
-        bufs = cache.get("gru2d_buffers")
-        if bufs is None:
-            bufs = (torch.empty((B, H, W, C + X + C), dtype=torch.float32, device=h.device),
-                    torch.empty((B, H, W, C), dtype=torch.float32, device=h.device))
-            cache["gru2d_buffers"] = bufs
-        Q, Z = bufs
+        Q, Z = self._state_buffers(cache, h, X)
         h_rows = Q[..., :C]
         if h.data_ptr() != h_rows.data_ptr():
             h_rows.copy_(h.permute(0, 2, 3, 1))
-        Q[..., C:C + X].copy_(x_dynamic.permute(0, 2, 3, 1))
+        if x_dynamic.data_ptr() != Q[..., C:C + X].data_ptr():      # (a producer that was handed dynamic_slot() wrote it in place)
+            Q[..., C:C + X].copy_(x_dynamic.permute(0, 2, 3, 1))
         xs_rows = x_static.permute(0, 2, 3, 1)
         if not ops.conv_gemm_ok(xs_rows):
             xs_rows = xs_rows.contiguous()
@@ -266,22 +279,21 @@ class MotionEncoder2D(nn.Module):
         B, _, H, W = flow.shape
         cf = torch.empty((B, H, W, 192 + 64), dtype=torch.float32, device=flow.device)
         tc.conv2d(tc.conv2d(flow, self.conv_f1, "relu"), self.conv_f2, "relu", out=cf[..., 192:])
-        return cf
+        # the encoder's output buffer [out | flow] with its flow columns filled: also off the image chain
+        n_out = self.conv.out_channels
+        mf = torch.empty((B, H, W, n_out + 2), dtype=torch.float32, device=flow.device)
+        mf[..., n_out:].copy_(flow.permute(0, 2, 3, 1))
+        return cf, mf
 
     def forward(self, flow, corr, cf=None):
         if tc.fused(corr):
             # every convolution with its ReLU in one kernel; the two branches write straight into the halves
             # of one channel-last buffer (no torch.cat)
-            if cf is None:
-                cf = self.flow_features(flow)
+            cf, mf = self.flow_features(flow) if cf is None else cf
             tc.conv2d(tc.conv2d(corr, self.conv_c1, "relu"), self.conv_c2, "relu", out=cf[..., :192])
             # the last convolution (ReLU + nan_to_num in its epilogue) and the flow land in one channel-last buffer
             # [out | flow]: no nan_to_num, cat or layout-conversion kernels
-            B, _, H, W = flow.shape
-            n_out = self.conv.out_channels
-            mf = torch.empty((B, H, W, n_out + 2), dtype=torch.float32, device=flow.device)
-            tc.conv2d(cf.permute(0, 3, 1, 2), self.conv, "relu_fix", out=mf[..., :n_out])
-            mf[..., n_out:].copy_(flow.permute(0, 2, 3, 1))
+            tc.conv2d(cf.permute(0, 3, 1, 2), self.conv, "relu_fix", out=mf[..., :self.conv.out_channels])
             return mf.permute(0, 3, 1, 2)
         c = tc.conv2d(tc.conv2d(corr, self.conv_c1, "relu"), self.conv_c2, "relu")
         f = tc.conv2d(tc.conv2d(flow, self.conv_f1, "relu"), self.conv_f2, "relu")

@@ -326,6 +326,13 @@ int camli_sk_fusion_tail(int B, int P, int C, int C_mid, const float* a_rows, co
                          float negative_slope, const float* w_mid, const float* w_out,
                          float* partial_scratch, float* weights_scratch, float* out_rows, void* stream);
 
+/* The same with output rows of pitch ld_out (>= C) floats: the blend lands in a channel slice of a wider buffer
+ * (the ConvGRU's [h | x | r*h] state), batch b's rows starting at out_rows + b * P * ld_out. */
+int camli_sk_fusion_tail_strided(int B, int P, int C, int C_mid, const float* a_rows, const float* b_rows,
+                                 float negative_slope, const float* w_mid, const float* w_out,
+                                 float* partial_scratch, float* weights_scratch, float* out_rows, int64_t ld_out,
+                                 void* stream);
+
 /*
  * ConvGRU gate stage (models/raft_core.py:125-128 / :132-135): zr [rows,2H] = pre-activation output
  * of the merged z|r convolution, h [rows,H], x [rows,X] (all channel-last rows):

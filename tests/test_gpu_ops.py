@@ -218,6 +218,11 @@ def test_sk_fusion_tail(dev, B, P, C):
     for slope in (1.0, 0.1):
         out = _ops().sk_fusion_tail(a, b, slope, w_mid, w_out)
         _close(out, R.sk_fusion_tail(a, b, slope, w_mid, w_out), 2e-5, what="sk_fusion_tail")
+        # the same into a channel slice of a wider channel-last buffer (camli_sk_fusion_tail_strided)
+        wide = torch.full((B, P, C + 24), 7.0, device=dev)
+        got = _ops().sk_fusion_tail(a, b, slope, w_mid, w_out, out=wide[..., 8:8 + C])
+        assert got.data_ptr() == wide[..., 8:8 + C].data_ptr() and torch.equal(wide[..., 8:8 + C], out)
+        assert bool((wide[..., :8] == 7.0).all()) and bool((wide[..., 8 + C:] == 7.0).all())
 
 
 @pytest.mark.parametrize("channels_last", [True, False])
