@@ -13,7 +13,7 @@ for name in ("bench_c3", "bench_c4", "bench_c5", "bench_c5_library", "bench_c5_f
         line = json.loads(open(src).read().strip().splitlines()[-1])
         json.dump(line, open(os.path.join(PROF, "%s_%s.json" % (tag, name)), "w"), indent=1)
         print(name, round(line["value"], 2), line["unit"])
-for name in ("microbench_l0.json", "cg_time.txt", "trace_train.txt", "cg_timeline.log"):
+for name in ("microbench_l0.json", "cg_time.txt", "cg_time_small.txt", "trace_train.txt", "trace_iteration.txt", "cg_timeline.log"):
     src = os.path.join(OUT, name)
     if os.path.exists(src):
         shutil.copy(src, os.path.join(PROF, "%s_%s" % (tag, name)))

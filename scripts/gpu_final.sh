@@ -15,6 +15,9 @@ timeout 600 python bench.py --workload c5 --train-precision fp32 --train-dense l
 timeout 300 python scripts/microbench_l0.py > gpurun_out/microbench_l0.log 2>&1; tail -3 gpurun_out/microbench_l0.log | cut -c1-200
 timeout 600 python scripts/trace_train.py 2>&1 | grep -v Warning | tail -48 | cut -c1-150 > gpurun_out/trace_train.txt
 timeout 300 python scripts/cg_time.py --header > gpurun_out/cg_time.txt 2>&1; cat gpurun_out/cg_time.txt
+CG_TIME_SMALL=1 timeout 300 python scripts/cg_time.py --header > gpurun_out/cg_time_small.txt 2>&1
+timeout 600 python scripts/trace_forward.py > gpurun_out/trace.log 2>&1
+python scripts/trace_iteration.py > gpurun_out/trace_iteration.txt 2>&1; head -9 gpurun_out/trace_iteration.txt
 python - <<'PY'
 import json
 for f in ("bench", "bench_c3", "bench_c4", "bench_c5", "bench_c5_library", "bench_c5_fp32", "bench_c5_fp32_library"):

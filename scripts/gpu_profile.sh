@@ -11,8 +11,8 @@ CAMLI_PROFILER_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__t
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-training-block --concurrent 1 > gpurun_out/ncu_bench.log 2>&1
 wc -l gpurun_out/launches.csv
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'corr2d_lookup_kernel|dw_gather_max|knn_warp_kernel|allpairs_tf32x3_kernel|corr3d_lookup_kernel|conv_gemm_tf32x3_kernel|conv_wgrad_tf32x3_kernel|transpose_split_kernel|fps_cluster_async|pointconv_group_kernel|sk_|clfm_interp' \
-    -c 60 -f -o /tmp/prof_kernels python scripts/profile_kernels.py --iters 1 > gpurun_out/ncu_kernels.log 2>&1
+    -k regex:'corr2d_lookup_kernel|dw_gather_max|knn_warp_kernel|allpairs_tf32x3_kernel|corr3d_lookup_kernel|conv_gemm_tf32x3_kernel|conv_wgrad_tf32x3_kernel|transpose_split_kernel|fps_cluster_async|fps_pruned|convex_upsample|pointconv_group|sk_|clfm_interp' \
+    -c 70 -f -o /tmp/prof_kernels python scripts/profile_kernels.py --iters 1 > gpurun_out/ncu_kernels.log 2>&1
 ncu -i /tmp/prof_kernels.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw.csv 2>/dev/null
 ncu -i /tmp/prof_kernels.ncu-rep --page details --csv > gpurun_out/prof_kernels_details.csv 2>/dev/null
 for k in corr2d_lookup_kernel dw_gather_max_kernel conv_gemm_tf32x3_kernel; do

@@ -35,6 +35,8 @@ def main():
     feat = torch.randn(1, N, 128, generator=g).to(dev)
     wn = MLP2d(3, [8, 32, 128], act="relu").to(dev)
     flow = (torch.randn(1, 3, N, generator=g) * 0.1).to(dev)
+    up_flow = torch.randn(1, 2, H, W, generator=g).to(dev)
+    up_mask = torch.randn(1, 576, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
 
     with torch.no_grad():
         pyr = ops.corr2d_build(f1, f2, 4)
@@ -50,6 +52,7 @@ def main():
             "knn_2048x2048_k16": lambda: k_nearest_neighbor(xyz, xyz, 16),
             "backwarp_3d_2048": lambda: ops.backwarp_3d(xyz, xyz, flow, 3),
             "fps_2x8192_s4096": lambda: furthest_point_sampling(pc, 4096),
+            "convex_upsample_x8_68x120": lambda: ops.convex_upsample(up_flow, up_mask, 8, 0.25),
         }
         # tensor-core linear / convolution kernel at the shapes of the model (B, H, W, Cin, Cout, kh, kw)
         for (cb, ch, cw, ci, co, kh, kw) in [(1, 1, 2048, 384, 128, 1, 1), (1, 1, 2048, 128, 128, 1, 1),

@@ -111,6 +111,8 @@ ENTRY_POINTS = {          # ncu kernel name prefix -> C-ABI entry point (the key
     "conv_wgrad_tf32x3_kernel": "camli_conv_wgrad",
     "allpairs_tf32x3_kernel": "camli_allpairs_correlation",
     "fps_cluster_async_kernel": "camli_furthest_point_sampling",
+    "fps_pruned_kernel": "camli_furthest_point_sampling",
+    "convex_upsample_kernel": "camli_convex_upsample",
     "corr3d_lookup_kernel": "camli_corr3d_lookup",
 }
 
