@@ -523,8 +523,8 @@ def run_ours(args, rank, world, local_rank):
                    "intermediate_predictions": False},
         # batch-1 latency (BASELINE config 2 is batch 1): one CUDA graph at a time
         "latency": {"ms_per_pair": ms_lat / n_lat / B, "pairs_per_s": B * world * n_lat / (ms_lat / 1e3), "pairs_timed": n_lat * B,
-                    "note": "one CUDA graph at a time (tile policy 'latency': 64-wide tiles on the layers that would leave half of "
-                            "the SMs idle), device-timed per pair, L2 flushed before each"},
+                    "note": "one CUDA graph at a time (tile policy 'latency': the narrowest tile that keeps a layer within one wave "
+                            "of CTAs), device-timed per pair, L2 flushed before each"},
         "e2e": {"value": all_pairs / (ms_e2e / 1e3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d * R, "d2h_bytes_per_step": d2h * R, "mode": e2e_mode, "engines_in_flight": n_eng,
                 "single_engine_pipelined": {"value": all_pairs / (ms_pipe / 1e3), "unit": "pairs/s",
