@@ -389,6 +389,8 @@ extern "C" int camli_transpose_split(const float* rows, int64_t ld, int64_t P, i
 extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const float* x_hi_t, const float* x_lo_t,
                                 int B, int H, int W, int Cout, int Cin, int kh, int kw, int dilation, int stride, int Hin,
                                 int passes, float* dw, void* stream) {
+    const bool accumulate = (passes & CAMLI_WGRAD_ACCUMULATE) != 0;                 // dw += ... (the caller's gradient buffer)
+    passes &= ~CAMLI_WGRAD_ACCUMULATE;
     const bool bf16 = passes == CAMLI_WGRAD_BF16;
     if (bf16) passes = 1;
     if (passes != 1 && passes != 3) return CAMLI_EINVAL;
@@ -433,8 +435,10 @@ extern "C" int camli_conv_wgrad(const float* g_hi_t, const float* g_lo_t, const 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(dw, 0, (size_t)Cout * P.ldw * sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
+    if (!accumulate) {
+        e = cudaMemsetAsync(dw, 0, (size_t)Cout * P.ldw * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
     const int grid = (int)(total < n_sms ? total : n_sms);
     conv_wgrad_tf32x3_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(m_ghi, m_glo, m_xhi, m_xlo, P);
     CAMLI_RETURN_LAUNCH_STATUS();

@@ -207,6 +207,43 @@ def recompute(kernel, formula, *args):
 
 # --------------------------------------------------------------------------------------- dense layers
 BF16_WGRAD = True  # under autocast (passes = 1): bf16 operands in the weight-gradient GEMM (A/B switch)
+# Weight gradients of 1x1 layers added straight into the parameter's own .grad (the trainer's flat buffer) by the
+# weight-gradient kernel -- its epilogue is an atomic add anyway -- instead of a zero-fill, a fresh tensor and autograd's
+# AccumulateGrad add per use (a recurrent update block uses every weight once per refinement iteration).  Only inside
+# fused_wgrad_accumulation(): torch.autograd.grad(...) and plain .backward() callers keep the functional behaviour.
+# Measured on the C5 step (bench.py --workload c5, CAMLI_FUSE_WGRAD=1 / 0): 37 of 177 weight-gradient launches qualify
+# (leaf 1x1 weights), the gradients agree to 3e-8, and the step gets SLOWER (97.5 -> 101.3 ms): the trainer leaves it off.
+_FUSE_WGRAD = False
+
+
+class fused_wgrad_accumulation:
+    """with grad.fused_wgrad_accumulation(): loss.backward() -- parameters must have contiguous fp32 .grad buffers already."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global _FUSE_WGRAD
+        self.prev, _FUSE_WGRAD = _FUSE_WGRAD, self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        global _FUSE_WGRAD
+        _FUSE_WGRAD = self.prev
+        return False
+
+
+def _grad_slot(weight, O, K):
+    """The [O, K] view of the leaf parameter's gradient buffer this 4-D weight (or 4-D view of a Linear / Conv1d weight)
+    accumulates into, or None when the fused accumulation does not apply."""
+    if not _FUSE_WGRAD:
+        return None
+    leaf = weight._base if weight._base is not None else weight
+    g = leaf.grad
+    if (not leaf.is_leaf or g is None or g.dtype != torch.float32 or leaf.dtype != torch.float32 or not g.is_contiguous()
+            or g.numel() != O * K or g.data_ptr() % 16):
+        return None
+    return g.view(O, K)
 _DENSE_W = {}      # (data_ptr, version, shape, flipped) -> (weak ref, hi, lo): lives for ONE training step (clear_dense_cache)
 
 
@@ -291,7 +328,8 @@ class DenseFn(torch.autograd.Function):
         if need_w:
             x_hi, x_lo, _, _ = ops.transpose_split(x_rows, n_shift=kw, shift_step=ctx.dilation, want_lo=not fast, xstride=st,
                                                    bf16=wg_bf16)
+            slot = _grad_slot(weight, O, Cin) if kh == 1 and kw == 1 else None      # (OHWI = OIHW only for a 1x1 window)
             dw2d = ops.conv_wgrad((g_hi, g_lo), (x_hi, x_lo), B, H, W, O, Cin, kh, kw, ctx.dilation, 16 if wg_bf16 else ctx.passes,
-                                  st, Hin)
-            dw = dw2d.view(O, kh, kw, Cin).permute(0, 3, 1, 2).to(weight.dtype)
+                                  st, Hin, accumulate_into=slot)
+            dw = None if slot is not None else dw2d.view(O, kh, kw, Cin).permute(0, 3, 1, 2).to(weight.dtype)
         return dx, dw, (db.to(weight.dtype) if need_b else None), None, None, None, None, None

@@ -492,11 +492,18 @@ def transpose_split(rows, y=None, act=None, slope=0.1, want_rows=False, want_col
     return hi_t, lo_t, g_rows, colsum
 
 
-def conv_wgrad(g_t, x_t, B, H, W, Cout, Cin, kh, kw, dilation=1, passes=3, stride=1, Hin=None):
+def conv_wgrad(g_t, x_t, B, H, W, Cout, Cin, kh, kw, dilation=1, passes=3, stride=1, Hin=None, accumulate_into=None):
     """dW [Cout, kh*kw*Cin] (OHWI) of the stride-1 "same" convolution from the transposed hi / lo operand pairs of
     transpose_split (camli_conv_wgrad: 3xTF32 on tcgen05, K split over the SMs; passes = 1: one tf32 product, lo parts unused).
-    H, W: the OUTPUT grid (= the grid of g); stride 2: Hin input rows, x_t prepared with xstride = 2."""
-    dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=g_t[0].device)
+    H, W: the OUTPUT grid (= the grid of g); stride 2: Hin input rows, x_t prepared with xstride = 2.
+    accumulate_into: a contiguous fp32 [Cout, kh*kw*Cin] buffer the result is ADDED to (CAMLI_WGRAD_ACCUMULATE) and returned."""
+    if accumulate_into is None:
+        dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=g_t[0].device)
+    else:
+        dw = accumulate_into
+        if tuple(dw.shape) != (Cout, kh * kw * Cin) or not dw.is_contiguous() or dw.dtype != torch.float32 or dw.data_ptr() % 16:
+            raise RuntimeError("conv_wgrad: accumulate_into must be a 16-byte aligned contiguous fp32 [Cout, kh*kw*Cin] buffer")
+        passes |= 0x100
     with torch.cuda.device(dw.device):
         native.call("camli_conv_wgrad", ptr(g_t[0]), ptr(g_t[1]), ptr(x_t[0]), ptr(x_t[1]), i32(B), i32(H), i32(W), i32(Cout),
                     i32(Cin), i32(kh), i32(kw), i32(dilation), i32(stride), i32(H if Hin is None else Hin), i32(passes), ptr(dw), stream(),

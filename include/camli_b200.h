@@ -364,6 +364,8 @@ int camli_gru_update(int64_t n, const float* z, const float* h, const float* q, 
 #define CAMLI_CONV_SINGLE_PASS   0x100   /* flag in the tile_n argument of camli_conv_gemm* (see there) */
 #define CAMLI_WGRAD_BF16          16      /* `passes` value of camli_conv_wgrad: bf16 operands (written by camli_transpose_split with  */
 #define CAMLI_TRANSPOSE_BF16      0x100   /* xstride | CAMLI_TRANSPOSE_BF16), one kind::f16 product, fp32 accumulation; W % 8 == 0      */
+#define CAMLI_WGRAD_ACCUMULATE    0x100   /* flag in `passes` of camli_conv_wgrad: dw is NOT zeroed, the result is added to it (gradient   */
+                                          /* accumulation into the parameter's own buffer: no zero-fill, no separate add kernel)            */
 
 /* x -> (hi, lo) with hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand split of the 3xTF32
  * tensor-core kernels; used once per weight tensor. */

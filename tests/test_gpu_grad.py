@@ -461,6 +461,52 @@ def test_captured_train_step_matches_eager(dev):
         assert abs(a - b) <= 2e-4 * abs(b), (out[True], out[False])
 
 
+def test_fused_wgrad_accumulation_matches_autograd(dev):
+    """grad.fused_wgrad_accumulation (the captured training step's backward): the weight-gradient kernel of every 1x1 layer
+    adds straight into the parameter's slice of the flat gradient buffer (CAMLI_WGRAD_ACCUMULATE) instead of returning a
+    tensor to autograd's AccumulateGrad -- same gradients (float atomics: 1e-5 of the buffer's norm), and it is really taken."""
+    from camliflow_b200 import grad, ops, trainer
+    from camliflow_b200.camliraft import CamLiRAFT
+    from camliflow_b200.config import camliraft_config
+    from camliflow_b200.init import seed_module_
+    from oracle import camliraft_oracle as co
+    from tests.test_train_golden import train_targets
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, H, W, N = 1, 128, 160, 8192
+    inputs = dict(co.synthetic_inputs(B, H, W, N, 41), **train_targets(B, H, W, N, 42))
+    inputs = {k: v.to(dev) for k, v in inputs.items()}
+    model = seed_module_(CamLiRAFT(camliraft_config(n_iters_train=2)), seed=0).to(dev).train()
+    model.track_metrics = False
+    flat = trainer.flatten_gradients(model)
+    taken = []
+    real = ops.conv_wgrad
+
+    def counting(*a, **kw):
+        taken.append(kw.get("accumulate_into") is not None)
+        return real(*a, **kw)
+
+    def run(fused):
+        flat.zero_()
+        grad.clear_dense_cache()
+        model(inputs)
+        with grad.fused_wgrad_accumulation(fused):
+            model.loss.backward()
+        return flat.clone()
+
+    ops.conv_wgrad = counting
+    try:
+        plain = run(False)
+        n_plain = sum(taken)
+        fused = run(True)
+    finally:
+        ops.conv_wgrad = real
+    assert n_plain == 0 and sum(taken) > 20, (n_plain, sum(taken), len(taken))
+    err = (fused - plain).norm().item() / plain.norm().item()
+    print("fused weight-gradient accumulation: %d of %d launches in place, relative difference %.2e" % (sum(taken), len(taken) // 2, err))
+    assert err <= 1e-5
+
+
 @pytest.mark.parametrize("B,H,W,s,scale", [(1, 68, 120, 8, 0.25), (2, 17, 23, 8, 0.25), (2, 33, 60, 4, 1.0), (1, 5, 3, 4, 1.0)])
 def test_convex_upsample_forward_backward(dev, B, H, W, s, scale):
     """camli_convex_upsample{,_backward} against the reference formula (oracle.convex_upsample = models/utils.py:191-204)
