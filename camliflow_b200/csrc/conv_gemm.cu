@@ -60,11 +60,11 @@ constexpr int CG_CHUNK = 2;                       // k-blocks (of 32 channels) a
 
 template <int BN> struct CgCfg {
     static constexpr int kStageBytes = 2 * CG_A_BYTES + 2 * BN * CG_BK * 4;
-    static constexpr int kStages = (BN >= 128) ? 3 : 4;
+    static constexpr int kStages = (BN >= 96) ? 3 : 4;
     static constexpr int kEpiWarps = BN >= 64 ? 8 : 4;
     static constexpr int kPadFloats = 16 * 36;    // one 16-row x 32-column transpose pad per epilogue warp (row pitch 36 floats)
     static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiWarps * kPadFloats * 4;
-    static constexpr int kTmemCols = 4 * BN;      // two [main | correction] accumulator buffers (ping-pong per chunk)
+    static constexpr int kTmemCols = BN == 96 ? 512 : 4 * BN;      // two [main | correction] accumulator buffers (ping-pong per chunk); power of two
 };
 
 struct CgParams {
@@ -207,11 +207,12 @@ __device__ __forceinline__ void cg_store_block(const CgBlock& k, int lane) {
 
 // A warp's whole 32-row x CW-column share of a tile: per 32-column group and 16-row half, registers -> pad -> rows.
 template <int ACT, int CW>
-__device__ __forceinline__ void cg_store_tile(float (&sum)[CW], const CgParams& P, uint32_t pad, int mypix, int n0, int lane) {
+__device__ __forceinline__ void cg_store_tile(float (&sum)[CW], const CgParams& P, uint32_t pad, int mypix, int n0, int lane,
+                                              int ncols) {                      // ncols <= CW: columns this warp really owns
 #pragma unroll
     for (int c = 0; c < CW / 32; ++c) {
         const int col0 = n0 + c * 32;
-        if (col0 >= P.Cout) break;                                              // (warp-uniform)
+        if (col0 >= P.Cout || c * 32 >= ncols) break;                           // (warp-uniform)
         const int col = col0 + (lane & 7) * 4;                                  // this lane's four columns (read side)
         // destination and side inputs of this 32-column group (split is a multiple of 32: a group never straddles it)
         const bool hi_part = ACT == CAMLI_ACT_GRU_GATE && col0 >= P.split;
@@ -264,7 +265,8 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     // epilogue: two warps per TMEM lane quarter, each owning half of the accumulator columns (a 32-column
     // tile is not worth splitting: only the first group of four warps works then)
     constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
-    constexpr int CW = BN >= 64 ? BN / 2 : BN;        // columns per epilogue warp
+    // columns per epilogue warp (a 96-column tile splits 64 | 32: the register blocks are 32 columns wide)
+    constexpr int CW = BN == 96 ? 64 : (BN >= 64 ? BN / 2 : BN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
@@ -416,6 +418,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int q = warp & 3;                                         // TMEM lane quarter of this warp
         const int half = (warp - 6) >> 2;                               // which half of the columns
         if (half * CW >= BN) goto done;                                 // (second group idle for 32-column tiles)
+        const int ncols = min(CW, BN - half * CW);                      // (32 for the second group of a 96-column tile)
         const int row = q * 32 + lane;                                  // accumulator row = pixel of the tile
         const int ty = row / P.tw, tx = row - ty * P.tw;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + half * CW;
@@ -438,6 +441,7 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 if (warp == 6 && lane == 0 && tile == blockIdx.x && kb0 < 32) CG_STAMP(80 + kb0 / CG_CHUNK);
 #pragma unroll
                 for (int c = 0; c < CW / 32; ++c) {
+                    if (c * 32 >= ncols) break;                          // (warp-uniform)
                     float v[32];
                     if (P.passes != 1) {
                         tmem_ld32(lane_base + acc * 2 * BN + BN + c * 32, v);       // corrections first (small)
@@ -459,17 +463,17 @@ conv_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             const int mypix = (x < P.W && y < P.H) ? (b * P.H + y) * P.W + x : -1;       // pixel of this lane's row
             switch (P.act) {
                 case CAMLI_ACT_RELU | CAMLI_ACT_FIX_NONFINITE:
-                    cg_store_tile<CAMLI_ACT_RELU | CAMLI_ACT_FIX_NONFINITE, CW>(sum, P, pad, mypix, n0, lane); break;
+                    cg_store_tile<CAMLI_ACT_RELU | CAMLI_ACT_FIX_NONFINITE, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
                 case CAMLI_ACT_NONE | CAMLI_ACT_FIX_NONFINITE:
-                    cg_store_tile<CAMLI_ACT_NONE | CAMLI_ACT_FIX_NONFINITE, CW>(sum, P, pad, mypix, n0, lane); break;
-                case CAMLI_ACT_RELU: cg_store_tile<CAMLI_ACT_RELU, CW>(sum, P, pad, mypix, n0, lane); break;
-                case CAMLI_ACT_LEAKY: cg_store_tile<CAMLI_ACT_LEAKY, CW>(sum, P, pad, mypix, n0, lane); break;
-                case CAMLI_ACT_TANH: cg_store_tile<CAMLI_ACT_TANH, CW>(sum, P, pad, mypix, n0, lane); break;
-                case CAMLI_ACT_SIGMOID: cg_store_tile<CAMLI_ACT_SIGMOID, CW>(sum, P, pad, mypix, n0, lane); break;
-                case CAMLI_ACT_GRU_GATE: cg_store_tile<CAMLI_ACT_GRU_GATE, CW>(sum, P, pad, mypix, n0, lane); break;
-                case CAMLI_ACT_GRU_UPDATE: cg_store_tile<CAMLI_ACT_GRU_UPDATE, CW>(sum, P, pad, mypix, n0, lane); break;
-                case CAMLI_ACT_GRU_UPDATE_FIX: cg_store_tile<CAMLI_ACT_GRU_UPDATE_FIX, CW>(sum, P, pad, mypix, n0, lane); break;
-                default: cg_store_tile<CAMLI_ACT_NONE, CW>(sum, P, pad, mypix, n0, lane); break;
+                    cg_store_tile<CAMLI_ACT_NONE | CAMLI_ACT_FIX_NONFINITE, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                case CAMLI_ACT_RELU: cg_store_tile<CAMLI_ACT_RELU, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                case CAMLI_ACT_LEAKY: cg_store_tile<CAMLI_ACT_LEAKY, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                case CAMLI_ACT_TANH: cg_store_tile<CAMLI_ACT_TANH, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                case CAMLI_ACT_SIGMOID: cg_store_tile<CAMLI_ACT_SIGMOID, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                case CAMLI_ACT_GRU_GATE: cg_store_tile<CAMLI_ACT_GRU_GATE, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                case CAMLI_ACT_GRU_UPDATE: cg_store_tile<CAMLI_ACT_GRU_UPDATE, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                case CAMLI_ACT_GRU_UPDATE_FIX: cg_store_tile<CAMLI_ACT_GRU_UPDATE_FIX, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
+                default: cg_store_tile<CAMLI_ACT_NONE, CW>(sum, P, pad, mypix, n0, lane, ncols); break;
             }
             if (warp == 6 && lane == 0 && tile == blockIdx.x) CG_STAMP(10);
         }
@@ -618,8 +622,10 @@ extern "C" int camli_conv_gemm_strided(const float* x, int B, int Hin, int Win, 
     // C_out <= 128 convolutions of the update block occupy 68 SMs instead of 136, a point-branch linear 16 instead of 64.
     P.passes = (tile_n & CAMLI_CONV_SINGLE_PASS) ? 1 : 3;
     int bn = tile_n & 0xff;
-    if (bn == 0) bn = Cout > 64 ? 128 : (Cout > 32 ? 64 : 32);
-    if (bn != 32 && bn != 64 && bn != 128) return CAMLI_EINVAL;
+    // (96-column tiles for the 96 / 192 / 288-channel layers -- the motion encoder's 3x3 256 -> 192, PWC's pyramid and
+    // estimator levels: with 128-wide tiles a quarter of their MMA columns would be padding)
+    if (bn == 0) bn = Cout > 64 ? ((Cout % 96 == 0 && Cout % 128 != 0) ? 96 : 128) : (Cout > 32 ? 64 : 32);
+    if (bn != 32 && bn != 64 && bn != 96 && bn != 128) return CAMLI_EINVAL;
     P.tiles_n = camli_div_up(Cout, bn);
     P.bias = bias; P.residual = residual; P.ldr = ldr; P.out = out; P.ldo = ldo; P.act = act; P.slope = slope; P.timeline = camli_cg_timeline;
     P.aux1 = aux1; P.ld1 = ld1; P.aux2 = aux2; P.ld2 = ld2; P.split = split; P.out2 = out2; P.ldo2 = ldo2;
@@ -648,6 +654,7 @@ extern "C" int camli_conv_gemm_strided(const float* x, int B, int Hin, int Win, 
     switch (bn) {
         case 32: return launch_conv_gemm<32>(mx, mwh, mwl, P, (int)total, st);
         case 64: return launch_conv_gemm<64>(mx, mwh, mwl, P, (int)total, st);
+        case 96: return launch_conv_gemm<96>(mx, mwh, mwl, P, (int)total, st);
         default: return launch_conv_gemm<128>(mx, mwh, mwl, P, (int)total, st);
     }
 }

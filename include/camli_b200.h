@@ -382,7 +382,7 @@ int camli_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stre
  * w_hi/lo  [Cout, kh*kw*Cin] f32 = camli_split_tf32 of the OHWI (channels_last) weight; kh, kw odd.
  * bias     [Cout] or NULL; residual [B*H*W, ldr] or NULL; act = CAMLI_ACT_*.
  * out      [B*H*W, ldo] f32: ldo >= Cout lets the layer write a channel slice of a wider tensor.
- * tile_n   0 = automatic; else 32 / 64 / 128 (accumulator tile width).  | CAMLI_CONV_SINGLE_PASS: ONE tf32 product per
+ * tile_n   0 = automatic; else 32 / 64 / 96 / 128 (accumulator tile width; automatic = the widest that Cout fills, 96 for Cout % 96 == 0).  | CAMLI_CONV_SINGLE_PASS: ONE tf32 product per
  *          element instead of three (operands cut to 10-bit mantissas, fp32 accumulation) -- the reduced-precision mode the
  *          training step uses under bf16 autocast (a tf32 operand is more accurate than a bf16 one); parity paths never set it.
  */

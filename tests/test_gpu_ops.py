@@ -285,6 +285,11 @@ CONV_GEMM_CASES = [
     (1, 17, 23, 8, 40, 7, 7, "sigmoid", False, 32),          # Cin below one k-block, wide window
     (1, 136, 240, 64, 256, 1, 1, "relu", True, 128),         # encoder 1x1, widest accumulator tile
     (1, 20, 36, 128, 256, 3, 3, None, False, 128),
+    # 96-column tiles (the automatic width of 96 / 192 / 288-channel layers): 64 | 32 column split of the epilogue warps
+    (1, 68, 120, 256, 192, 3, 3, "relu", True, 96),
+    (2, 30, 44, 64, 288, 1, 1, "leaky_relu", False, 0),
+    (1, 17, 23, 40, 100, 3, 3, "tanh", True, 96),           # ragged: a 96-column tile and one with 4 live columns
+    (1, 1, 300, 128, 96, 1, 1, None, False, 0),
 ]
 
 
