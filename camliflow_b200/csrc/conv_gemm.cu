@@ -616,9 +616,10 @@ extern "C" int camli_conv_gemm_strided(const float* x, int B, int Hin, int Win, 
     }
     P.th = best_th; P.tw = CG_BM / best_th;
     P.tiles_y = camli_div_up(H, P.th); P.tiles_x = camli_div_up(W, P.tw);
-    // N tile: the widest tile that Cout fills.  A tf32 MMA instruction costs the same ~140 cycles whatever its N
-    // (measured, M = 128), so a narrow tile does not shorten a CTA's k-loop -- it only multiplies the CTAs (and the
-    // activation splits).  Few, wide CTAs also leave SMs free for the kernels of the other branch's stream: the
+    // N tile: the widest tile that Cout fills.  Inside this kernel a k-step costs ~280 cycles at BN = 128 and hardly less
+    // at BN = 64 / 32 (the issue micro-benchmark, scripts/probes/mma_probe.cu, gives 120 / 61 / 47 / 45 cycles per
+    // instruction for N = 256 / 128 / 64 / 32: the floor of a narrow instruction plus the per-k-block costs of the pipeline
+    // dominate), so a narrow tile does not shorten a CTA's k-loop much -- it multiplies the CTAs (and the activation splits).  Few, wide CTAs also leave SMs free for the kernels of the other branch's stream: the
     // C_out <= 128 convolutions of the update block occupy 68 SMs instead of 136, a point-branch linear 16 instead of 64.
     P.passes = (tile_n & CAMLI_CONV_SINGLE_PASS) ? 1 : 3;
     int bn = tile_n & 0xff;
