@@ -112,7 +112,8 @@ class CamLiRAFT_Core(nn.Module):
         # iteration i+1 depend on flow_3d alone, and the point branch finishes an iteration well before the image branch
         # (ConvGRU + flow head); issued right behind the point update they are done when the image chain comes round,
         # instead of standing in front of the correlation fusion (~60 us of every iteration).
-        ahead = par.enabled and not cfgs.fuse_hidden and os.environ.get("CAMLI_PIPELINE_3D", "1") != "0"
+        pipe = os.environ.get("CAMLI_PIPELINE_3D", "1")       # "0": program order; "force": also without streams (host tests)
+        ahead = (par.enabled or pipe == "force") and not cfgs.fuse_hidden and pipe != "0"
         corr_3d_next = None
         for it in range(n_iters):
             if it > 0:

@@ -42,6 +42,20 @@ def test_product_graph_matches_reference_golden_small():
     assert e2 <= 1e-3 and e3 <= 1e-4, (e2, e3)
 
 
+def test_pipelined_point_branch_is_the_same_computation(monkeypatch):
+    """The software-pipelined schedule of the recurrent core (the point branch's back-warp + correlation lookup of
+    iteration i+1 issued behind the point update of iteration i) only moves launches: bit-identical flows."""
+    inputs = co.synthetic_inputs(1, 160, 224, 8192, seed=11)
+    outs = {}
+    for mode in ("0", "force"):
+        monkeypatch.setenv("CAMLI_PIPELINE_3D", mode)
+        with cpu_kernels(), torch.no_grad():
+            outs[mode] = _model(3)(inputs)
+    assert bool(torch.isfinite(outs["0"]["flow_3d"]).all())
+    assert torch.equal(outs["0"]["flow_2d"], outs["force"]["flow_2d"])
+    assert torch.equal(outs["0"]["flow_3d"], outs["force"]["flow_3d"])
+
+
 def test_module_surface_matches_rows_fast_path():
     """PointConvDW / CLFM public (channel-first) calls equal their channel-last fast paths."""
     from camliflow_b200 import ops

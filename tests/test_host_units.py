@@ -121,3 +121,50 @@ def test_losses_match_reference_formulas():
     assert torch.allclose(calc_sequence_loss_3d(p3, t3, AttrDict(gamma=0.8, order="l2-norm")), want)
     with pytest.raises(ValueError):
         calc_sequence_loss_3d(p3, t3, AttrDict(gamma=0.8, order="nope"))
+
+
+def test_latency_tile_policy_keeps_a_layer_within_one_wave():
+    """ops._latency_tile: the narrowest of 32 / 64 / 128 output columns with m_tiles * n_tiles <= 148 CTAs; 0 (= the library's
+    automatic width, which also knows the 96-column tile) when the widest tile is the answer or nothing fits."""
+    from camliflow_b200 import ops
+    assert ops._latency_tile(1, 1, 2048, 128) == 32          # 16 pixel tiles x 4
+    assert ops._latency_tile(1, 68, 120, 128) == 64          # 68 x 2 = 136 (32 columns would need two waves)
+    assert ops._latency_tile(1, 68, 120, 256) == 0           # 68 x 2 at 128 columns: the automatic width
+    assert ops._latency_tile(1, 68, 120, 192) == 0           # -> two 96-column tiles inside the library
+    assert ops._latency_tile(1, 68, 120, 324) == 0           # more than one wave at every width
+    assert ops._latency_tile(4, 68, 120, 128) == 0           # four pairs per forward fill the GPU anyway
+    assert ops._latency_tile(1, 1, 2048, 16) == 0            # one 32-column tile is the widest there is
+    assert ops._latency_tile(1, 17, 30, 64) == 32
+
+
+def test_fork_join_helper_runs_inline_without_streams():
+    """camliraft_core._TwoStreams with streams disabled (CPU, training): run() and fork() execute in program order and
+    hand the results through."""
+    from camliflow_b200.camliraft_core import _Joined, _TwoStreams
+    order = []
+    par = _TwoStreams(False)
+    a, b = par.run(lambda: order.append("main") or 1, lambda: order.append("side") or 2)
+    h = par.fork(lambda: order.append("fork") or 3)
+    assert (a, b, h.join(), h.join()) == (1, 2, 3, 3) and order == ["main", "side", "fork"]
+    assert isinstance(h, _Joined) and h.stream is None
+
+
+def test_fused_wgrad_accumulation_context_is_scoped_and_declines_without_buffers():
+    """grad.fused_wgrad_accumulation only applies inside the context and only to leaf fp32 parameters that already own a
+    contiguous, 16-byte aligned gradient buffer of the right size."""
+    from camliflow_b200 import grad
+    w = torch.nn.Parameter(torch.randn(8, 4, 1, 1))
+    assert grad._grad_slot(w, 8, 4) is None                              # outside the context
+    with grad.fused_wgrad_accumulation():
+        assert grad._grad_slot(w, 8, 4) is None                          # no .grad yet
+        w.grad = torch.zeros_like(w)
+        slot = grad._grad_slot(w, 8, 4)
+        assert slot is not None and slot.shape == (8, 4) and slot.data_ptr() == w.grad.data_ptr()
+        lin = torch.nn.Parameter(torch.randn(8, 4))
+        lin.grad = torch.zeros_like(lin)
+        assert grad._grad_slot(lin[:, :, None, None], 8, 4).data_ptr() == lin.grad.data_ptr()    # a Linear weight seen as 4-D
+        assert grad._grad_slot(w * 2.0, 8, 4) is None                    # not a leaf (e.g. a folded BatchNorm)
+        with grad.fused_wgrad_accumulation(False):
+            assert grad._grad_slot(w, 8, 4) is None
+        assert grad._grad_slot(w, 8, 4) is not None
+    assert grad._grad_slot(w, 8, 4) is None
