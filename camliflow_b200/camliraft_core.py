@@ -48,8 +48,25 @@ class CamLiRAFT_Core(nn.Module):
             f12 = b2.fnet(torch.cat([image1, image2], dim=0))
             return f12[:image1.shape[0]], f12[image1.shape[0]:], b2.cnet(image1)
 
+        fh, fw = image1.shape[-2] // 8, image1.shape[-1] // 8        # the 1/8 feature grid of the image encoders
+
+        def geometry(xyz1, xyz2):
+            """Everything that depends on the point COORDINATES only: projected positions on the feature grid, the pixel ->
+            nearest projected point tables of CLFM (computed once per cloud; the reference repeats the search at every
+            fusion site and iteration) and the k = 32 self-neighbour table of the update block."""
+            sh, sw = camera_info["sensor_h"], camera_info["sensor_w"]
+            sx, sy = (fw - 1) / (sw - 1), (fh - 1) / (sh - 1)
+            uv1, uv2 = project_pc2image(xyz1, camera_info), project_pc2image(xyz2, camera_info)
+            uv1 = torch.stack([uv1[:, 0] * sx, uv1[:, 1] * sy], dim=1)
+            uv2 = torch.stack([uv2[:, 0] * sx, uv2[:, 1] * sy], dim=1)
+            nn1 = ops.nearest_point_2d(uv1, fh, fw)
+            nn2 = ops.nearest_point_2d(uv2, fh, fw) if cfgs.fuse_fnet else None
+            return uv1, uv2, nn1, nn2, k_nearest_neighbor(xyz1, xyz1, k=32)
+
         def encode_3d():
             xyzs1, xyzs2, _, _ = build_pc_pyramid(pc1, pc2, [4096, 2048, 1024, 512, 256])
+            # (forked as soon as the pyramid exists: ~110 us of searches and glue beside the encoders instead of behind them)
+            geo = par.fork(lambda: geometry(xyzs1[2], xyzs2[2]), "geo")
             B = pc1.shape[0]
             # neighbour tables depend on the geometry only: ONE search per level for both clouds, shared by the feature
             # and the context encoder of frame 1 (the reference searches again in each of the 3 encoder passes)
@@ -62,42 +79,48 @@ class CamLiRAFT_Core(nn.Module):
                 feats = f12[:B], f12[B:], b3.cnet(xyzs1[:3], t1)[2]
             else:
                 feats = b3.fnet(xyzs1[:3], t1)[2], b3.fnet(xyzs2[:3], [t[B:] for t in tables])[2], b3.cnet(xyzs1[:3], t1)[2]
-            return xyzs1, xyzs2, [ops.rows_of(f) for f in feats]      # channel-last point features from here on
+            return xyzs1, xyzs2, [ops.rows_of(f) for f in feats], geo      # channel-last point features from here on
 
-        (feat1_2d, feat2_2d, featc_2d), (xyzs1, xyzs2, (feat1_3d, feat2_3d, featc_3d)) = par.run(encode_2d, encode_3d)
+        (feat1_2d, feat2_2d, featc_2d), (xyzs1, xyzs2, (feat1_3d, feat2_3d, featc_3d), geo) = par.run(encode_2d, encode_3d)
 
         xyzs1, xyzs2 = xyzs1[2:], xyzs2[2:]        # working pyramid 2048 / 1024 / 512 / 256
         xyz1, xyz2 = xyzs1[0], xyzs2[0]
+        assert tuple(feat1_2d.shape[-2:]) == (fh, fw), (tuple(feat1_2d.shape), fh, fw)
+        uv1, uv2, nn1, nn2, nbr = geo.join()
 
-        # projected point positions on the 1/8 feature grid
-        sh, sw = camera_info["sensor_h"], camera_info["sensor_w"]
-        fh, fw = feat1_2d.shape[-2:]
-        sx, sy = (fw - 1) / (sw - 1), (fh - 1) / (sh - 1)
-        uv1, uv2 = project_pc2image(xyz1, camera_info), project_pc2image(xyz2, camera_info)
-        uv1 = torch.stack([uv1[:, 0] * sx, uv1[:, 1] * sy], dim=1)
-        uv2 = torch.stack([uv2[:, 0] * sx, uv2[:, 1] * sy], dim=1)
-
-        # pixel -> nearest projected point tables, computed once per cloud (the reference repeats the
-        # search at every fusion site and iteration)
-        nn1 = ops.nearest_point_2d(uv1, fh, fw)
+        # The fusion sites in front of the loop (frame 1, frame 2, context) are independent of each other: the second and
+        # third run on streams of their own beside the first (each a chain of ~10 short kernels)
+        site_2 = site_c = None
         if cfgs.fuse_fnet:
-            nn2 = ops.nearest_point_2d(uv2, fh, fw)
-            feat1_2d, feat1_3d = self.clfm_fnet.forward_rows(uv1, feat1_2d, feat1_3d, nn1, par)
-            feat2_2d, feat2_3d = self.clfm_fnet.forward_rows(uv2, feat2_2d, feat2_3d, nn2, par)
+            site_2 = par.fork(lambda: self.clfm_fnet.forward_rows(uv2, feat2_2d, feat2_3d, nn2), "site2")
         if cfgs.fuse_cnet:
-            featc_2d, featc_3d = self.clfm_cnet.forward_rows(uv1, featc_2d, featc_3d, nn1, par)
+            site_c = par.fork(lambda: self.clfm_cnet.forward_rows(uv1, featc_2d, featc_3d, nn1), "sitec")
+        if cfgs.fuse_fnet:
+            feat1_2d, feat1_3d = self.clfm_fnet.forward_rows(uv1, feat1_2d, feat1_3d, nn1, par)
+            feat2_2d, feat2_3d = site_2.join()
+        if cfgs.fuse_cnet:
+            featc_2d, featc_3d = site_c.join()
 
         def init_2d():
-            h, x = torch.split(tc.conv2d(featc_2d, b2.cnet_aligner), [128, 128], dim=1)
             b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
+            conv = b2.cnet_aligner
+            if tc.fused(featc_2d):
+                # tanh / ReLU of the two halves in the epilogues of two 128-column launches (a strided elementwise kernel on a
+                # channel slice of the 256-channel output costs more than the convolution itself)
+                w_hi, w_lo, bias = ops.tc_weight([conv.weight, conv.bias], lambda: (conv.weight.flatten(1), conv.bias))
+                rows = ops.nhwc_rows(featc_2d)
+                h = ops.conv_gemm(rows, w_hi[:128], w_lo[:128], 1, 1, bias[:128], "tanh")
+                x = ops.conv_gemm(rows, w_hi[128:], w_lo[128:], 1, 1, bias[128:], "relu")
+                return ops.nchw_view(h), ops.nchw_view(x)
+            h, x = torch.split(tc.conv2d(featc_2d, conv), [128, 128], dim=1)
             return torch.tanh(h), torch.relu(x)
 
         def init_3d():
             hx = tc.linear(featc_3d, b3.cnet_aligner.weight, b3.cnet_aligner.bias)
             b3.correlation.build_cost_volume_pyramid(ops.cf_of(feat1_3d), ops.cf_of(feat2_3d), xyzs2)
-            return torch.tanh(hx[..., :128]), torch.relu(hx[..., 128:]), k_nearest_neighbor(xyz1, xyz1, k=32)
+            return torch.tanh(hx[..., :128]), torch.relu(hx[..., 128:])
 
-        (h_2d, x_2d), (h_3d, x_3d, nbr) = par.run(init_2d, init_3d)
+        (h_2d, x_2d), (h_3d, x_3d) = par.run(init_2d, init_3d)
 
         n_iters = cfgs.n_iters_train if self.training else cfgs.n_iters_eval
         every = self.training if self.all_predictions is None else self.all_predictions

@@ -270,6 +270,14 @@ ACT_CODES = {None: 0, "none": 0, "relu": 1, "leaky_relu": 2, "tanh": 3, "sigmoid
 _TC_WEIGHTS = {}
 
 
+def _publish_cached_weight():
+    """A cached weight is prepared by kernels on whichever stream first needs the layer, and later launches on OTHER streams
+    (the forked fusion sites share one CLFM module) find it in the cache without any ordering against those kernels: finish
+    them before the entry becomes visible.  Once per weight; never inside a stream capture (engines warm up eagerly first)."""
+    if torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.current_stream().synchronize()
+
+
 def tc_weight(key_params, builder):
     """(w_hi, w_lo, bias) of a layer for conv_gemm: `builder()` returns the effective (weight [N, taps*Cin] in
     OHWI order, bias [N] or None) -- e.g. with an eval BatchNorm folded in -- which is split into its tf32
@@ -286,6 +294,7 @@ def tc_weight(key_params, builder):
             with torch.cuda.device(w2d.device):
                 native.call("camli_split_tf32", ptr(w2d), ptr(hi), ptr(lo), i64(w2d.numel()), stream())
             slot = (key, weakref.ref(live[0]), hi, lo, None if bias is None else bias.float().contiguous())
+            _publish_cached_weight()
         _TC_WEIGHTS[key[0][0]] = slot
     return slot[2], slot[3], slot[4]
 

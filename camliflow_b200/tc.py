@@ -142,6 +142,7 @@ def _plain_weight(key_params, builder):
         with torch.no_grad():
             w2d, bias = builder()
             slot = (key, weakref.ref(live[0]), w2d.float().contiguous(), None if bias is None else bias.float().contiguous())
+            ops._publish_cached_weight()
         _PLAIN[key[0][0]] = slot
     return slot[2], slot[3]
 
