@@ -102,7 +102,6 @@ class CamLiRAFT_Core(nn.Module):
             featc_2d, featc_3d = site_c.join()
 
         def init_2d():
-            b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
             conv = b2.cnet_aligner
             if tc.fused(featc_2d):
                 # tanh / ReLU of the two halves in the epilogues of two 128-column launches (a strided elementwise kernel on a
@@ -111,8 +110,11 @@ class CamLiRAFT_Core(nn.Module):
                 rows = ops.nhwc_rows(featc_2d)
                 h = ops.conv_gemm(rows, w_hi[:128], w_lo[:128], 1, 1, bias[:128], "tanh")
                 x = ops.conv_gemm(rows, w_hi[128:], w_lo[128:], 1, 1, bias[128:], "relu")
+                # (the volume build last: its persistent all-pairs GEMM holds every SM for ~190 us)
+                b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
                 return ops.nchw_view(h), ops.nchw_view(x)
             h, x = torch.split(tc.conv2d(featc_2d, conv), [128, 128], dim=1)
+            b2.correlation.build_cost_volume_pyramid(feat1_2d, feat2_2d)
             return torch.tanh(h), torch.relu(x)
 
         def init_3d():
