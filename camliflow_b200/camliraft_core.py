@@ -217,7 +217,7 @@ class _TwoStreams:
             dev = torch.cuda.current_device()
             if dev not in _TwoStreams._side:
                 # the point branch is a chain of short kernels: give its CTAs precedence whenever SMs free up
-                _TwoStreams._side[dev] = torch.cuda.Stream(dev, priority=-1)
+                _TwoStreams._side[dev] = torch.cuda.Stream(dev, priority=int(os.environ.get("CAMLI_SIDE_PRIORITY", "-1")))
             self.side = _TwoStreams._side[dev]
 
     def fork(self, fn, key="aux"):
